@@ -1,0 +1,221 @@
+/*
+ * ngsb200.h -- C ABI of libngsb200: NGSolve's assembled-system solve hot path on B200.
+ *
+ * This is the drop-in boundary.  Every entry point replaces one piece of the
+ * reference's device layer (ngscuda/) or of the ngla interface that layer plugs
+ * into; the reference location is cited next to each declaration (paths relative
+ * to the NGSolve source tree).  The NGSolve-side adapter that binds these calls
+ * (BaseVector/BaseMatrix subclasses registered through
+ * BaseMatrix::RegisterDeviceMatrixCreator / BaseVector::RegisterDeviceVectorCreator,
+ * linalg/basematrix.hpp:209-215, linalg/basevector.hpp:321-327) is shown in
+ * INTEGRATION.md.
+ *
+ * Conventions
+ *  - plain C: opaque handles, pointers and sizes only; no C++/torch types.
+ *  - every call returns an int status (NGSB_OK = 0); ngsb_last_error() gives the
+ *    message of the last failing call on the calling thread.  The reference
+ *    throws ngstd::Exception instead (e.g. size mismatch, linalg/basevector.cpp:151);
+ *    the adapter turns a non-zero status into that exception.
+ *  - scalars are passed as double[2] = (re, im); im is ignored for real objects.
+ *  - "kind": NGSB_REAL (double), NGSB_COMPLEX (std::complex<double>, interleaved),
+ *    NGSB_BLOCK3 (Mat<3,3,double> entries / Vec<3,double> vector entries, row-major).
+ *  - host pointers are borrowed for the duration of the call only; handles own
+ *    their device memory (same as DevSparseMatrix, ngscuda/cuda_linalg.cpp:187-231).
+ *  - all work of a context is enqueued on that context's stream; calls that
+ *    return a value to the host synchronise that stream, all others are async.
+ *  - there is no CPU fallback: without a CUDA device ngsb_ctx_create fails.
+ */
+#ifndef NGSB200_H
+#define NGSB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NGSB_OK 0
+#define NGSB_ERR_INVALID 1   /* bad argument / size mismatch */
+#define NGSB_ERR_CUDA 2      /* CUDA runtime error          */
+#define NGSB_ERR_NOMEM 3
+#define NGSB_ERR_UNSUPPORTED 4
+#define NGSB_ERR_COMM 5      /* NCCL error */
+
+#define NGSB_REAL 0
+#define NGSB_COMPLEX 1
+#define NGSB_BLOCK3 3
+
+/* inner-product flavours of CGSolver<IPTYPE>, linalg/basevector.hpp:1099-1124 */
+#define NGSB_IP_REAL 0
+#define NGSB_IP_COMPLEX 1          /* bilinear  sum x_i y_i        */
+#define NGSB_IP_COMPLEX_CONJ 2     /* sum x_i conj(y_i)            */
+
+typedef struct ngsb_ctx ngsb_ctx;
+typedef struct ngsb_vec ngsb_vec;
+typedef struct ngsb_scalar ngsb_scalar;
+typedef struct ngsb_csr ngsb_csr;
+typedef struct ngsb_jacobi ngsb_jacobi;
+typedef struct ngsb_comm ngsb_comm;
+typedef struct ngsb_parmat ngsb_parmat;
+
+const char *ngsb_last_error(void);
+const char *ngsb_version(void);
+
+/* ---- context: replaces InitCUDA + InitCuLinalg + the global ngs_cuda_stream ------------
+ * ngscuda/cuda_ngstd.cpp:84-108 (device choice by NGS_CUDA_DEVICE_INDEX, stream),
+ * ngscuda/cuda_linalg.cpp:70-171 (handles + creator registration).  device < 0 reads
+ * NGS_CUDA_DEVICE_INDEX like the reference (default 0). */
+int ngsb_ctx_create(int device, ngsb_ctx **out);
+int ngsb_ctx_destroy(ngsb_ctx *ctx);
+int ngsb_ctx_sync(ngsb_ctx *ctx);                       /* SyncNGSStream, ngscuda/cuda_core.hpp */
+int ngsb_ctx_device(const ngsb_ctx *ctx, int *device, int *sm_count);
+void *ngsb_ctx_stream(ngsb_ctx *ctx);                   /* cudaStream_t */
+/* kernels of this library launched on ctx so far (bench.py's gpu_launches) */
+int ngsb_ctx_launch_count(const ngsb_ctx *ctx, uint64_t *count);
+/* tuning knobs: name in {"spmv_algo" (0 auto,1 subwarp,2 tma-stream), "cg_batch",
+ * "spmv_ctas_per_sm", "timing"}; unknown names fail with NGSB_ERR_INVALID. */
+int ngsb_ctx_set_option(ngsb_ctx *ctx, const char *name, long value);
+/* device time in ms of the kernels recorded since the last reset for a class
+ * ("spmv", "cgupdate", "all"); only meaningful when option "timing" is 1. */
+int ngsb_ctx_kernel_time(ngsb_ctx *ctx, const char *klass, double *ms, uint64_t *launches);
+int ngsb_ctx_kernel_time_reset(ngsb_ctx *ctx);
+
+/* ---- vectors: replaces UnifiedVector (ngscuda/unifiedvector.hpp:8-98, .cpp:7-345) ---------
+ * n_entries entries of `kind`; NGSB_BLOCK3 entries are Vec<3,double> (the reference's
+ * UnifiedVector cannot hold these, ngscuda/unifiedvector.cpp:22-26). */
+int ngsb_vec_create(ngsb_ctx *ctx, size_t n_entries, int kind, ngsb_vec **out);
+int ngsb_vec_destroy(ngsb_vec *v);
+int ngsb_vec_info(const ngsb_vec *v, size_t *n_entries, int *kind, size_t *n_scalars);
+void *ngsb_vec_devptr(ngsb_vec *v);                      /* DevData(), unifiedvector.hpp:73 */
+/* aliasing view of entries [begin,end): UnifiedVector::Range, unifiedvector.cpp:130-133.
+ * The view keeps the parent's storage alive. */
+int ngsb_vec_range(ngsb_vec *v, size_t begin, size_t end, ngsb_vec **view);
+/* host<->device copies of whole entries: UpdateDevice/UpdateHost, unifiedvector.cpp:288-330.
+ * d2h synchronises; h2d is stream-ordered and returns after the copy was issued from a
+ * staging copy (the host buffer may be reused immediately). */
+int ngsb_vec_h2d(ngsb_vec *v, const void *host, size_t first_entry, size_t n_entries);
+int ngsb_vec_d2h(const ngsb_vec *v, void *host, size_t first_entry, size_t n_entries);
+/* BaseVector::SetScalar / Scale / Set / Add: linalg/basevector.cpp:113-138, 75-111,
+ * 146-199, 203-257; device versions ngscuda/unifiedvector.cpp:136-213. */
+int ngsb_vec_set_scalar(ngsb_vec *x, const double s[2]);
+int ngsb_vec_scale(ngsb_vec *x, const double s[2]);
+int ngsb_vec_set(ngsb_vec *y, const double s[2], const ngsb_vec *x);      /* y  = s*x */
+int ngsb_vec_axpy(ngsb_vec *y, const double s[2], const ngsb_vec *x);     /* y += s*x */
+/* S_BaseVector<SCAL>::InnerProduct: linalg/basevector.cpp:1108-1159 (conjugate acts on
+ * the argument y); device version ngscuda/unifiedvector.cpp:215-237 (cublasDdot). */
+int ngsb_vec_dot(const ngsb_vec *x, const ngsb_vec *y, int conjugate, double out[2]);
+/* BaseVector::L2Norm: linalg/basevector.cpp:41-73; ngscuda/unifiedvector.cpp:239-247. */
+int ngsb_vec_nrm2(const ngsb_vec *x, double *out);
+
+/* ---- device-resident scalars: replaces UnifiedScalar (ngscuda/unifiedvector.hpp:107-136)
+ * and the BaseScalar hooks linalg/basevector.cpp:259-298, linalg/basescalar.hpp:17-29. */
+int ngsb_scalar_create(ngsb_ctx *ctx, ngsb_scalar **out);
+int ngsb_scalar_destroy(ngsb_scalar *s);
+int ngsb_scalar_set(ngsb_scalar *s, const double v[2]);
+int ngsb_scalar_get(const ngsb_scalar *s, double v[2]);                   /* synchronises */
+/* out = a / b, out = -a, out = a   (the Div/Neg/Scal expression kernels,
+ * ngscuda/unifiedvector.hpp:126-135, ngscuda/cuda_krylov.cpp:88-95) */
+int ngsb_scalar_div(ngsb_scalar *out, const ngsb_scalar *a, const ngsb_scalar *b);
+int ngsb_scalar_neg(ngsb_scalar *out, const ngsb_scalar *a);
+int ngsb_scalar_copy(ngsb_scalar *out, const ngsb_scalar *a);
+int ngsb_vec_dot_dev(const ngsb_vec *x, const ngsb_vec *y, int conjugate, ngsb_scalar *out);
+int ngsb_vec_axpy_dev(ngsb_vec *y, const ngsb_scalar *s, const ngsb_vec *x);
+int ngsb_vec_scale_dev(ngsb_vec *x, const ngsb_scalar *s);
+
+/* ---- CSR matrices: replaces DevSparseMatrix (ngscuda/cuda_linalg.hpp:50-72,
+ * ngscuda/cuda_linalg.cpp:187-316) for SparseMatrix<double>, SparseMatrix<Complex> and
+ * SparseMatrix<Mat<3,3,double>> (linalg/sparsematrix.hpp:65-167, 340-542).
+ * rowptr/col/val are exactly what SparseMatrix::CSR() returns
+ * (linalg/python_linalg.cpp:121-138): uint64 row pointers (h+1), int32 columns sorted
+ * ascending per row, values of `kind` (9 doubles row-major per entry for NGSB_BLOCK3). */
+int ngsb_csr_create(ngsb_ctx *ctx, size_t height, size_t width, size_t nnz,
+                    const uint64_t *rowptr, const int32_t *col, const void *val, int kind,
+                    ngsb_csr **out);
+/* same, adopting DEVICE arrays (copied device-to-device); for systems assembled on
+ * the device.  rowptr is uint64 on the device as well. */
+int ngsb_csr_create_from_device(ngsb_ctx *ctx, size_t height, size_t width, size_t nnz,
+                                const uint64_t *d_rowptr, const int32_t *d_col, const void *d_val,
+                                int kind, ngsb_csr **out);
+int ngsb_csr_destroy(ngsb_csr *A);
+int ngsb_csr_info(const ngsb_csr *A, size_t *height, size_t *width, size_t *nnz, int *kind);
+/* SparseMatrix::MultAdd(double|Complex s, x, y): linalg/sparsematrix_impl.hpp:264-279,
+ * 378-396;  DevSparseMatrix::MultAdd ngscuda/cuda_linalg.cpp:244-276.   y += s*A*x */
+int ngsb_csr_multadd(const ngsb_csr *A, const double s[2], const ngsb_vec *x, ngsb_vec *y);
+/* BaseMatrix::Mult (= SetZero + MultAdd(1)), linalg/basematrix.cpp:120-127.   y = A*x */
+int ngsb_csr_mult(const ngsb_csr *A, const ngsb_vec *x, ngsb_vec *y);
+/* SparseMatrix::Reorder(perm): linalg/sparsematrix_impl.hpp:762-783.
+ * new(i, inv[c]) = old(perm[i], c); perm is a host array of `height` indices. */
+int ngsb_csr_reorder(const ngsb_csr *A, const uint64_t *perm, ngsb_csr **out);
+/* copy the device CSR back (pattern parity checks): any pointer may be NULL */
+int ngsb_csr_download(const ngsb_csr *A, uint64_t *rowptr, int32_t *col, void *val);
+/* algorithmic bytes of one Mult: nnz*(b*b*S+4) + 4*h + 2*N*S */
+int ngsb_csr_mult_bytes(const ngsb_csr *A, double *bytes);
+
+/* ---- Jacobi: replaces DevDiagonalMatrix built from JacobiPrecond<TM>::invdiag
+ * (ngscuda/cuda_linalg.cpp:103-115, 321-366; linalg/jacobi.cpp:39-155).
+ * invdiag: n entries of `kind` (9 doubles per entry for NGSB_BLOCK3); freebits: the
+ * `inner` BitArray bytes (bit i -> byte i/8, bit i%8), or NULL. */
+int ngsb_jacobi_create(ngsb_ctx *ctx, size_t n, const void *invdiag, int kind,
+                       const uint8_t *freebits, ngsb_jacobi **out);
+/* JacobiPrecond ctor on the device matrix (mat.CreateSmoother(freedofs),
+ * linalg/python_linalg.cpp:1220-1236; linalg/jacobi.cpp:39-68). */
+int ngsb_jacobi_create_from_csr(const ngsb_csr *A, const uint8_t *freebits, ngsb_jacobi **out);
+int ngsb_jacobi_destroy(ngsb_jacobi *J);
+int ngsb_jacobi_download(const ngsb_jacobi *J, void *invdiag);
+int ngsb_jacobi_multadd(const ngsb_jacobi *J, const double s[2], const ngsb_vec *x, ngsb_vec *y);
+int ngsb_jacobi_mult(const ngsb_jacobi *J, const ngsb_vec *x, ngsb_vec *y);
+
+/* ---- Krylov solvers ----------------------------------------------------------------------
+ * ngsb_cg_solve: CGSolver<IPTYPE>::Mult, linalg/cg.cpp:503-633 (same recurrences, same
+ * stopping rule `n++ < maxsteps && Abs(wdn) > prec^2*Abs(wdn0)`, *steps = GetSteps()),
+ * replacing DevCGSolver::Mult (ngscuda/cuda_krylov.cpp:19-203).  The loop runs on the
+ * device: fused kernels, device-resident scalars and a device-side stop flag.
+ * C may be NULL (w = d).  history (host, may be NULL) receives Abs(wdn) of the initial
+ * residual and of every iteration, at most hist_cap values; *nhist = how many exist. */
+int ngsb_cg_solve(const ngsb_csr *A, const ngsb_jacobi *C, const ngsb_vec *f, ngsb_vec *u,
+                  double prec, int maxsteps, int ip_mode, int initialize,
+                  int *steps, double *history, int hist_cap, int *nhist);
+/* the same solve with HOST right-hand side / solution buffers (the call a script makes
+ * through `gfu.vec.data = inv * f.vec`): copies f in, solves, copies u out, synchronises. */
+int ngsb_cg_solve_host(const ngsb_csr *A, const ngsb_jacobi *C, const void *f_host, void *u_host,
+                       double prec, int maxsteps, int ip_mode,
+                       int *steps, double *history, int hist_cap, int *nhist);
+/* GMRESSolver<IPTYPE>::Mult, linalg/cg.cpp:854-1022 (left-preconditioned, MGS, Givens,
+ * no restart).  *steps = GetSteps(). */
+int ngsb_gmres_solve(const ngsb_csr *A, const ngsb_jacobi *C, const ngsb_vec *f, ngsb_vec *x,
+                     double prec, int maxsteps, int initialize,
+                     int *steps, double *history, int hist_cap, int *nhist);
+
+/* ---- distributed: ParallelDofs / ParallelMatrix / Cumulate on one GPU per process -------
+ * linalg/paralleldofs.cpp:20-108, parallel/parallelvvector.cpp:247-331,
+ * parallel/parallel_matrices.cpp:519-536.  uid is an ncclUniqueId (128 bytes) created by
+ * rank 0 with ngsb_comm_unique_id and distributed by the caller (torch.distributed). */
+int ngsb_comm_unique_id(void *uid128);
+int ngsb_comm_create(ngsb_ctx *ctx, int nranks, int rank, const void *uid128, ngsb_comm **out);
+int ngsb_comm_destroy(ngsb_comm *comm);
+/* local matrix + exchange tables: exchangedofs as a CSR table over ranks
+ * (ex_first[nranks+1], ex_dofs ascending local dofs), exactly ParallelDofs::exchangedofs. */
+int ngsb_parmat_create(ngsb_comm *comm, const ngsb_csr *local, const uint64_t *ex_first,
+                       const int32_t *ex_dofs, ngsb_parmat **out);
+int ngsb_parmat_destroy(ngsb_parmat *P);
+/* masterdofs bytes as the reference derives them (lowest rank owns), n entries */
+int ngsb_parmat_masterdofs(const ngsb_parmat *P, uint8_t *ismaster);
+/* ParallelBaseVector::Cumulate on a DISTRIBUTED vector: neighbour exchange + add */
+int ngsb_parmat_cumulate(const ngsb_parmat *P, ngsb_vec *v);
+/* ParallelMatrix::MultAdd (C2D): x cumulated in, y distributed out */
+int ngsb_parmat_mult(const ngsb_parmat *P, const ngsb_vec *x, ngsb_vec *y);
+/* global inner product of a CUMULATED and a DISTRIBUTED vector (local dot + AllReduce),
+ * or of two CUMULATED vectors (masked by master dofs), parallelvvector.cpp:289-331 */
+int ngsb_parmat_dot(const ngsb_parmat *P, const ngsb_vec *x, const ngsb_vec *y, int both_cumulated,
+                    double *out);
+/* distributed Jacobi-PCG: f DISTRIBUTED in, u CUMULATED out; C holds the cumulated
+ * inverse diagonal (linalg/jacobi.cpp:60-61). */
+int ngsb_parmat_cg_solve(const ngsb_parmat *P, const ngsb_jacobi *C, const ngsb_vec *f, ngsb_vec *u,
+                         double prec, int maxsteps, int *steps, double *history, int hist_cap,
+                         int *nhist);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NGSB200_H */

@@ -1,0 +1,123 @@
+// common.cuh -- shared definitions of libngsb200 (internal, not part of the C ABI)
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <stdlib.h>
+#include <string>
+#include <vector>
+#include <memory>
+
+#include "../../include/ngsb200.h"
+
+namespace ngsb {
+
+void set_error(const char *fmt, ...);
+
+#define NGSB_CUDA(call)                                                                        \
+    do {                                                                                       \
+        cudaError_t e__ = (call);                                                              \
+        if (e__ != cudaSuccess) {                                                              \
+            ngsb::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, \
+                            __LINE__);                                                         \
+            return NGSB_ERR_CUDA;                                                              \
+        }                                                                                      \
+    } while (0)
+
+#define NGSB_REQUIRE(cond, ...)            \
+    do {                                   \
+        if (!(cond)) {                     \
+            ngsb::set_error(__VA_ARGS__);  \
+            return NGSB_ERR_INVALID;       \
+        }                                  \
+    } while (0)
+
+#define NGSB_TRY(call)                 \
+    do {                               \
+        int rc__ = (call);             \
+        if (rc__ != NGSB_OK) return rc__; \
+    } while (0)
+
+// kernel classes for the optional per-class device timing (option "timing")
+enum KClass { KC_SPMV = 0, KC_CGUPDATE = 1, KC_VEC = 2, KC_OTHER = 3, KC_COUNT = 4 };
+
+struct TimedSpan {
+    cudaEvent_t a, b;
+    int klass;
+};
+
+} // namespace ngsb
+
+// device-resident scalar block used by the solvers (all (re,im) pairs)
+struct ngsb_scalar {
+    ngsb_ctx *ctx;
+    double *d;      // 2 doubles on the device
+};
+
+struct ngsb_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    uint64_t launches = 0;
+    // options
+    long spmv_algo = 0;          // 0 auto, 1 subwarp, 2 tma-stream
+    long cg_batch = 16;          // iterations enqueued between two polls of the stop flag
+    long spmv_ctas_per_sm = 0;   // 0 = kernel default
+    long timing = 0;
+    // reduction workspace (partials + counters), pinned host scratch
+    double *d_partials = nullptr;   // 2 * max_partials doubles
+    unsigned int *d_counter = nullptr;
+    double *h_pinned = nullptr;     // small pinned scratch (>= 4096 doubles)
+    void *h_stage = nullptr;        // pinned staging for h2d/d2h
+    size_t h_stage_bytes = 0;
+    cudaEvent_t stage_free = nullptr;
+    std::vector<ngsb::TimedSpan> spans;
+    std::vector<cudaEvent_t> event_pool;
+    // solver workspace cache (krylov.cu), released by ngsb_ctx_destroy
+    void *ws = nullptr;
+    void (*ws_free)(void *) = nullptr;
+};
+
+struct ngsb_vec {
+    ngsb_ctx *ctx;
+    size_t n;            // entries
+    int kind;
+    size_t nscal;        // doubles
+    double *d;           // device pointer (may alias parent storage)
+    std::shared_ptr<void> storage;   // owner of the allocation
+};
+
+namespace ngsb {
+
+inline size_t kind_scalars(int kind) { return kind == NGSB_REAL ? 1 : (kind == NGSB_COMPLEX ? 2 : 3); }
+inline size_t kind_matscalars(int kind) { return kind == NGSB_REAL ? 1 : (kind == NGSB_COMPLEX ? 2 : 9); }
+inline bool kind_valid(int kind) { return kind == NGSB_REAL || kind == NGSB_COMPLEX || kind == NGSB_BLOCK3; }
+
+static const int MAX_PARTIALS = 4096;
+
+// RAII-less helper: record a timed span around a launch when ctx->timing is on
+struct SpanGuard {
+    ngsb_ctx *ctx;
+    int idx;
+    SpanGuard(ngsb_ctx *c, int klass);
+    ~SpanGuard();
+};
+
+int stage_reserve(ngsb_ctx *ctx, size_t bytes);
+
+// ---- vector kernels (vec.cu), all enqueue on ctx->stream --------------------------------
+int launch_fill(ngsb_ctx *ctx, double *x, size_t N, double re, double im, bool cplx);
+// y = a*x (+ y if accumulate); complex if cplx (N complex entries), scalars from host
+int launch_axpby(ngsb_ctx *ctx, double *y, const double *x, size_t N, double sr, double si, bool cplx,
+                 bool accumulate);
+// scalar taken from device memory (2 doubles); neg => use -s
+int launch_axpby_dev(ngsb_ctx *ctx, double *y, const double *x, size_t N, const double *ds, bool cplx,
+                     bool accumulate, bool neg);
+int launch_scale_dev(ngsb_ctx *ctx, double *x, size_t N, const double *ds, bool cplx);
+// deterministic dot: out (device, 2 doubles) = sum x_i * (conj? conj(y_i) : y_i)
+// mode: 0 real, 1 complex bilinear, 2 complex conj(y), 3 real sum of squares of x (norm^2)
+int launch_dot(ngsb_ctx *ctx, const double *x, const double *y, size_t N, int mode, double *d_out);
+
+} // namespace ngsb

@@ -1,0 +1,866 @@
+// krylov.cu -- device-resident CG and GMRES.
+//
+// CG: CGSolver<IPTYPE>::Mult (linalg/cg.cpp:503-633) with the same recurrences and stopping
+// rule, replacing DevCGSolver::Mult (ngscuda/cuda_krylov.cpp:19-203: 12 unfused graph nodes
+// per iteration).  One iteration here is three kernels:
+//   A  spmv (+ fused kss = <s, A s>, last block: al = wd/kss)                 [spmv.cu]
+//   B  u += al s ; d -= al as ; w = C d ; wdn = <d, w> ; last block: be, loop condition
+//   C  s = be s + w
+// All scalars and the loop counter live in a CgState on the device; every kernel returns
+// at once when state->done is set, so the host enqueues iterations in batches (optionally
+// as one CUDA graph per batch) and only polls the flag between batches.
+//
+// GMRES: GMRESSolver<IPTYPE>::Mult (linalg/cg.cpp:854-1022): left preconditioning, modified
+// Gram-Schmidt in the reference's order (each projection fused with the next inner product),
+// Givens rotations and the triangular solve in single-thread kernels on the device.
+#include "jacobi.cuh"
+
+#include <map>
+
+namespace ngsb {
+
+// ------------------------------------------------------------------------------------------
+// workspace cache
+// ------------------------------------------------------------------------------------------
+struct Workspace {
+    std::vector<std::pair<size_t, double *>> free_bufs;
+    CgState *d_state = nullptr;
+    CgState *h_state = nullptr;       // pinned
+    double *d_hist = nullptr;
+    size_t hist_cap = 0;
+    cudaGraphExec_t graph_exec = nullptr;
+    // key of the cached graph
+    const void *g_A = nullptr, *g_C = nullptr;
+    double *g_ptrs[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    long g_batch = 0;
+    int g_ip = -1;
+    long g_algo = -1, g_cps = -1;
+};
+
+static void ws_free(void *p)
+{
+    Workspace *ws = (Workspace *)p;
+    for (auto &b : ws->free_bufs) cudaFree(b.second);
+    if (ws->d_state) cudaFree(ws->d_state);
+    if (ws->h_state) cudaFreeHost(ws->h_state);
+    if (ws->d_hist) cudaFree(ws->d_hist);
+    if (ws->graph_exec) cudaGraphExecDestroy(ws->graph_exec);
+    delete ws;
+}
+
+static Workspace *get_ws(ngsb_ctx *ctx)
+{
+    if (!ctx->ws) {
+        ctx->ws = new Workspace();
+        ctx->ws_free = ws_free;
+    }
+    return (Workspace *)ctx->ws;
+}
+
+static int ws_get_buf(ngsb_ctx *ctx, size_t nscal, double **out)
+{
+    Workspace *ws = get_ws(ctx);
+    for (size_t i = 0; i < ws->free_bufs.size(); i++)
+        if (ws->free_bufs[i].first == nscal) {
+            *out = ws->free_bufs[i].second;
+            ws->free_bufs.erase(ws->free_bufs.begin() + i);
+            return NGSB_OK;
+        }
+    void *p = nullptr;
+    size_t bytes = nscal * sizeof(double);
+    cudaError_t e = cudaMalloc(&p, bytes ? bytes : 16);
+    if (e != cudaSuccess) {
+        // out of memory: release every cached buffer and retry once
+        cudaGetLastError();
+        cudaStreamSynchronize(ctx->stream);
+        for (auto &b : ws->free_bufs) cudaFree(b.second);
+        ws->free_bufs.clear();
+        e = cudaMalloc(&p, bytes ? bytes : 16);
+    }
+    if (e != cudaSuccess) { set_error("solver workspace: cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); return NGSB_ERR_NOMEM; }
+    *out = (double *)p;
+    return NGSB_OK;
+}
+
+static void ws_put_buf(ngsb_ctx *ctx, size_t nscal, double *p)
+{
+    if (p) get_ws(ctx)->free_bufs.emplace_back(nscal, p);
+}
+
+static int ws_state(ngsb_ctx *ctx, size_t hist_cap)
+{
+    Workspace *ws = get_ws(ctx);
+    if (!ws->d_state) {
+        NGSB_CUDA(cudaMalloc(&ws->d_state, sizeof(CgState)));
+        NGSB_CUDA(cudaMallocHost(&ws->h_state, 4 * sizeof(CgState)));
+    }
+    if (ws->hist_cap < hist_cap + 1) {
+        if (ws->d_hist) { cudaStreamSynchronize(ctx->stream); cudaFree(ws->d_hist); }
+        NGSB_CUDA(cudaMalloc(&ws->d_hist, (hist_cap + 1) * sizeof(double)));
+        ws->hist_cap = hist_cap + 1;
+        if (ws->graph_exec) { cudaGraphExecDestroy(ws->graph_exec); ws->graph_exec = nullptr; }
+    }
+    return NGSB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// fused CG kernels
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool bit_test_k(const uint8_t *bits, uint64_t i) { return (bits[i >> 3] >> (i & 7)) & 1; }
+
+__device__ __forceinline__ double warp_sum_k(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+struct CgVecs {
+    double *u, *d, *w, *s;
+    const double *as, *f;
+    const double *invdiag;     // NULL: no preconditioner (w aliases d, never stored)
+    const uint8_t *bits;
+    uint64_t n;                // entries
+    CgState *state;
+    double *hist;
+    double *partials;
+    unsigned int *counter;
+    int ip_mode;
+};
+
+// grid-wide deterministic reduction finish; returns true on thread 0 of the last block
+__device__ __forceinline__ bool grid_finish(double a, double b, double *partials, unsigned int *counter, double2 *total)
+{
+    __shared__ double red[64];
+    __shared__ int s_last;
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    a = warp_sum_k(a);
+    b = warp_sum_k(b);
+    if (lane == 0) { red[wid] = a; red[32 + wid] = b; }
+    __syncthreads();
+    if (wid == 0) {
+        int nw = (blockDim.x + 31) >> 5;
+        a = lane < nw ? red[lane] : 0.0;
+        b = lane < nw ? red[32 + lane] : 0.0;
+        a = warp_sum_k(a);
+        b = warp_sum_k(b);
+        if (lane == 0) {
+            partials[2 * blockIdx.x] = a;
+            partials[2 * blockIdx.x + 1] = b;
+            __threadfence();
+            unsigned int t = atomicAdd(counter, 1u);
+            s_last = (t == gridDim.x - 1);
+        }
+    }
+    __syncthreads();
+    if (!s_last || threadIdx.x >= 32) return false;
+    __threadfence();
+    a = 0.0;
+    b = 0.0;
+    for (unsigned int k = threadIdx.x; k < gridDim.x; k += 32) {
+        a += __ldcg(&partials[2 * k]);
+        b += __ldcg(&partials[2 * k + 1]);
+    }
+    a = warp_sum_k(a);
+    b = warp_sum_k(b);
+    if (threadIdx.x == 0) {
+        *counter = 0;
+        *total = make_double2(a, b);
+        return true;
+    }
+    return false;
+}
+
+// w = C*d for one entry (masked Jacobi) -- returns w, or d when there is no preconditioner
+template <int KIND>
+__device__ __forceinline__ void prec_entry(const CgVecs &v, uint64_t i, const double *dn, double *wn)
+{
+    if (v.invdiag == nullptr) {
+        wn[0] = dn[0];
+        if (KIND != NGSB_REAL) wn[1] = dn[1];
+        if (KIND == NGSB_BLOCK3) wn[2] = dn[2];
+        return;
+    }
+    const bool in = v.bits == nullptr || bit_test_k(v.bits, i);
+    if (KIND == NGSB_REAL) {
+        wn[0] = in ? v.invdiag[i] * dn[0] : 0.0;
+    } else if (KIND == NGSB_COMPLEX) {
+        if (in) {
+            double2 m = reinterpret_cast<const double2 *>(v.invdiag)[i];
+            wn[0] = m.x * dn[0] - m.y * dn[1];
+            wn[1] = m.x * dn[1] + m.y * dn[0];
+        } else { wn[0] = 0.0; wn[1] = 0.0; }
+    } else {
+        if (in) {
+            const double *m = v.invdiag + 9 * i;
+            wn[0] = m[0] * dn[0] + m[1] * dn[1] + m[2] * dn[2];
+            wn[1] = m[3] * dn[0] + m[4] * dn[1] + m[5] * dn[2];
+            wn[2] = m[6] * dn[0] + m[7] * dn[1] + m[8] * dn[2];
+        } else { wn[0] = 0.0; wn[1] = 0.0; wn[2] = 0.0; }
+    }
+}
+
+// MODE 0: init      d = f (or f - as when !initialize, flag in `sub`), w = C d, s = w, <w,d>
+// MODE 1: update    u += al s, d -= al as, w = C d, <d,w>
+template <int KIND, int MODE>
+__global__ void __launch_bounds__(256) cg_fused_kernel(const CgVecs v, int sub)
+{
+    constexpr int ES = KIND == NGSB_REAL ? 1 : (KIND == NGSB_COMPLEX ? 2 : 3);
+    CgState *st = v.state;
+    if (MODE == 1 && st->done) return;
+    const double alr = MODE == 1 ? st->al[0] : 0.0;
+    const double ali = MODE == 1 ? st->al[1] : 0.0;
+    const bool conj = v.ip_mode == NGSB_IP_COMPLEX_CONJ;
+    // contiguous chunk per block (fixed -> deterministic)
+    uint64_t per = (v.n + gridDim.x - 1) / gridDim.x;
+    uint64_t lo = (uint64_t)blockIdx.x * per;
+    uint64_t hi = lo + per < v.n ? lo + per : v.n;
+    double accr = 0.0, acci = 0.0;
+    for (uint64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        double dn[3], wn[3];
+        if (MODE == 0) {
+#pragma unroll
+            for (int c = 0; c < ES; c++) {
+                dn[c] = v.f[ES * i + c];
+                if (sub) dn[c] -= v.as[ES * i + c];
+            }
+        } else {
+            if (KIND == NGSB_COMPLEX) {
+                double sr = v.s[2 * i], si = v.s[2 * i + 1];
+                double ar = v.as[2 * i], ai = v.as[2 * i + 1];
+                v.u[2 * i] += alr * sr - ali * si;
+                v.u[2 * i + 1] += alr * si + ali * sr;
+                dn[0] = v.d[2 * i] - (alr * ar - ali * ai);
+                dn[1] = v.d[2 * i + 1] - (alr * ai + ali * ar);
+            } else {
+#pragma unroll
+                for (int c = 0; c < ES; c++) {
+                    v.u[ES * i + c] += alr * v.s[ES * i + c];
+                    dn[c] = v.d[ES * i + c] - alr * v.as[ES * i + c];
+                }
+            }
+        }
+        prec_entry<KIND>(v, i, dn, wn);
+#pragma unroll
+        for (int c = 0; c < ES; c++) {
+            v.d[ES * i + c] = dn[c];
+            if (v.invdiag != nullptr) v.w[ES * i + c] = wn[c];
+            if (MODE == 0) v.s[ES * i + c] = wn[c];
+        }
+        if (KIND == NGSB_COMPLEX) {
+            // init: <w, d> (conj on d) ; update: <d, w> (conj on w)
+            double xr = MODE == 0 ? wn[0] : dn[0], xi = MODE == 0 ? wn[1] : dn[1];
+            double yr = MODE == 0 ? dn[0] : wn[0], yi = MODE == 0 ? dn[1] : wn[1];
+            if (conj) yi = -yi;
+            accr += xr * yr - xi * yi;
+            acci += xr * yi + xi * yr;
+        } else {
+#pragma unroll
+            for (int c = 0; c < ES; c++) accr = fma(dn[c], wn[c], accr);
+        }
+    }
+    double2 total;
+    if (grid_finish(accr, acci, v.partials, v.counter, &total)) {
+        if (MODE == 0) cg_finalize_init(st, total, v.hist);
+        else cg_finalize_wdn(st, total, v.hist);
+    }
+}
+
+// s = be*s + w   (`s *= be; s += w`, linalg/cg.cpp:611-612: two roundings, kept)
+template <bool CPLX>
+__global__ void __launch_bounds__(256) cg_dir_kernel(double *__restrict__ s, const double *__restrict__ w, uint64_t N,
+                                                    const CgState *__restrict__ st)
+{
+    if (st->done) return;
+    const double ber = st->be[0], bei = st->be[1];
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (CPLX) {
+        double2 *s2 = reinterpret_cast<double2 *>(s);
+        const double2 *w2 = reinterpret_cast<const double2 *>(w);
+        for (; i < N; i += stride) {
+            double2 a = s2[i], b = w2[i];
+            double pr = a.x * ber - a.y * bei, pi = a.x * bei + a.y * ber;
+            s2[i] = make_double2(__dadd_rn(pr, b.x), __dadd_rn(pi, b.y));
+        }
+    } else {
+        uint64_t n2 = N / 2;
+        double2 *s2 = reinterpret_cast<double2 *>(s);
+        const double2 *w2 = reinterpret_cast<const double2 *>(w);
+        for (uint64_t k = i; k < n2; k += stride) {
+            double2 a = s2[k], b = w2[k];
+            s2[k] = make_double2(__dadd_rn(__dmul_rn(a.x, ber), b.x), __dadd_rn(__dmul_rn(a.y, ber), b.y));
+        }
+        if (i == 0 && (N & 1)) s[N - 1] = __dadd_rn(__dmul_rn(s[N - 1], ber), w[N - 1]);
+    }
+}
+
+static int reduce_grid(ngsb_ctx *ctx, uint64_t n)
+{
+    uint64_t blocks = (n + 2047) / 2048;
+    uint64_t cap = (uint64_t)ctx->sm_count * 4;
+    if (cap > (uint64_t)MAX_PARTIALS - 8) cap = MAX_PARTIALS - 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+template <int MODE>
+static int launch_cg_fused(ngsb_ctx *ctx, int kind, const CgVecs &v, int sub)
+{
+    SpanGuard g(ctx, KC_CGUPDATE);
+    int grid = reduce_grid(ctx, v.n);
+    if (kind == NGSB_REAL) cg_fused_kernel<NGSB_REAL, MODE><<<grid, 256, 0, ctx->stream>>>(v, sub);
+    else if (kind == NGSB_COMPLEX) cg_fused_kernel<NGSB_COMPLEX, MODE><<<grid, 256, 0, ctx->stream>>>(v, sub);
+    else cg_fused_kernel<NGSB_BLOCK3, MODE><<<grid, 256, 0, ctx->stream>>>(v, sub);
+    NGSB_CUDA(cudaGetLastError());
+    return NGSB_OK;
+}
+
+static int launch_cg_dir(ngsb_ctx *ctx, int kind, const CgVecs &v)
+{
+    SpanGuard g(ctx, KC_CGUPDATE);
+    const bool cplx = kind == NGSB_COMPLEX;
+    uint64_t N = cplx ? v.n : v.n * kind_scalars(kind);
+    uint64_t blocks = (N + 1023) / 1024;
+    uint64_t cap = (uint64_t)ctx->sm_count * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    const double *w = v.invdiag ? v.w : v.d;
+    if (cplx) cg_dir_kernel<true><<<(int)blocks, 256, 0, ctx->stream>>>(v.s, w, N, v.state);
+    else cg_dir_kernel<false><<<(int)blocks, 256, 0, ctx->stream>>>(v.s, w, N, v.state);
+    NGSB_CUDA(cudaGetLastError());
+    return NGSB_OK;
+}
+
+static int enqueue_iteration(ngsb_ctx *ctx, const ngsb_csr *A, const CgVecs &v, double *as)
+{
+    SpmvArgs a;
+    memset(&a, 0, sizeof(a));
+    a.A = A; a.x = v.s; a.y = as; a.sr = 1.0; a.si = 0.0; a.accumulate = false;
+    a.epi = EPI_CG_KSS; a.dotvec = v.s; a.dot_conj = v.ip_mode == NGSB_IP_COMPLEX_CONJ; a.state = v.state;
+    NGSB_TRY(spmv_launch(a));
+    NGSB_TRY(launch_cg_fused<1>(ctx, A->kind, v, 0));
+    NGSB_TRY(launch_cg_dir(ctx, A->kind, v));
+    return NGSB_OK;
+}
+
+int cg_solve_device(const ngsb_csr *A, const ngsb_jacobi *C, const double *f, double *u, double prec, int maxsteps,
+                    int ip_mode, int initialize, int *steps, double *history, int hist_cap, int *nhist)
+{
+    ngsb_ctx *ctx = A->ctx;
+    Workspace *ws = get_ws(ctx);
+    const size_t nscal = A->h * kind_scalars(A->kind);
+    if (hist_cap < 0) hist_cap = 0;
+    if (!history) hist_cap = 0;
+    NGSB_TRY(ws_state(ctx, (size_t)hist_cap));
+    double *w = nullptr, *s = nullptr, *d = nullptr, *as = nullptr;
+    NGSB_TRY(ws_get_buf(ctx, nscal, &s));
+    NGSB_TRY(ws_get_buf(ctx, nscal, &d));
+    NGSB_TRY(ws_get_buf(ctx, nscal, &as));
+    if (C) NGSB_TRY(ws_get_buf(ctx, nscal, &w));
+
+    CgState *hs = ws->h_state;
+    memset(hs, 0, sizeof(CgState));
+    hs->prec2 = prec * prec;
+    hs->maxsteps = maxsteps;
+    hs->hist_cap = hist_cap;
+    hs->cplx = ip_mode != NGSB_IP_REAL;
+    hs->done = 0;
+    NGSB_CUDA(cudaMemcpyAsync(ws->d_state, hs, sizeof(CgState), cudaMemcpyHostToDevice, ctx->stream));
+
+    CgVecs v;
+    memset(&v, 0, sizeof(v));
+    v.u = u; v.d = d; v.w = w; v.s = s; v.as = as; v.f = f;
+    v.invdiag = C ? C->d_invdiag : nullptr;
+    v.bits = C ? C->d_bits : nullptr;
+    v.n = A->h;
+    v.state = ws->d_state;
+    v.hist = ws->d_hist;
+    v.partials = ctx->d_partials;
+    v.counter = ctx->d_counter;
+    v.ip_mode = ip_mode;
+
+    int sub = 0;
+    if (initialize) {
+        NGSB_CUDA(cudaMemsetAsync(u, 0, nscal * sizeof(double), ctx->stream));   // u = 0.0
+    } else {
+        SpmvArgs a;
+        memset(&a, 0, sizeof(a));
+        a.A = A; a.x = u; a.y = as; a.sr = 1.0; a.accumulate = false; a.epi = EPI_NONE;
+        NGSB_TRY(spmv_launch(a));
+        sub = 1;                                                                // d = f - A*u
+    }
+    NGSB_TRY(launch_cg_fused<0>(ctx, A->kind, v, sub));
+
+    // iterate in batches; the stop flag is polled one batch behind the enqueue front
+    const long batch = ctx->cg_batch;
+    const bool use_graph = !ctx->timing && getenv("NGSB_NO_CUDA_GRAPH") == nullptr && batch > 1;
+    if (use_graph) {
+        double *key[6] = {u, d, w, s, as, (double *)f};
+        bool hit = ws->graph_exec && ws->g_A == A && ws->g_C == C && ws->g_batch == batch && ws->g_ip == ip_mode &&
+                   ws->g_algo == ctx->spmv_algo && ws->g_cps == ctx->spmv_ctas_per_sm && memcmp(key, ws->g_ptrs, sizeof(key)) == 0;
+        if (!hit) {
+            if (ws->graph_exec) { cudaGraphExecDestroy(ws->graph_exec); ws->graph_exec = nullptr; }
+            cudaGraph_t graph = nullptr;
+            uint64_t launches_before = ctx->launches;
+            NGSB_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+            int rc = NGSB_OK;
+            for (long k = 0; k < batch && rc == NGSB_OK; k++) rc = enqueue_iteration(ctx, A, v, as);
+            cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
+            ctx->launches = launches_before;
+            if (rc != NGSB_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+            NGSB_CUDA(ce);
+            NGSB_CUDA(cudaGraphInstantiate(&ws->graph_exec, graph, 0));
+            cudaGraphDestroy(graph);
+            ws->g_A = A; ws->g_C = C; ws->g_batch = batch; ws->g_ip = ip_mode;
+            ws->g_algo = ctx->spmv_algo; ws->g_cps = ctx->spmv_ctas_per_sm;
+            memcpy(ws->g_ptrs, key, sizeof(key));
+        }
+    }
+
+    cudaEvent_t ev[2];
+    NGSB_CUDA(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
+    NGSB_CUDA(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+    long enq = 0;          // batches enqueued
+    bool finished = false;
+    int rc = NGSB_OK;
+    // upper bound of batches ever needed
+    const long max_batches = ((long)maxsteps + batch - 1) / batch + 1;
+    while (!finished) {
+        if (enq < max_batches) {
+            if (use_graph) {
+                cudaError_t e = cudaGraphLaunch(ws->graph_exec, ctx->stream);
+                if (e != cudaSuccess) { set_error("cudaGraphLaunch failed: %s", cudaGetErrorString(e)); rc = NGSB_ERR_CUDA; break; }
+                ctx->launches += 3 * batch;
+            } else {
+                for (long k = 0; k < batch && rc == NGSB_OK; k++) rc = enqueue_iteration(ctx, A, v, as);
+                if (rc != NGSB_OK) break;
+            }
+        }
+        cudaMemcpyAsync(&hs[1 + (enq & 1)], ws->d_state, sizeof(CgState), cudaMemcpyDeviceToHost, ctx->stream);
+        cudaEventRecord(ev[enq & 1], ctx->stream);
+        if (enq > 0) {
+            // look at the state copied after the previous batch
+            cudaError_t e = cudaEventSynchronize(ev[(enq - 1) & 1]);
+            if (e != cudaSuccess) { set_error("CG: %s", cudaGetErrorString(e)); rc = NGSB_ERR_CUDA; break; }
+            if (hs[1 + ((enq - 1) & 1)].done) finished = true;
+        }
+        enq++;
+        if (!finished && enq > max_batches + 1) {
+            set_error("CG: device loop did not terminate");
+            rc = NGSB_ERR_CUDA;
+            break;
+        }
+    }
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (rc == NGSB_OK && e != cudaSuccess) { set_error("CG: %s", cudaGetErrorString(e)); rc = NGSB_ERR_CUDA; }
+    cudaEventDestroy(ev[0]);
+    cudaEventDestroy(ev[1]);
+    if (rc == NGSB_OK) {
+        NGSB_CUDA(cudaMemcpyAsync(&hs[3], ws->d_state, sizeof(CgState), cudaMemcpyDeviceToHost, ctx->stream));
+        NGSB_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (steps) *steps = hs[3].n;
+        int nh = hs[3].nhist;
+        if (nhist) *nhist = nh;
+        int ncopy = nh < hist_cap ? nh : hist_cap;
+        if (history && ncopy > 0) {
+            NGSB_CUDA(cudaMemcpyAsync(history, ws->d_hist, ncopy * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+            NGSB_CUDA(cudaStreamSynchronize(ctx->stream));
+        }
+    }
+    ws_put_buf(ctx, nscal, s);
+    ws_put_buf(ctx, nscal, d);
+    ws_put_buf(ctx, nscal, as);
+    if (w) ws_put_buf(ctx, nscal, w);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------
+// GMRES
+// ------------------------------------------------------------------------------------------
+struct GmresState {
+    double norm, err, prec;
+    int j;            // the reference's loop variable
+    int done;
+    int maxsteps;
+    int cplx;
+    int nhist, hist_cap;
+    double tmp[2];    // reduction result slot
+    double tmp2[2];
+    double scale[2];  // scalar for the next "v = scale * w"
+};
+
+__device__ __forceinline__ double2 z_mul(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ double2 z_div(double2 a, double2 b)
+{
+    if (b.y == 0.0 && a.y == 0.0) return make_double2(a.x / b.x, 0.0);
+    double den = b.x * b.x + b.y * b.y;
+    return make_double2((a.x * b.x + a.y * b.y) / den, (a.y * b.x - a.x * b.y) / den);
+}
+__device__ __forceinline__ double2 z_sqrt(double2 z, int cplx)
+{
+    if (!cplx) return make_double2(sqrt(z.x), 0.0);
+    double r = hypot(z.x, z.y);
+    if (r == 0.0) return make_double2(0.0, 0.0);
+    double re, im;
+    if (z.x >= 0.0) { re = sqrt(0.5 * (r + z.x)); im = z.y / (2.0 * re); }
+    else { im = sqrt(0.5 * (r - z.x)); if (z.y < 0.0) im = -im; re = z.y / (2.0 * im); }
+    return make_double2(re, im);
+}
+
+// after norm2 = sum |r|^2 (tmp) and rr = <r,r> (tmp2): cg.cpp:889-903
+__global__ void gmres_init_kernel(GmresState *st, double2 *gammai, double *hist)
+{
+    st->norm = sqrt(st->tmp[0]);
+    double2 rr = make_double2(st->tmp2[0], st->cplx ? st->tmp2[1] : 0.0);
+    double2 sq = z_sqrt(rr, st->cplx);
+    double2 sc = z_div(make_double2(1.0, 0.0), sq);
+    st->scale[0] = sc.x;
+    st->scale[1] = sc.y;
+    gammai[0] = make_double2(st->norm, 0.0);
+    if (st->hist_cap > 0) hist[0] = st->norm;
+    st->nhist = 1;
+    st->err = st->prec * fabs(st->norm);
+    st->j = -1;
+    st->done = 0;
+    bool cont = (st->j++ < st->maxsteps - 2) && (st->norm > st->err);
+    if (!cont) st->done = 1;
+}
+
+// h(i,j) = tmp; publish -h(i,j) as the next axpy scalar (kept in hcol[i])
+__global__ void gmres_store_h_kernel(GmresState *st, double2 *h, int ms, int i)
+{
+    if (st->done) return;
+    int j = st->j;
+    h[(size_t)i * ms + j] = make_double2(st->tmp[0], st->cplx ? st->tmp[1] : 0.0);
+}
+
+// after <w,w> (tmp): h(j+1,j), scale, Givens, norm, loop condition -- cg.cpp:934-962
+__global__ void gmres_givens_kernel(GmresState *st, double2 *h, double2 *gammai, double2 *ci, double2 *si, int ms, double *hist)
+{
+    if (st->done) return;
+    const int j = st->j;
+    const int cplx = st->cplx;
+#define H(a, b) h[(size_t)(a) * ms + (b)]
+    double2 ww = make_double2(st->tmp[0], cplx ? st->tmp[1] : 0.0);
+    H(j + 1, j) = z_sqrt(ww, cplx);
+    double2 sc = z_div(make_double2(1.0, 0.0), H(j + 1, j));
+    st->scale[0] = sc.x;
+    st->scale[1] = sc.y;
+    for (int i = 0; i < j; i++) {
+        double2 hi = H(i, j), hip = H(i + 1, j);
+        double2 a = z_mul(ci[i + 1], hi), b = z_mul(si[i + 1], hip);
+        double2 c = z_mul(si[i + 1], hi), d = z_mul(ci[i + 1], hip);
+        H(i, j) = make_double2(a.x + b.x, a.y + b.y);
+        H(i + 1, j) = make_double2(c.x - d.x, c.y - d.y);
+    }
+    double2 hjj = H(j, j), hj1 = H(j + 1, j);
+    double2 q1 = z_mul(hjj, hjj), q2 = z_mul(hj1, hj1);
+    double2 beta = z_sqrt(make_double2(q1.x + q2.x, q1.y + q2.y), cplx);
+    si[j + 1] = z_div(hj1, beta);
+    ci[j + 1] = z_div(hjj, beta);
+    H(j, j) = beta;
+    gammai[j + 1] = z_mul(si[j + 1], gammai[j]);
+    gammai[j] = z_mul(ci[j + 1], gammai[j]);
+    st->norm = cplx ? hypot(gammai[j].x, gammai[j].y) : fabs(gammai[j].x);
+    if (st->nhist < st->hist_cap) hist[st->nhist] = st->norm;
+    st->nhist++;
+    bool cont = (st->j++ < st->maxsteps - 2) && (st->norm > st->err);
+    if (!cont) st->done = 1;
+#undef H
+}
+
+// back substitution (cg.cpp:964-973); y[i] for i <= jfinal, jfinal = j-1 after the loop
+__global__ void gmres_backsolve_kernel(GmresState *st, const double2 *h, const double2 *gammai, double2 *y, int ms)
+{
+    int j = st->j - 1;
+    for (int i = j; i >= 0; i--) {
+        double2 sum = gammai[i];
+        for (int k = i + 1; k <= j; k++) {
+            double2 p = z_mul(h[(size_t)i * ms + k], y[k]);
+            sum.x -= p.x;
+            sum.y -= p.y;
+        }
+        y[i] = z_div(sum, h[(size_t)i * ms + i]);
+    }
+}
+
+// w -= hprev * vprev (if vprev), then partial <vnext, w> (bilinear) -> tmp.  selfdot: vnext = w.
+template <bool CPLX>
+__global__ void __launch_bounds__(256) gmres_mgs_kernel(double *__restrict__ w, const double *__restrict__ vprev,
+                                                       const double2 *__restrict__ hprev, const double *__restrict__ vnext,
+                                                       int selfdot, uint64_t N, GmresState *st, double *partials,
+                                                       unsigned int *counter)
+{
+    if (st->done) return;
+    double hr = 0.0, hi = 0.0;
+    if (vprev) { hr = hprev->x; hi = CPLX ? hprev->y : 0.0; }
+    uint64_t per = (N + gridDim.x - 1) / gridDim.x;
+    uint64_t lo = (uint64_t)blockIdx.x * per;
+    uint64_t hi_ = lo + per < N ? lo + per : N;
+    double ar = 0.0, ai = 0.0;
+    for (uint64_t i = lo + threadIdx.x; i < hi_; i += blockDim.x) {
+        if (CPLX) {
+            double2 wv = reinterpret_cast<double2 *>(w)[i];
+            if (vprev) {
+                double2 p = reinterpret_cast<const double2 *>(vprev)[i];
+                wv.x -= hr * p.x - hi * p.y;
+                wv.y -= hr * p.y + hi * p.x;
+                reinterpret_cast<double2 *>(w)[i] = wv;
+            }
+            double2 q = selfdot ? wv : reinterpret_cast<const double2 *>(vnext)[i];
+            ar += q.x * wv.x - q.y * wv.y;
+            ai += q.x * wv.y + q.y * wv.x;
+        } else {
+            double wv = w[i];
+            if (vprev) { wv -= hr * vprev[i]; w[i] = wv; }
+            double q = selfdot ? wv : vnext[i];
+            ar = fma(q, wv, ar);
+        }
+    }
+    double2 total;
+    if (grid_finish(ar, ai, partials, counter, &total)) {
+        st->tmp[0] = total.x;
+        st->tmp[1] = total.y;
+    }
+}
+
+// x += y[i] * v_i
+template <bool CPLX>
+__global__ void __launch_bounds__(256) gmres_update_kernel(double *__restrict__ x, const double *__restrict__ vi, const double2 *__restrict__ yi,
+                                                          uint64_t N, const GmresState *st, int i)
+{
+    if (i > st->j - 1) return;
+    double yr = yi->x, yim = yi->y;
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < N; k += stride) {
+        if (CPLX) {
+            double2 a = reinterpret_cast<const double2 *>(vi)[k];
+            double2 o = reinterpret_cast<double2 *>(x)[k];
+            o.x += yr * a.x - yim * a.y;
+            o.y += yr * a.y + yim * a.x;
+            reinterpret_cast<double2 *>(x)[k] = o;
+        } else x[k] += yr * vi[k];
+    }
+}
+
+} // namespace ngsb
+
+using namespace ngsb;
+
+static int check_solver_args(const ngsb_csr *A, const ngsb_jacobi *C, const ngsb_vec *f, const ngsb_vec *u, const char *who)
+{
+    NGSB_REQUIRE(A && f && u, "%s: NULL argument", who);
+    NGSB_REQUIRE(A->h == A->w, "%s: matrix must be square", who);
+    NGSB_REQUIRE(f->ctx == A->ctx && u->ctx == A->ctx && (!C || C->ctx == A->ctx), "%s: objects belong to different contexts", who);
+    NGSB_REQUIRE(f->kind == A->kind && u->kind == A->kind, "%s: vector kind does not match matrix kind", who);
+    NGSB_REQUIRE(f->n == A->h && u->n == A->h, "%s: size of matrix = %zu, f = %zu, u = %zu", who, A->h, f->n, u->n);
+    NGSB_REQUIRE(!C || (C->n == A->h && C->kind == A->kind), "%s: preconditioner does not match matrix", who);
+    NGSB_REQUIRE(f->d != u->d, "%s: f and u must be different vectors", who);
+    return NGSB_OK;
+}
+
+extern "C" int ngsb_cg_solve(const ngsb_csr *A, const ngsb_jacobi *C, const ngsb_vec *f, ngsb_vec *u, double prec, int maxsteps,
+                             int ip_mode, int initialize, int *steps, double *history, int hist_cap, int *nhist)
+{
+    NGSB_TRY(check_solver_args(A, C, f, u, "CGSolver::Mult"));
+    NGSB_REQUIRE(ip_mode >= 0 && ip_mode <= 2, "CGSolver::Mult: bad ip_mode %d", ip_mode);
+    NGSB_REQUIRE((A->kind == NGSB_COMPLEX) == (ip_mode != NGSB_IP_REAL), "CGSolver::Mult: ip_mode %d does not fit matrix kind %d", ip_mode, A->kind);
+    NGSB_REQUIRE(maxsteps >= 0, "CGSolver::Mult: maxsteps < 0");
+    NGSB_CUDA(cudaSetDevice(A->ctx->device));
+    return cg_solve_device(A, C, f->d, u->d, prec, maxsteps, ip_mode, initialize, steps, history, hist_cap, nhist);
+}
+
+extern "C" int ngsb_cg_solve_host(const ngsb_csr *A, const ngsb_jacobi *C, const void *f_host, void *u_host, double prec,
+                                  int maxsteps, int ip_mode, int *steps, double *history, int hist_cap, int *nhist)
+{
+    NGSB_REQUIRE(A && f_host && u_host, "ngsb_cg_solve_host: NULL argument");
+    ngsb_ctx *ctx = A->ctx;
+    NGSB_CUDA(cudaSetDevice(ctx->device));
+    const size_t nscal = A->h * kind_scalars(A->kind);
+    double *f = nullptr, *u = nullptr;
+    NGSB_TRY(ws_get_buf(ctx, nscal + 1, &f));   // +1: keep these apart from the solver's own buffers
+    NGSB_TRY(ws_get_buf(ctx, nscal + 1, &u));
+    ngsb_vec fv, uv;
+    fv.ctx = ctx; fv.n = A->h; fv.kind = A->kind; fv.nscal = nscal; fv.d = f;
+    uv = fv; uv.d = u;
+    int rc = ngsb_vec_h2d(&fv, f_host, 0, A->h);
+    if (rc == NGSB_OK) rc = ngsb_cg_solve(A, C, &fv, &uv, prec, maxsteps, ip_mode, 1, steps, history, hist_cap, nhist);
+    if (rc == NGSB_OK) rc = ngsb_vec_d2h(&uv, u_host, 0, A->h);
+    ws_put_buf(ctx, nscal + 1, f);
+    ws_put_buf(ctx, nscal + 1, u);
+    return rc;
+}
+
+extern "C" int ngsb_gmres_solve(const ngsb_csr *A, const ngsb_jacobi *C, const ngsb_vec *fvec, ngsb_vec *xvec, double prec,
+                                int maxsteps, int initialize, int *steps, double *history, int hist_cap, int *nhist)
+{
+    NGSB_TRY(check_solver_args(A, C, fvec, xvec, "GMRESSolver::Mult"));
+    NGSB_REQUIRE(maxsteps >= 1, "GMRESSolver::Mult: maxsteps < 1");
+    ngsb_ctx *ctx = A->ctx;
+    NGSB_CUDA(cudaSetDevice(ctx->device));
+    const bool cplx = A->kind == NGSB_COMPLEX;
+    const size_t nscal = A->h * kind_scalars(A->kind);
+    const uint64_t N = cplx ? A->h : nscal;        // reduction / update length in scalars of the IP type
+    const int ms = maxsteps;
+    if (hist_cap < 0 || !history) hist_cap = 0;
+
+    // small device arrays
+    GmresState *d_st = nullptr;
+    double2 *d_h = nullptr, *d_gam = nullptr, *d_ci = nullptr, *d_si = nullptr, *d_y = nullptr;
+    double *d_hist = nullptr, *d_scale = nullptr;
+    std::vector<double *> vi;
+    double *av = nullptr, *hv = nullptr, *w = nullptr, *r = nullptr;
+    int rc = NGSB_OK;
+    GmresState hst;
+    auto cleanup = [&]() {
+        cudaStreamSynchronize(ctx->stream);
+        cudaFree(d_st); cudaFree(d_h); cudaFree(d_gam); cudaFree(d_ci); cudaFree(d_si); cudaFree(d_y); cudaFree(d_hist); cudaFree(d_scale);
+        for (auto p : vi) cudaFree(p);
+        cudaFree(av); cudaFree(hv); cudaFree(w); cudaFree(r);
+    };
+#define GM_CUDA(call)                                                                                      \
+    do {                                                                                                   \
+        cudaError_t e__ = (call);                                                                          \
+        if (e__ != cudaSuccess) { set_error("%s failed: %s", #call, cudaGetErrorString(e__)); cleanup(); return NGSB_ERR_CUDA; } \
+    } while (0)
+#define GM_TRY(call)                                      \
+    do {                                                  \
+        rc = (call);                                      \
+        if (rc != NGSB_OK) { cleanup(); return rc; }      \
+    } while (0)
+
+    GM_CUDA(cudaMalloc(&d_st, sizeof(GmresState)));
+    GM_CUDA(cudaMalloc(&d_h, sizeof(double2) * (size_t)(ms + 1) * ms));
+    GM_CUDA(cudaMemsetAsync(d_h, 0, sizeof(double2) * (size_t)(ms + 1) * ms, ctx->stream));
+    GM_CUDA(cudaMalloc(&d_gam, sizeof(double2) * (ms + 2)));
+    GM_CUDA(cudaMalloc(&d_ci, sizeof(double2) * (ms + 2)));
+    GM_CUDA(cudaMalloc(&d_si, sizeof(double2) * (ms + 2)));
+    GM_CUDA(cudaMalloc(&d_y, sizeof(double2) * (ms + 2)));
+    GM_CUDA(cudaMemsetAsync(d_gam, 0, sizeof(double2) * (ms + 2), ctx->stream));
+    GM_CUDA(cudaMemsetAsync(d_ci, 0, sizeof(double2) * (ms + 2), ctx->stream));
+    GM_CUDA(cudaMemsetAsync(d_si, 0, sizeof(double2) * (ms + 2), ctx->stream));
+    GM_CUDA(cudaMemsetAsync(d_y, 0, sizeof(double2) * (ms + 2), ctx->stream));
+    GM_CUDA(cudaMalloc(&d_hist, sizeof(double) * (hist_cap + 1)));
+    GM_CUDA(cudaMalloc(&d_scale, sizeof(double) * 2));
+    const size_t vbytes = (nscal ? nscal : 2) * sizeof(double);
+    GM_CUDA(cudaMalloc(&av, vbytes));
+    GM_CUDA(cudaMalloc(&hv, vbytes));
+    GM_CUDA(cudaMalloc(&w, vbytes));
+    GM_CUDA(cudaMalloc(&r, vbytes));
+
+    memset(&hst, 0, sizeof(hst));
+    hst.prec = prec;
+    hst.maxsteps = maxsteps;
+    hst.cplx = cplx ? 1 : 0;
+    hst.hist_cap = hist_cap;
+    GM_CUDA(cudaMemcpyAsync(d_st, &hst, sizeof(hst), cudaMemcpyHostToDevice, ctx->stream));
+    GM_CUDA(cudaStreamSynchronize(ctx->stream));
+
+    double *x = xvec->d;
+    const double *f = fvec->d;
+    auto spmv = [&](const double *in, double *out) {
+        SpmvArgs a;
+        memset(&a, 0, sizeof(a));
+        a.A = A; a.x = in; a.y = out; a.sr = 1.0; a.accumulate = false; a.epi = EPI_NONE;
+        return spmv_launch(a);
+    };
+    const int rgrid = reduce_grid(ctx, N);
+    auto mgs = [&](const double *vprev, const double2 *hprev, const double *vnext, int selfdot) {
+        SpanGuard g(ctx, KC_VEC);
+        if (cplx) gmres_mgs_kernel<true><<<rgrid, 256, 0, ctx->stream>>>(w, vprev, hprev, vnext, selfdot, N, d_st, ctx->d_partials, ctx->d_counter);
+        else gmres_mgs_kernel<false><<<rgrid, 256, 0, ctx->stream>>>(w, vprev, hprev, vnext, selfdot, N, d_st, ctx->d_partials, ctx->d_counter);
+        return cudaGetLastError() == cudaSuccess ? NGSB_OK : NGSB_ERR_CUDA;
+    };
+
+    // r = f (or f - A x); r = C r
+    if (initialize) {
+        GM_CUDA(cudaMemsetAsync(x, 0, nscal * sizeof(double), ctx->stream));
+        GM_CUDA(cudaMemcpyAsync(r, f, nscal * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    } else {
+        GM_TRY(spmv(x, av));
+        GM_CUDA(cudaMemcpyAsync(r, f, nscal * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+        GM_TRY(launch_axpby(ctx, r, av, N, -1.0, 0.0, cplx, true));
+    }
+    if (C) {
+        GM_TRY(jacobi_apply(C, 1.0, 0.0, r, hv, false));
+        GM_CUDA(cudaMemcpyAsync(r, hv, nscal * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    // norm = r.L2Norm(); v = 1/sqrt(<r,r>) r
+    GM_TRY(launch_dot(ctx, r, r, nscal, 3, (double *)((char *)d_st + offsetof(GmresState, tmp))));
+    GM_TRY(launch_dot(ctx, r, r, N, cplx ? 1 : 0, (double *)((char *)d_st + offsetof(GmresState, tmp2))));
+    {
+        SpanGuard g(ctx, KC_OTHER);
+        gmres_init_kernel<<<1, 1, 0, ctx->stream>>>(d_st, d_gam, d_hist);
+    }
+    double *d_st_scale = (double *)((char *)d_st + offsetof(GmresState, scale));
+    // v_0
+    {
+        double *v0 = nullptr;
+        GM_CUDA(cudaMalloc(&v0, vbytes));
+        vi.push_back(v0);
+        GM_TRY(launch_axpby_dev(ctx, v0, r, N, d_st_scale, cplx, false, false));
+    }
+
+    int j = -1;
+    bool done = false;
+    GM_CUDA(cudaMemcpyAsync(&hst, d_st, sizeof(hst), cudaMemcpyDeviceToHost, ctx->stream));
+    GM_CUDA(cudaStreamSynchronize(ctx->stream));
+    done = hst.done != 0;
+    while (!done) {
+        j = hst.j;   // current column
+        double *v = vi[j];
+        GM_TRY(spmv(v, av));
+        const double *avp = av;
+        if (C) { GM_TRY(jacobi_apply(C, 1.0, 0.0, av, hv, false)); avp = hv; }
+        GM_CUDA(cudaMemcpyAsync(w, avp, nscal * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+        // MGS: h(i,j) = <v_i, w>; w -= h(i,j) v_i  (projection i fused with inner product i+1)
+        for (int i = 0; i <= j; i++) {
+            GM_TRY(mgs(i > 0 ? vi[i - 1] : nullptr, i > 0 ? d_h + (size_t)(i - 1) * ms + j : nullptr, vi[i], 0));
+            SpanGuard g(ctx, KC_OTHER);
+            gmres_store_h_kernel<<<1, 1, 0, ctx->stream>>>(d_st, d_h, ms, i);
+        }
+        GM_TRY(mgs(vi[j], d_h + (size_t)j * ms + j, nullptr, 1));       // last projection + <w,w>
+        {
+            SpanGuard g(ctx, KC_OTHER);
+            gmres_givens_kernel<<<1, 1, 0, ctx->stream>>>(d_st, d_h, d_gam, d_ci, d_si, ms, d_hist);
+        }
+        // v_{j+1} = 1/h(j+1,j) * w  (always formed, like the reference)
+        double *vn = nullptr;
+        GM_CUDA(cudaMalloc(&vn, vbytes));
+        vi.push_back(vn);
+        GM_TRY(launch_axpby_dev(ctx, vn, w, N, d_st_scale, cplx, false, false));
+        GM_CUDA(cudaMemcpyAsync(&hst, d_st, sizeof(hst), cudaMemcpyDeviceToHost, ctx->stream));
+        GM_CUDA(cudaStreamSynchronize(ctx->stream));
+        done = hst.done != 0;
+    }
+    // j-- ; back substitution ; x += y_i v_i
+    {
+        SpanGuard g(ctx, KC_OTHER);
+        gmres_backsolve_kernel<<<1, 1, 0, ctx->stream>>>(d_st, d_h, d_gam, d_y, ms);
+    }
+    const int jfinal = hst.j - 1;
+    for (int i = 0; i <= jfinal; i++) {
+        SpanGuard g(ctx, KC_VEC);
+        uint64_t blocks = (N + 1023) / 1024;
+        uint64_t cap = (uint64_t)ctx->sm_count * 8;
+        if (blocks > cap) blocks = cap;
+        if (blocks < 1) blocks = 1;
+        if (cplx) gmres_update_kernel<true><<<(int)blocks, 256, 0, ctx->stream>>>(x, vi[i], d_y + i, N, d_st, i);
+        else gmres_update_kernel<false><<<(int)blocks, 256, 0, ctx->stream>>>(x, vi[i], d_y + i, N, d_st, i);
+    }
+    GM_CUDA(cudaGetLastError());
+    GM_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (steps) *steps = jfinal;
+    if (nhist) *nhist = hst.nhist;
+    int ncopy = hst.nhist < hist_cap ? hst.nhist : hist_cap;
+    if (history && ncopy > 0) {
+        GM_CUDA(cudaMemcpyAsync(history, d_hist, ncopy * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        GM_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    cleanup();
+#undef GM_CUDA
+#undef GM_TRY
+    return NGSB_OK;
+}

@@ -1,0 +1,59 @@
+// spmv.cuh -- internal interface of the CSR SpMV (spmv.cu), used by krylov.cu / dist.cu
+#pragma once
+#include "common.cuh"
+#include "cg_state.cuh"
+
+// one TMA-streamed row block: rows [row_begin, row_begin+nrows), whose entries live in
+// the 4-entry-aligned window [nnz_base, nnz_base + 4*nwin4) of col/val.
+struct SpmvBlock {
+    uint64_t nnz_base;
+    uint32_t row_begin;
+    uint32_t roff_base;   // index (in uint16 units, multiple of 8) into the row-offset array
+    uint16_t nrows;
+    uint16_t nwin4;       // window length / 4 entries
+    uint32_t flags;       // 1: long row (handled by the long-row kernel, only its dot part here)
+    uint64_t pad;
+};
+
+struct ngsb_csr {
+    ngsb_ctx *ctx = nullptr;
+    size_t h = 0, w = 0, nnz = 0;
+    int kind = 0;
+    uint64_t *d_rowptr = nullptr;   // h+1
+    int32_t *d_col = nullptr;       // nnz (+ slack)
+    double *d_val = nullptr;        // nnz * matscalars (+ slack)
+    // TMA-stream structures
+    SpmvBlock *d_blocks = nullptr;
+    uint16_t *d_rowoff = nullptr;
+    uint32_t nblocks = 0;
+    uint32_t *d_longrows = nullptr;
+    uint32_t nlong = 0;
+    int subwarp = 8;                // lanes per row
+    double mean_row = 0.0;
+    size_t max_row = 0;
+};
+
+namespace ngsb {
+
+// epilogue selector for the fused dot
+enum SpmvEpi { EPI_NONE = 0, EPI_DOT_OUT = 1, EPI_CG_KSS = 2 };
+
+struct SpmvArgs {
+    const ngsb_csr *A;
+    const double *x;
+    double *y;
+    double sr, si;          // scale
+    bool accumulate;        // y += s*A*x  vs  y = s*A*x
+    int epi;                // SpmvEpi
+    const double *dotvec;   // vector dotted with the result rows (EPI_DOT_OUT / EPI_CG_KSS)
+    int dot_conj;           // complex: conjugate the RESULT (argument) in the dot
+    double *dot_out;        // EPI_DOT_OUT: device (re,im)
+    CgState *state;         // EPI_CG_KSS (also: skip when state->done)
+    // row subset for the distributed path (interior/boundary split); nblocks==0 -> all
+    uint32_t block_begin, block_end;
+    bool use_range;
+};
+
+int spmv_launch(const SpmvArgs &a);
+
+} // namespace ngsb
