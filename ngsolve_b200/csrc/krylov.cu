@@ -13,7 +13,7 @@
 // GMRES: GMRESSolver<IPTYPE>::Mult (linalg/cg.cpp:854-1022): left preconditioning, modified
 // Gram-Schmidt in the reference's order (each projection fused with the next inner product),
 // Givens rotations and the triangular solve in single-thread kernels on the device.
-#include "jacobi.cuh"
+#include "krylov.cuh"
 
 #include <map>
 
@@ -57,7 +57,7 @@ static Workspace *get_ws(ngsb_ctx *ctx)
     return (Workspace *)ctx->ws;
 }
 
-static int ws_get_buf(ngsb_ctx *ctx, size_t nscal, double **out)
+int ws_get_buf(ngsb_ctx *ctx, size_t nscal, double **out)
 {
     Workspace *ws = get_ws(ctx);
     for (size_t i = 0; i < ws->free_bufs.size(); i++)
@@ -82,12 +82,12 @@ static int ws_get_buf(ngsb_ctx *ctx, size_t nscal, double **out)
     return NGSB_OK;
 }
 
-static void ws_put_buf(ngsb_ctx *ctx, size_t nscal, double *p)
+void ws_put_buf(ngsb_ctx *ctx, size_t nscal, double *p)
 {
     if (p) get_ws(ctx)->free_bufs.emplace_back(nscal, p);
 }
 
-static int ws_state(ngsb_ctx *ctx, size_t hist_cap)
+static int ws_state_impl(ngsb_ctx *ctx, size_t hist_cap)
 {
     Workspace *ws = get_ws(ctx);
     if (!ws->d_state) {
@@ -103,6 +103,16 @@ static int ws_state(ngsb_ctx *ctx, size_t hist_cap)
     return NGSB_OK;
 }
 
+int ws_state(ngsb_ctx *ctx, size_t hist_cap, CgState **d_state, CgState **h_state, double **d_hist)
+{
+    NGSB_TRY(ws_state_impl(ctx, hist_cap));
+    Workspace *ws = get_ws(ctx);
+    *d_state = ws->d_state;
+    *h_state = ws->h_state;
+    *d_hist = ws->d_hist;
+    return NGSB_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // fused CG kernels
 // ------------------------------------------------------------------------------------------
@@ -115,18 +125,6 @@ __device__ __forceinline__ double warp_sum_k(double v)
     return v;
 }
 
-struct CgVecs {
-    double *u, *d, *w, *s;
-    const double *as, *f;
-    const double *invdiag;     // NULL: no preconditioner (w aliases d, never stored)
-    const uint8_t *bits;
-    uint64_t n;                // entries
-    CgState *state;
-    double *hist;
-    double *partials;
-    unsigned int *counter;
-    int ip_mode;
-};
 
 // grid-wide deterministic reduction finish; returns true on thread 0 of the last block
 __device__ __forceinline__ bool grid_finish(double a, double b, double *partials, unsigned int *counter, double2 *total)
@@ -247,6 +245,7 @@ __global__ void __launch_bounds__(256) cg_fused_kernel(const CgVecs v, int sub)
             if (v.invdiag != nullptr) v.w[ES * i + c] = wn[c];
             if (MODE == 0) v.s[ES * i + c] = wn[c];
         }
+        if (v.master != nullptr && !v.master[i]) continue;
         if (KIND == NGSB_COMPLEX) {
             // init: <w, d> (conj on d) ; update: <d, w> (conj on w)
             double xr = MODE == 0 ? wn[0] : dn[0], xi = MODE == 0 ? wn[1] : dn[1];
@@ -261,7 +260,8 @@ __global__ void __launch_bounds__(256) cg_fused_kernel(const CgVecs v, int sub)
     }
     double2 total;
     if (grid_finish(accr, acci, v.partials, v.counter, &total)) {
-        if (MODE == 0) cg_finalize_init(st, total, v.hist);
+        if (v.dot_out != nullptr) { v.dot_out[0] = total.x; v.dot_out[1] = total.y; }
+        else if (MODE == 0) cg_finalize_init(st, total, v.hist);
         else cg_finalize_wdn(st, total, v.hist);
     }
 }
@@ -317,6 +317,28 @@ static int launch_cg_fused(ngsb_ctx *ctx, int kind, const CgVecs &v, int sub)
     return NGSB_OK;
 }
 
+__global__ void cg_finalize_kernel(int which, CgState *st, const double *dot, double *hist)
+{
+    if (which != 0 && st->done) return;
+    double2 t = make_double2(dot[0], dot[1]);
+    if (which == 0) cg_finalize_init(st, t, hist);
+    else if (which == 1) cg_finalize_kss(st, t);
+    else cg_finalize_wdn(st, t, hist);
+}
+
+int cg_launch_finalize(ngsb_ctx *ctx, int which, CgState *st, const double *dot, double *hist)
+{
+    SpanGuard g(ctx, KC_OTHER);
+    cg_finalize_kernel<<<1, 1, 0, ctx->stream>>>(which, st, dot, hist);
+    NGSB_CUDA(cudaGetLastError());
+    return NGSB_OK;
+}
+
+int cg_launch_fused(ngsb_ctx *ctx, int kind, int mode, const CgVecs &v, int sub)
+{
+    return mode == 0 ? launch_cg_fused<0>(ctx, kind, v, sub) : launch_cg_fused<1>(ctx, kind, v, sub);
+}
+
 static int launch_cg_dir(ngsb_ctx *ctx, int kind, const CgVecs &v)
 {
     SpanGuard g(ctx, KC_CGUPDATE);
@@ -332,6 +354,8 @@ static int launch_cg_dir(ngsb_ctx *ctx, int kind, const CgVecs &v)
     NGSB_CUDA(cudaGetLastError());
     return NGSB_OK;
 }
+
+int cg_launch_dir(ngsb_ctx *ctx, int kind, const CgVecs &v) { return launch_cg_dir(ctx, kind, v); }
 
 static int enqueue_iteration(ngsb_ctx *ctx, const ngsb_csr *A, const CgVecs &v, double *as)
 {
@@ -353,7 +377,7 @@ int cg_solve_device(const ngsb_csr *A, const ngsb_jacobi *C, const double *f, do
     const size_t nscal = A->h * kind_scalars(A->kind);
     if (hist_cap < 0) hist_cap = 0;
     if (!history) hist_cap = 0;
-    NGSB_TRY(ws_state(ctx, (size_t)hist_cap));
+    NGSB_TRY(ws_state_impl(ctx, (size_t)hist_cap));
     double *w = nullptr, *s = nullptr, *d = nullptr, *as = nullptr;
     NGSB_TRY(ws_get_buf(ctx, nscal, &s));
     NGSB_TRY(ws_get_buf(ctx, nscal, &d));

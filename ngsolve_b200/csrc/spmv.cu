@@ -266,9 +266,11 @@ __global__ void __launch_bounds__(NTHREADS) spmv_stream_kernel(const SpmvParams 
                     const uint32_t roff_bytes = (((uint32_t)d.nrows + 1u + 7u) & ~7u) * 2u;
                     const uint32_t bytes = nwin * (uint32_t)C::VB + nwin * 4u + roff_bytes;
                     mbar_arrive_expect_tx(&full[s], bytes);
-                    tma_bulk_g2s(st + L::VALS, reinterpret_cast<const unsigned char *>(p.val) + d.nnz_base * (uint64_t)C::VB,
-                                 nwin * (uint32_t)C::VB, &full[s]);
-                    tma_bulk_g2s(st + L::COLS, p.col + d.nnz_base, nwin * 4u, &full[s]);
+                    if (nwin) {   // a block of empty rows has no entries to stream
+                        tma_bulk_g2s(st + L::VALS, reinterpret_cast<const unsigned char *>(p.val) + d.nnz_base * (uint64_t)C::VB,
+                                     nwin * (uint32_t)C::VB, &full[s]);
+                        tma_bulk_g2s(st + L::COLS, p.col + d.nnz_base, nwin * 4u, &full[s]);
+                    }
                     tma_bulk_g2s(st + L::ROFF, p.rowoff + d.roff_base, roff_bytes, &full[s]);
                 }
             }

@@ -1,0 +1,384 @@
+"""GPU parity: the CUDA library (through the C ABI, via ngsolve_b200.la) against the golden
+vectors produced by the reference and against the CPU oracle on the same inputs.
+
+Tolerances (BASELINE.json north_star): pattern / reordering bit-exact; SpMV relative error
+<= 1e-12 in FP64; CG iteration count within +-2 of the reference CGSolver.
+"""
+import numpy as np
+import pytest
+
+from conftest import SYSTEMS, kind_of, load_golden, relerr
+from oracle import pyoracle as orc
+
+pytestmark = pytest.mark.gpu
+
+SPMV_TOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def la():
+    import ngsolve_b200.la as la
+    la.default_context()          # raises without a GPU / without the built library
+    return la
+
+
+def host_matrix(la, g):
+    return la.SparseMatrix(g["rowptr"], g["col"], g["val"], entrysize=3 if kind_of(g) == 3 else 1)
+
+
+def vec(la, g, arr):
+    return la.BaseVector(np.asarray(arr), entrysize=3 if kind_of(g) == 3 else 1)
+
+
+@pytest.fixture(scope="module", params=SYSTEMS)
+def sysm(request, la):
+    g = load_golden(request.param)
+    A = host_matrix(la, g)
+    dev = A.CreateDeviceMatrix()
+    assert isinstance(dev, la.DevSparseMatrix)          # not the silent host fallback of the reference registry
+    return request.param, g, A, dev
+
+
+@pytest.mark.parametrize("algo", [2, 1])
+def test_mult_multadd(la, sysm, algo):
+    name, g, A, dev = sysm
+    dev.ctx.set_option("spmv_algo", algo)
+    try:
+        x = vec(la, g, g["x"])
+        y = dev.CreateColVector()
+        dev.Mult(x, y)
+        assert relerr(y.NumPy().reshape(-1), g["y_mult"]) <= SPMV_TOL
+        y = vec(la, g, g["y0"])
+        dev.MultAdd(0.7, x, y)
+        assert relerr(y.NumPy().reshape(-1), g["y_multadd"]) <= SPMV_TOL
+        if kind_of(g) == 1:
+            y = vec(la, g, g["y0"])
+            dev.MultAdd(0.3 - 0.9j, x, y)
+            assert relerr(y.NumPy().reshape(-1), g["y_multadd_cs"]) <= SPMV_TOL
+        else:
+            with pytest.raises(la.NgsbError):
+                dev.MultAdd(1j, x, y)                     # "MultAdd(complex) called for real matrix"
+        # expression form used by scripts: y.data = 2.0 * A * x  (tests/pytest/test_basematrix.py)
+        y2 = dev.CreateColVector()
+        y2.data = 2.0 * dev * x
+        assert relerr(y2.NumPy().reshape(-1), 2.0 * g["y_mult"]) <= SPMV_TOL
+    finally:
+        dev.ctx.set_option("spmv_algo", 0)
+
+
+def test_pattern_bit_exact(la, sysm):
+    name, g, A, dev = sysm
+    val, col, rowptr = dev.CSR()
+    assert rowptr.dtype == np.uint64 and col.dtype == np.int32
+    assert np.array_equal(rowptr, g["rowptr"]) and np.array_equal(col, g["col"])
+    assert np.array_equal(val.view(np.float64), np.ascontiguousarray(g["val"]).reshape(-1).view(np.float64))
+
+
+def test_vector_ops(la, sysm):
+    name, g, A, dev = sysm
+    x, y0 = vec(la, g, g["x"]), vec(la, g, g["y0"])
+    if kind_of(g) == 1:
+        assert abs(x.InnerProduct(y0, conjugate=False) - g["dot_xy"][0]) <= 1e-13 * abs(g["dot_xy"][0])
+        assert abs(x.InnerProduct(y0, conjugate=True) - g["dot_xy_conj"][0]) <= 1e-13 * abs(g["dot_xy_conj"][0])
+    else:
+        assert abs(x.InnerProduct(y0) - g["dot_xy"][0]) <= 1e-13 * abs(g["dot_xy"][0])
+    assert abs(x.Norm() - g["norm_x"][0]) <= 1e-13 * g["norm_x"][0]
+    y = vec(la, g, g["y0"])
+    y.data += 0.5 * x
+    assert relerr(y.NumPy().reshape(-1), g["axpy_05"]) <= 1e-15
+    y.data = 3.0 * x
+    assert relerr(y.NumPy().reshape(-1), g["set_3"]) <= 1e-15
+    y *= 0.5
+    assert relerr(y.NumPy().reshape(-1), 1.5 * np.asarray(g["x"])) <= 1e-15
+    y[:] = 0
+    assert not y.NumPy().any()
+    # Range views alias the parent (UnifiedVector::Range)
+    n = x.size
+    r = y.Range(n // 4, n // 2)
+    r.data = x.Range(n // 4, n // 2)
+    full = y.NumPy()
+    ref = np.zeros_like(full)
+    xs = x.NumPy()
+    ref[n // 4:n // 2] = xs[n // 4:n // 2]
+    assert np.array_equal(full, ref)
+    with pytest.raises(la.NgsbError):
+        y.Add(1.0, la.BaseVector(n + 1, x.is_complex, x.entrysize))
+
+
+def test_jacobi(la, sysm):
+    name, g, A, dev = sysm
+    kind = kind_of(g)
+    J = A.CreateSmoother(la.BitArray(g["freebits"])).CreateDeviceMatrix(dev)
+    assert isinstance(J, la.DevJacobiMatrix)
+    oj = orc.Jacobi(orc.Csr(g["rowptr"], g["col"], g["val"], kind), g["freebits"])
+    inv = J.InvDiag()
+    if kind == 0:
+        assert np.array_equal(inv, oj.invdiag)            # 1/a is correctly rounded on both sides
+    else:
+        assert relerr(inv, oj.invdiag) <= 1e-14
+    x = vec(la, g, g["x"])
+    y = dev.CreateColVector()
+    J.Mult(x, y)
+    assert relerr(y.NumPy().reshape(-1), g["jac_mult"]) <= 1e-13
+    y = vec(la, g, g["y0"])
+    J.MultAdd(0.25, x, y)
+    assert relerr(y.NumPy().reshape(-1), g["jac_multadd"]) <= 1e-13
+    # a DevDiagonalMatrix handed the reference's inverse diagonal directly behaves the same
+    J2 = la.DevJacobiMatrix(invdiag=oj.invdiag, freedofs=la.BitArray(g["freebits"]), entrysize=3 if kind == 3 else 1)
+    y2 = dev.CreateColVector()
+    J2.Mult(x, y2)
+    assert relerr(y2.NumPy().reshape(-1), g["jac_mult"]) <= 1e-13
+
+
+@pytest.mark.parametrize("graph", [True, False])
+def test_cg_fused_matches_reference(la, sysm, graph, monkeypatch):
+    name, g, A, dev = sysm
+    if not graph:
+        monkeypatch.setenv("NGSB_NO_CUDA_GRAPH", "1")
+    kind = kind_of(g)
+    jac = A.CreateSmoother(la.BitArray(g["freebits"]))
+    f = vec(la, g, g["f"])
+    u = f.CreateVector()
+    inv = la.CGSolver(dev, jac, precision=float(g["cg_prec"]), maxsteps=int(g["cg_maxsteps"]))
+    u.data = inv * f
+    assert abs(inv.GetSteps() - int(g["cg_steps"])) <= 2, (inv.GetSteps(), int(g["cg_steps"]))
+    assert relerr(u.NumPy().reshape(-1), g["cg_u"]) <= 1e-6
+    # same convergence curve as the reference's python CG (residuals = sqrt|<d,w>|)
+    res = g["pycg_residuals"]
+    k = min(len(res), len(inv.history), 20) - 1
+    assert np.allclose(np.sqrt(inv.history[:k]), res[:k], rtol=1e-6, atol=0)
+    # and as the oracle, iteration by iteration, for the early part
+    oA = orc.Csr(g["rowptr"], g["col"], g["val"], kind)
+    ou, osteps, ohist = orc.cg_solve(oA, orc.Jacobi(oA, g["freebits"]), g["f"], prec=float(g["cg_prec"]), maxsteps=int(g["cg_maxsteps"]))
+    assert abs(inv.GetSteps() - osteps) <= 2
+    assert np.allclose(inv.history[:k], ohist[:k], rtol=1e-6, atol=0)
+    # exit by maxsteps: 7 iterations -> GetSteps() == 8
+    inv7 = la.CGSolver(dev, jac, precision=1e-30, maxsteps=7)
+    u7 = (inv7 * f).Evaluate()
+    assert inv7.GetSteps() == int(g["cg7_steps"]) == 8
+    assert relerr(u7.NumPy().reshape(-1), g["cg7_u"]) <= 1e-11
+    if kind == 1:
+        invc = la.CGSolver(dev, jac, precision=float(g["cg_prec"]), maxsteps=int(g["cg_maxsteps"]), conjugate=True)
+        uc = (invc * f).Evaluate()
+        assert abs(invc.GetSteps() - int(g["cgconj_steps"])) <= 2
+        if int(g["cgconj_steps"]) < int(g["cg_maxsteps"]):
+            assert relerr(uc.NumPy().reshape(-1), g["cgconj_u"]) <= 1e-5
+
+
+@pytest.mark.parametrize("name", ["poisson_h1p3", "elasticity_h1p4_dim3", "shifted_laplace_complex"])
+def test_cg_op_by_op_paths(la, name):
+    """The generic virtual-call path (what an unchanged script drives): the C++-style loop on
+    arbitrary operators and the python krylovspace.CGSolver, both on device vectors."""
+    from ngsolve_b200 import krylovspace
+    g = load_golden(name)
+    A = host_matrix(la, g)
+    dev = A.CreateDeviceMatrix()
+    jac = dev.CreateSmoother(la.BitArray(g["freebits"]))
+    f = vec(la, g, g["f"])
+
+    class Wrapped(la.BaseMatrix):            # python-derived BaseMatrix, tests/pytest/test_basematrix.py:31-45
+        def __init__(self, m):
+            self.m = m
+            self.height, self.width, self.is_complex, self.entrysize, self.ctx = m.height, m.width, m.is_complex, m.entrysize, m.ctx
+
+        def Mult(self, x, y):
+            self.m.Mult(x, y)
+
+    inv = la.CGSolver(Wrapped(dev), jac, precision=float(g["cg_prec"]), maxsteps=int(g["cg_maxsteps"]))
+    u = (inv * f).Evaluate()
+    assert abs(inv.GetSteps() - int(g["cg_steps"])) <= 2
+    assert relerr(u.NumPy().reshape(-1), g["cg_u"]) <= 1e-6
+    pinv = krylovspace.CGSolver(dev, jac, tol=float(g["cg_prec"]), maxiter=int(g["cg_maxsteps"]))
+    up = pinv.Solve(rhs=f)
+    assert abs(pinv.iterations - int(g["pycg_iterations"])) <= 2
+    m = min(len(pinv.residuals), len(g["pycg_residuals"]), 20)
+    assert np.allclose(pinv.residuals[:m], g["pycg_residuals"][:m], rtol=1e-6)
+    assert relerr(up.NumPy().reshape(-1), g["cg_u"]) <= 1e-6
+
+
+@pytest.mark.parametrize("name", ["poisson_h1p3", "helmholtz_h1p4_complex", "shifted_laplace_complex", "square_h1p4_testsolvers"])
+def test_gmres_matches_reference(la, name):
+    g = load_golden(name)
+    A = host_matrix(la, g)
+    dev = A.CreateDeviceMatrix()
+    jac = dev.CreateSmoother(la.BitArray(g["freebits"]))
+    f = vec(la, g, g["f"])
+    inv = la.GMRESSolver(dev, jac, precision=float(g["gmres_prec"]), maxsteps=int(g["gmres_maxsteps"]))
+    x = (inv * f).Evaluate()
+    assert abs(inv.GetSteps() - int(g["gmres_steps"])) <= 2, (inv.GetSteps(), int(g["gmres_steps"]))
+    assert relerr(x.NumPy().reshape(-1), g["gmres_u"]) <= 1e-6
+
+
+def test_python_gmres_solver(la):
+    """tests/pytest/test_solvers.py:59-79 flavour: python GMResSolver on the unit-square p4 problem."""
+    from ngsolve_b200 import krylovspace
+    g = load_golden("square_h1p4_testsolvers")
+    dev = host_matrix(la, g).CreateDeviceMatrix()
+    jac = dev.CreateSmoother(la.BitArray(g["freebits"]))
+    f = vec(la, g, g["f"])
+    inv = krylovspace.GMResSolver(dev, jac, tol=1e-10, maxiter=300)
+    u = inv.Solve(rhs=f)
+    ex = load_golden("square_h1p4_exact")
+    assert relerr(u.NumPy(), ex["u_direct"]) < 1e-7
+    assert inv.iterations < 300
+
+
+def test_reference_test_solvers_problem(la):
+    """tests/pytest/test_solvers.py:59-79 (Jacobi instead of BDDC): p4 is exact, L2 error < 1e-12."""
+    g = load_golden("square_h1p4_testsolvers")
+    ex = load_golden("square_h1p4_exact")
+    dev = host_matrix(la, g).CreateDeviceMatrix()
+    jac = dev.CreateSmoother(la.BitArray(g["freebits"]))
+    f = vec(la, g, g["f"])
+    inv = la.CGSolver(dev, jac, precision=1e-13, maxsteps=3000)
+    u = (inv * f).Evaluate()
+    M = la.SparseMatrix(ex["mass_rowptr"], ex["mass_col"], ex["mass_val"]).CreateDeviceMatrix()
+    e = u.CreateVector()
+    e.data = u - la.BaseVector(ex["u_interp"])
+    assert np.sqrt(abs(la.InnerProduct(e, M * e))) < 1e-12
+    assert relerr(u.NumPy(), ex["u_direct"]) < 1e-11
+
+
+def test_reference_test_matrix_golden_entry(la):
+    """tests/pytest/test_matrix.py:85-93 through the block SpMV: A e_(1,c) has x in row 1, comp c."""
+    g = load_golden("test_matrix_cube_h1dim3")
+    dev = la.SparseMatrix(g["rowptr"], g["col"], g["val"], entrysize=3).CreateDeviceMatrix()
+    x = float(g["golden_x"])
+    for c in range(3):
+        e = np.zeros((dev.height, 3))
+        e[1, c] = 1.0
+        y = (dev * la.BaseVector(e)).Evaluate().NumPy()
+        assert abs(y[1, c] - x) < 1e-8 and abs(y[1, (c + 1) % 3]) < 1e-12
+
+
+def test_reorder_bit_exact(la):
+    g = load_golden("poisson_h1p3")
+    dev = host_matrix(la, g).CreateDeviceMatrix()
+    rng = np.random.default_rng(3)
+    perm = rng.permutation(dev.height).astype(np.uint64)
+    val, col, rowptr = dev.Reorder(perm).CSR()
+    ref = orc.Csr(g["rowptr"], g["col"], g["val"], 0).reorder(perm)
+    assert np.array_equal(rowptr, ref.rowptr) and np.array_equal(col, ref.col) and np.array_equal(val, ref.val)
+    with pytest.raises(la.NgsbError):
+        dev.Reorder(np.zeros(dev.height, dtype=np.uint64))
+
+
+def _random_csr(rng, n, rowlens, kind, width=None):
+    width = width or n
+    rowptr = np.zeros(n + 1, dtype=np.uint64)
+    rowptr[1:] = np.cumsum(rowlens)
+    cols = np.concatenate([np.sort(rng.choice(width, size=int(k), replace=False)) for k in rowlens] + [np.zeros(0, dtype=np.int64)])
+    nnz = int(rowptr[-1])
+    ms = {0: 1, 1: 1, 3: 9}[kind]
+    val = rng.standard_normal(nnz * ms)
+    if kind == 1:
+        val = val + 1j * rng.standard_normal(nnz * ms)
+    return rowptr, cols.astype(np.int32), val
+
+
+@pytest.mark.parametrize("kind", [0, 1, 3])
+@pytest.mark.parametrize("algo", [2, 1])
+def test_ragged_and_long_rows(la, kind, algo):
+    """empty rows, rows longer than one streamed tile, a rectangular matrix, very short rows."""
+    rng = np.random.default_rng(7 + kind)
+    n, w = 1500, 4000
+    rowlens = rng.integers(0, 40, size=n)
+    rowlens[::97] = 0
+    rowlens[5] = 3000          # > tile for every kind
+    rowlens[700] = 2500
+    rowlens[n - 1] = 2200
+    rowptr, col, val = _random_csr(rng, n, rowlens, kind, width=w)
+    ctx = la.default_context()
+    ctx.set_option("spmv_algo", algo)
+    try:
+        dev = la.SparseMatrix(rowptr, col, val, n, w, entrysize=3 if kind == 3 else 1).CreateDeviceMatrix()
+        es = 3 if kind == 3 else 1
+        xs = rng.standard_normal(w * es) + (1j * rng.standard_normal(w * es) if kind == 1 else 0)
+        y0 = rng.standard_normal(n * es) + (1j * rng.standard_normal(n * es) if kind == 1 else 0)
+        x = la.BaseVector(xs, entrysize=es)
+        y = la.BaseVector(y0, entrysize=es)
+        dev.MultAdd(-1.3, x, y)
+        oA = orc.Csr(rowptr, col, val, kind)
+        yref = y0.copy()
+        oA.multadd(-1.3, xs, yref)
+        assert relerr(y.NumPy().reshape(-1), yref) <= SPMV_TOL
+        dev.Mult(x, y)
+        assert relerr(y.NumPy().reshape(-1), oA.mult(xs)) <= SPMV_TOL
+    finally:
+        ctx.set_option("spmv_algo", 0)
+
+
+def test_empty_and_tiny(la):
+    A = la.SparseMatrix(np.zeros(1, dtype=np.uint64), np.zeros(0, dtype=np.int32), np.zeros(0), 0, 0).CreateDeviceMatrix()
+    x, y = A.CreateRowVector(), A.CreateColVector()
+    A.Mult(x, y)
+    assert x.InnerProduct(y) == 0.0 and x.Norm() == 0.0
+    # 1x1 and all-empty rows
+    B = la.SparseMatrix(np.array([0, 1], dtype=np.uint64), np.array([0], dtype=np.int32), np.array([2.5])).CreateDeviceMatrix()
+    xb = la.BaseVector(np.array([4.0]))
+    assert (B * xb).Evaluate().NumPy()[0] == 10.0
+    Z = la.SparseMatrix(np.zeros(11, dtype=np.uint64), np.zeros(0, dtype=np.int32), np.zeros(0), 10, 10).CreateDeviceMatrix()
+    yz = la.BaseVector(np.ones(10))
+    Z.Mult(la.BaseVector(np.ones(10)), yz)
+    assert not yz.NumPy().any()
+    # the 5x5 tridiagonal of SURVEY 3.1: 3 iterations -> GetSteps() == 4
+    n = 5
+    rp = np.array([0, 2, 5, 8, 11, 13], dtype=np.uint64)
+    col = np.array([0, 1, 0, 1, 2, 1, 2, 3, 2, 3, 4, 3, 4], dtype=np.int32)
+    val = np.array([2, -1, -1, 2, -1, -1, 2, -1, -1, 2, -1, -1, 2.0])
+    T = la.SparseMatrix(rp, col, val).CreateDeviceMatrix()
+    inv = la.CGSolver(T, T.CreateSmoother(), precision=1e-8, maxsteps=200)
+    f = np.ones(n)
+    u = (inv * la.BaseVector(f)).Evaluate().NumPy()
+    ou, osteps, _ = orc.cg_solve(orc.Csr(rp, col, val, 0), orc.Jacobi(orc.Csr(rp, col, val, 0)), f)
+    assert inv.GetSteps() == osteps == 4
+    assert np.allclose(u, ou, rtol=1e-12)
+
+
+def test_errors_are_loud(la):
+    g = load_golden("poisson_h1p3")
+    dev = host_matrix(la, g).CreateDeviceMatrix()
+    with pytest.raises(la.NgsbError):
+        dev.Mult(la.BaseVector(dev.width + 1), dev.CreateColVector())
+    with pytest.raises(la.NgsbError):
+        x = dev.CreateRowVector()
+        dev.Mult(x, x)
+    bad = g["col"].copy()
+    bad[3] = dev.width
+    with pytest.raises(la.NgsbError):
+        la.SparseMatrix(g["rowptr"], bad, g["val"]).CreateDeviceMatrix()
+    with pytest.raises(la.NgsbError):
+        host_matrix(la, g).Mult(None, None)               # no CPU path
+    with pytest.raises(la.NgsbError):
+        la.CreateDevMatrix(la.BaseMatrix())
+
+
+def test_host_device_coherence(la):
+    """UnifiedVector contract: host writes through FV().NumPy() are seen by the next device op
+    and device results by the next host read (ngscuda/unifiedvector.cpp:288-330)."""
+    v = la.UnifiedVector(1000)
+    v.FV().NumPy()[:] = np.arange(1000.0)
+    assert v.Norm() == pytest.approx(np.linalg.norm(np.arange(1000.0)), rel=1e-14)
+    w = v.CreateVector()
+    w.data = 2.0 * v
+    assert np.array_equal(w.FV().NumPy(), 2.0 * np.arange(1000.0))
+    w.FV().NumPy()[0] = 7.0
+    assert w.InnerProduct(w) == pytest.approx(49.0 + float(np.sum((2.0 * np.arange(1, 1000.0)) ** 2)), rel=1e-14)
+
+
+def test_cg_solve_host_entry(la):
+    g = load_golden("poisson_h1p3")
+    dev = host_matrix(la, g).CreateDeviceMatrix()
+    jac = dev.CreateSmoother(la.BitArray(g["freebits"]))
+    u, steps, hist = la.cg_solve_host(dev, jac, g["f"], precision=float(g["cg_prec"]), maxsteps=int(g["cg_maxsteps"]))
+    assert abs(steps - int(g["cg_steps"])) <= 2
+    assert relerr(u, g["cg_u"]) <= 1e-6
+
+
+def test_dots_are_deterministic(la):
+    rng = np.random.default_rng(0)
+    a, b = rng.standard_normal(1 << 20), rng.standard_normal(1 << 20)
+    x, y = la.BaseVector(a), la.BaseVector(b)
+    vals = {x.InnerProduct(y) for _ in range(5)}
+    assert len(vals) == 1
+    assert abs(vals.pop() - orc.inner(a, b)) <= 1e-12 * np.linalg.norm(a) * np.linalg.norm(b)
