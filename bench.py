@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""bench.py -- CG iterations/s (and SpMV HBM GB/s) of the assembled-system solve path on B200.
+
+Workload (BASELINE.json configs[2], the config the metric and target are quoted on; it fits one
+GPU): Poisson, H1 order 3, unit cube, ~100 M dofs, Jacobi-preconditioned CG.  The system is
+assembled on the device by the library's synthetic FE generator (structured Kuhn tetrahedral
+mesh, NGSolve dof numbering, see include/ngsb200_workloads.h) because netgen/NGSolve do not exist
+on the GPU box.  One step = one CG iteration (SpMV + fused vector updates / dots / Jacobi).
+At N > 1 the SAME global grid is split into N slabs of elements, one per rank (strong scaling,
+the reference's ParallelDofs / ParallelMatrix split; interface values move by NCCL over NVLink).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--size M] [--impl reference]
+
+--impl reference times the CPU restatement of the reference path (oracle/, OpenMP on all host
+cores; NGSolve itself needs cmake + netgen and cannot be built on the box) on a bounded sample
+of the same workload, scaled to the full size by the nnz ratio.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "cg_iterations_per_s"
+UNIT = "iterations/s"
+SAMPLE_M = 33            # CPU sample: (3*33+1)^3 = 1.0 M dofs (BASELINE.json configs[0] size)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--size", type=int, default=155, help="cubes per axis of the global grid; dofs = (3*size+1)^3")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-full-solve", action="store_true")
+    ap.add_argument("--cpu-iters", type=int, default=150)
+    return ap.parse_args()
+
+
+def workload_name(m):
+    return "Poisson unit cube H1 order 3, %d^3 cubes x 6 tets, %.1fM dofs, Jacobi-PCG" % (m, (3 * m + 1) ** 3 / 1e6)
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference path
+# ---------------------------------------------------------------------------------------------
+def cpu_cg(iters, full_nnz, full_ndof):
+    """Jacobi-PCG of the oracle (reference recurrences, 16-chunk dots, OpenMP rows) on the sample
+    system; returns dict(value scaled to the full size, raw numbers)."""
+    from oracle import pyoracle as orc
+    from ngsolve_b200 import workloads as W
+    box = W.FemBox(SAMPLE_M, order=3)
+    rp, col, val, rhs = box.host_csr()          # host loop of the generator (no GPU involved)
+    free = box.freedofs()
+    A = orc.Csr(rp, col, val, 0)
+    J = orc.Jacobi(A, free.bytes)
+    cores = orc.max_threads()
+    orc.cg_solve(A, J, rhs, prec=0.0, maxsteps=3)                     # warm-up
+    t0 = time.perf_counter()
+    _, steps, _ = orc.cg_solve(A, J, rhs, prec=0.0, maxsteps=iters)
+    dt = time.perf_counter() - t0
+    its = steps - 1
+    raw = its / dt
+    nnz = int(rp[-1])
+    b_iter = nnz * 12 + box.ndof * (4 + 8 + 8) + 21 * box.ndof * 8      # reference's unfused sequence
+    return dict(value=raw * nnz / full_nnz, unit=UNIT, cores=cores, kind="port",
+                sample="oracle Jacobi-PCG, %d iterations on the %.2fM-dof system of the same family (%d^3 cubes): %.1f it/s "
+                       "= %.1f GB/s of the reference's per-iteration traffic; scaled by nnz ratio %.4g to the full size"
+                       % (its, box.ndof / 1e6, SAMPLE_M, raw, raw * b_iter / 1e9, nnz / full_nnz),
+                raw_iterations_per_s=raw, sample_ndof=box.ndof, sample_nnz=nnz)
+
+
+def full_sizes(m):
+    """(ndof, nnz) of the full single-box system without assembling it: row pointers of the sample
+    family are cheap, but for the full size use the generator's count on a small box and scale?  No:
+    ask the generator itself (row-pointer pass only is O(ndof) on the host, too slow at 100 M), so
+    use the closed forms: ndof = (3m+1)^3; nnz from the entity stencils = measured by the GPU arm and
+    cached next to this file, else estimated from the sample's nnz/dof."""
+    ndof = (3 * m + 1) ** 3
+    cache = os.path.join(ROOT, "profiles", "workload_sizes.json")
+    if os.path.exists(cache):
+        try:
+            d = json.load(open(cache))
+            if str(m) in d:
+                return ndof, int(d[str(m)])
+        except Exception:
+            pass
+    return ndof, None
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from ngsolve_b200 import workloads as W
+    m = args.size
+    ndof, nnz = full_sizes(m)
+    if nnz is None:
+        # nnz per dof of this mesh family is size independent up to surface terms: take it from the sample
+        box = W.FemBox(SAMPLE_M, order=3)
+        rp = np.empty(box.ndof + 1, dtype=np.uint64)
+        W.check(W._lib().ngsb_femgen_host(box.handle, rp.ctypes.data, None, None, None))
+        nnz = int(int(rp[-1]) / box.ndof * ndof)
+    iters = max(1, args.steps)
+    t0 = time.perf_counter()
+    base = cpu_cg(iters + args.warmup, nnz, ndof)
+    dt = time.perf_counter() - t0
+    line = {
+        "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 / base["value"], "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(m), "global_dofs": ndof, "nnz": nnz, "precond": "Jacobi (freedofs-masked)",
+                   "note": "CPU arm = oracle port of the reference path (NGSolve needs cmake+netgen: unbuildable on the box), "
+                           "timed on a bounded sample and scaled by nnz"},
+        "cpu_baseline": base,
+        "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": dt,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                pass
+
+    def summary(self, t0, t1):
+        rows = [r for (t, r) in self.rows if t0 <= t <= t1 and len(r) >= 7] or [r for (_, r) in self.rows if len(r) >= 7]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[0]) for r in rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(r[3 + k].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]), "power_w_max": max(float(r[2]) for r in rows),
+                "samples": len(rows), "reasons": reasons}
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import ctypes as C
+    from ngsolve_b200 import la, workloads as W, _capi
+    from ngsolve_b200 import parallel as par
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit("bench.py: --gpus %d but WORLD_SIZE=%d (launch with torch.distributed.run)" % (args.gpus, world))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = la.Context(local_rank)
+    m, K, Wm = args.size, args.steps, args.warmup
+    G = (m, m, m)
+    t_setup = time.perf_counter()
+    if world == 1:
+        box = W.FemBox(G, order=3)
+        A, f = box.device_system(ctx)
+        jac = A.CreateSmoother(box.freedofs())
+        solver = None
+    else:
+        n, off = W.slab_partition(G, world)[rank]
+        boxes = [W.FemBox(nn, order=3, offset=oo, global_n=G) for nn, oo in W.slab_partition(G, world)]
+        box = boxes[rank]
+        A, f = box.device_system(ctx)
+        comm = par.Communicator(ctx, world, rank, dist)
+        pd = par.ParallelDofs(*W.exchange_tables(boxes, rank), ndof=box.ndof, nranks=world, rank=rank)
+        pmat = par.ParallelMatrix(A, pd, comm)
+        jac = pmat.CreateSmoother(box.freedofs())
+        solver = pmat
+    ctx.sync()
+    setup_s = time.perf_counter() - t_setup
+    nnz_local, ndof_local = A.nze, A.height
+    counts = torch.tensor([nnz_local, ndof_local], dtype=torch.int64, device="cuda")
+    if world > 1:
+        dist.all_reduce(counts)
+    nnz_sum = int(counts[0].item())
+    global_ndof = box.global_ndof
+
+    stream = torch.cuda.ExternalStream(ctx.stream)
+
+    def barrier():
+        ctx.sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    u = f.CreateVector()
+
+    def solve(maxsteps, prec=0.0):
+        if world == 1:
+            inv = la.CGSolver(A, jac, precision=prec, maxsteps=maxsteps)
+            inv.Mult(f, u)
+            return inv
+        return pmat.cg_solve(jac, f, u, precision=prec, maxsteps=maxsteps)
+
+    def timed(fn):
+        """fn() between CUDA events on the library's stream, barrier + sync on both sides; ms, max over ranks"""
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(stream)
+        out = fn()
+        e1.record(stream)
+        barrier()
+        t1 = time.perf_counter()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), out, (t0, t1)
+
+    # ---- warm-up (W iterations; also builds the CUDA graph of a batch) then the timed K iterations
+    solve(max(Wm, 3))
+    solve(K)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    l0 = ctx.launches
+    ms, inv, span = timed(lambda: solve(K))
+    launches = ctx.launches - l0
+    its = inv.GetSteps() - 1
+    assert its == K, "CG stopped after %d of %d iterations" % (its, K)
+    value = its / (ms * 1e-3)
+
+    # ---- roofline of the dominant kernel: same K iterations with an event pair around every launch
+    ctx.set_option("timing", 1)
+    ctx.kernel_time_reset()
+    solve(K)
+    spmv_ms, spmv_n = ctx.kernel_time("spmv")
+    upd_ms, upd_n = ctx.kernel_time("cgupdate")
+    all_ms, all_n = ctx.kernel_time("all")
+    ctx.kernel_time_reset()
+    ctx.set_option("timing", 0)
+    b_spmv = A.MultBytes()                                  # nnz*12 + 4h + 8h + 8h
+    t_spmv = spmv_ms / max(1, spmv_n) * 1e-3
+    achieved = b_spmv / t_spmv / 1e9
+    peaks = {}
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        peaks = json.load(open(pk))
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
+
+    # ---- e2e: the C-ABI call a script's `gfu.vec.data = inv * f.vec` makes, host buffers, copies timed
+    e2e = None
+    if world == 1:
+        f_host = torch.empty(ndof_local, dtype=torch.float64, pin_memory=True)
+        u_host = torch.empty(ndof_local, dtype=torch.float64, pin_memory=True)
+        f_host.copy_(torch.from_numpy(f.NumPy()))
+        steps_c, nh_c = C.c_int(), C.c_int()
+
+        def host_call():
+            _capi.check(_capi.lib().ngsb_cg_solve_host(A.handle, jac.handle, f_host.data_ptr(), u_host.data_ptr(), 0.0, K, 0,
+                                                       C.byref(steps_c), None, 0, C.byref(nh_c)))
+        host_call()
+        t0 = time.perf_counter()
+        host_call()
+        dt = time.perf_counter() - t0            # wall clock: the call returns after the D2H copy completed
+        assert steps_c.value - 1 == K
+        e2e = {"value": K / dt, "unit": UNIT, "h2d_bytes_per_step": ndof_local * 8 / K, "d2h_bytes_per_step": ndof_local * 8 / K,
+               "note": "ngsb_cg_solve_host: f (pinned host) -> device, %d iterations, u -> pinned host; bytes are per call / %d" % (K, K)}
+    else:
+        f_host = torch.from_numpy(f.NumPy()).pin_memory()
+        u_host = torch.empty_like(f_host).pin_memory()
+        fv = la.BaseVector(ndof_local, ctx=ctx)
+
+        def host_call():
+            _capi.check(_capi.lib().ngsb_vec_h2d(fv.handle, f_host.data_ptr(), 0, ndof_local))
+            r = pmat.cg_solve(jac, fv, u, precision=0.0, maxsteps=K)
+            _capi.check(_capi.lib().ngsb_vec_d2h(u.handle, u_host.data_ptr(), 0, ndof_local))
+            return r
+        host_call()
+        barrier()
+        t0 = time.perf_counter()
+        host_call()
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": K / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": ndof_local * 8 / K,
+               "d2h_bytes_per_step": ndof_local * 8 / K, "note": "per rank: local f host->device, distributed CG, local u device->host"}
+
+    # ---- a full solve to the reference's default tolerance (not the timed number; shows convergence)
+    full = None
+    if not args.no_full_solve:
+        msf, invf, _ = timed(lambda: solve(20000, 1e-8))
+        hist = invf.history
+        full = {"precision": 1e-8, "steps": invf.GetSteps(), "seconds": msf * 1e-3,
+                "wdn_reduction": float(hist[-1] / hist[0]) if len(hist) > 1 and hist[0] > 0 else None}
+    if rank == 0:
+        sampler.stop()
+    clocks = sampler.summary(*span) if rank == 0 else None
+
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        cpu = cpu_cg(args.cpu_iters, nnz_sum, global_ndof)
+    if rank == 0:
+        if world == 1:
+            try:
+                cache = os.path.join(ROOT, "profiles", "workload_sizes.json")
+                d = json.load(open(cache)) if os.path.exists(cache) else {}
+                d[str(m)] = nnz_sum
+                json.dump(d, open(cache, "w"))
+            except Exception:
+                pass
+        b_cg = b_spmv + 11 * ndof_local * 8
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(Wm, 3), "ms_per_step": ms / K,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(m), "global_dofs": global_ndof, "nnz_total": nnz_sum, "rows_per_gpu": ndof_local,
+                       "precond": "Jacobi (freedofs-masked)", "partition": "1 box" if world == 1 else "%d z-slabs of elements, NCCL halo" % world,
+                       "l2": "inputs (%.1f GB per GPU) far larger than the 126 MB L2" % (b_spmv / 1e9),
+                       "setup_s": setup_s, "full_solve": full,
+                       "cg_gbs_per_gpu": b_cg * value / 1e9, "cg_bytes_per_iteration_per_gpu": b_cg,
+                       "spmv_pct_of_8TBs": achieved / 8000.0 * 100.0},
+            "roofline": {"bound": "hbm", "kernel": "spmv_stream_kernel (CSR SpMV + fused <s,As>)", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": b_spmv, "avg_launch_ms": t_spmv * 1e3, "launches_timed": spmv_n,
+                         "kernel_share_of_step": spmv_ms / all_ms if all_ms else None,
+                         "cg_update_kernels_ms_per_iteration": upd_ms / K},
+            "cpu_baseline": cpu,
+            "e2e": e2e,
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

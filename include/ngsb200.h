@@ -201,6 +201,9 @@ int ngsb_parmat_create(ngsb_comm *comm, const ngsb_csr *local, const uint64_t *e
 int ngsb_parmat_destroy(ngsb_parmat *P);
 /* masterdofs bytes as the reference derives them (lowest rank owns), n entries */
 int ngsb_parmat_masterdofs(const ngsb_parmat *P, uint8_t *ismaster);
+/* JacobiPrecond of a ParallelMatrix: diagonal summed over the sharing ranks, then inverted
+ * (AllReduceDofData(invdiag, SUM), linalg/jacobi.cpp:60-61); collective over the communicator */
+int ngsb_parmat_jacobi_create(const ngsb_parmat *P, const uint8_t *freebits, ngsb_jacobi **out);
 /* ParallelBaseVector::Cumulate on a DISTRIBUTED vector: neighbour exchange + add */
 int ngsb_parmat_cumulate(const ngsb_parmat *P, ngsb_vec *v);
 /* ParallelMatrix::MultAdd (C2D): x cumulated in, y distributed out */

@@ -80,6 +80,7 @@ PROTOTYPES = {
     "ngsb_parmat_create": [_vp, _vp, _vp, _vp, _pvp],
     "ngsb_parmat_destroy": [_vp],
     "ngsb_parmat_masterdofs": [_vp, _vp],
+    "ngsb_parmat_jacobi_create": [_vp, _vp, _pvp],
     "ngsb_parmat_cumulate": [_vp, _vp],
     "ngsb_parmat_mult": [_vp, _vp, _vp],
     "ngsb_parmat_dot": [_vp, _vp, _vp, _i, C.POINTER(_d)],

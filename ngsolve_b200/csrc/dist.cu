@@ -139,6 +139,28 @@ __global__ void __launch_bounds__(256) unpack_add_kernel(double *__restrict__ v,
     for (int c = 0; c < ES; c++) v[ES * dof + c] = acc[c];
 }
 
+// run-time entry size versions (setup only: the 9-double diagonal blocks of the Jacobi ctor)
+__global__ void pack_rt_kernel(const double *__restrict__ v, const int32_t *__restrict__ exdofs, double *__restrict__ send, size_t nex, int es)
+{
+    size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nex) return;
+    const size_t dof = (size_t)exdofs[k];
+    for (int c = 0; c < es; c++) send[es * k + c] = v[es * dof + c];
+}
+
+__global__ void unpack_add_rt_kernel(double *__restrict__ v, const int32_t *__restrict__ if_dof, const uint32_t *__restrict__ if_first,
+                                     const uint32_t *__restrict__ if_pos, const double *__restrict__ recv, size_t nif, int es)
+{
+    size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nif) return;
+    const size_t dof = (size_t)if_dof[k];
+    for (int c = 0; c < es; c++) {
+        double acc = v[es * dof + c];
+        for (uint32_t q = if_first[k]; q < if_first[k + 1]; q++) acc += recv[es * (size_t)if_pos[q] + c];
+        v[es * dof + c] = acc;
+    }
+}
+
 static int all_reduce2(ngsb_comm *comm, double *d_buf)
 {
     if (comm->nranks == 1) return NGSB_OK;
@@ -197,9 +219,51 @@ int launch_mask_zero(ngsb_ctx *ctx, double *v, const uint8_t *master, size_t n, 
     return NGSB_OK;
 }
 
+// Cumulate of an array with `es` doubles per dof through temporary buffers (setup path)
+static int cumulate_any(void *arg, double *v, int es)
+{
+    const ngsb_parmat *P = (const ngsb_parmat *)arg;
+    ngsb_comm *comm = P->comm;
+    ngsb_ctx *ctx = comm->ctx;
+    if (P->nex == 0 || comm->nranks == 1) return NGSB_OK;
+    double *send = nullptr, *recv = nullptr;
+    NGSB_CUDA(cudaMalloc(&send, P->nex * es * sizeof(double)));
+    NGSB_CUDA(cudaMalloc(&recv, P->nex * es * sizeof(double)));
+    pack_rt_kernel<<<(unsigned)((P->nex + 255) / 256), 256, 0, ctx->stream>>>(v, P->d_exdofs, send, P->nex, es);
+    ctx->launches += 3;
+    int rc = NGSB_OK;
+    do {
+        ncclResult_t r = g_nccl.GroupStart();
+        for (size_t q = 0; q < P->peers.size() && r == ncclSuccess; q++) {
+            const size_t off = P->peer_off[q] * es, cnt = (P->peer_off[q + 1] - P->peer_off[q]) * es;
+            r = g_nccl.Send(send + off, cnt, ncclDouble, P->peers[q], comm->comm, ctx->stream);
+            if (r == ncclSuccess) r = g_nccl.Recv(recv + off, cnt, ncclDouble, P->peers[q], comm->comm, ctx->stream);
+        }
+        ncclResult_t r2 = g_nccl.GroupEnd();
+        if (r == ncclSuccess) r = r2;
+        if (r != ncclSuccess) { set_error("Cumulate(diagonal): %s", g_nccl.GetErrorString(r)); rc = NGSB_ERR_COMM; }
+    } while (0);
+    if (rc == NGSB_OK) {
+        unpack_add_rt_kernel<<<(unsigned)((P->nif + 255) / 256), 256, 0, ctx->stream>>>(v, P->d_if_dof, P->d_if_first, P->d_if_pos, recv, P->nif, es);
+        if (cudaGetLastError() != cudaSuccess) rc = NGSB_ERR_CUDA;
+    }
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(send);
+    cudaFree(recv);
+    return rc;
+}
+
 } // namespace ngsb
 
 using namespace ngsb;
+
+// JacobiPrecond on a ParallelMatrix: the diagonal is summed over the sharing ranks before it is
+// inverted (paralleldofs->AllReduceDofData(invdiag, SUM), linalg/jacobi.cpp:60-61)
+extern "C" int ngsb_parmat_jacobi_create(const ngsb_parmat *P, const uint8_t *freebits, ngsb_jacobi **out)
+{
+    NGSB_REQUIRE(P && out, "ngsb_parmat_jacobi_create: NULL argument");
+    return jacobi_build(P->local, freebits, cumulate_any, (void *)P, out);
+}
 
 extern "C" int ngsb_comm_unique_id(void *uid128)
 {

@@ -85,12 +85,16 @@ __device__ int calc_inverse3(double *inv)
     return 0;
 }
 
-// invdiag[i] = inverse(A(i,i)) for i in inner, 0 otherwise (linalg/jacobi.cpp:49-67)
+// JacobiPrecond ctor in two phases (linalg/jacobi.cpp:49-67):
+//   extract: invdiag[i] = A(i,i) for i in inner, TM(0) otherwise   (absent position reads as 0)
+//   [distributed: AllReduceDofData(invdiag, SUM), jacobi.cpp:60-61 -- done by the caller]
+//   invert : CalcInverse(invdiag[i]) for i in inner
 template <int KIND>
-__global__ void __launch_bounds__(256) jacobi_setup_kernel(const uint64_t *__restrict__ rowptr, const int32_t *__restrict__ col,
-                                                          const double *__restrict__ val, const uint8_t *__restrict__ bits,
-                                                          double *__restrict__ invdiag, uint64_t n, int *__restrict__ status)
+__global__ void __launch_bounds__(256) jacobi_extract_kernel(const uint64_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+                                                            const double *__restrict__ val, const uint8_t *__restrict__ bits,
+                                                            double *__restrict__ invdiag, uint64_t n, int *__restrict__ status)
 {
+    constexpr int MS = KIND == NGSB_REAL ? 1 : (KIND == NGSB_COMPLEX ? 2 : 9);
     uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const bool in = bits == nullptr || bit_test(bits, i);
@@ -103,31 +107,40 @@ __global__ void __launch_bounds__(256) jacobi_setup_kernel(const uint64_t *__res
             if ((uint64_t)c == i) { pos = (int64_t)mid; break; }
             if ((uint64_t)c < i) lo = mid + 1; else hi = mid;
         }
+        if (KIND == NGSB_BLOCK3 && in && pos < 0) atomicExch(status, 2);
+#pragma unroll
+        for (int k = 0; k < MS; k++) invdiag[MS * i + k] = (in && pos >= 0) ? val[MS * pos + k] : 0.0;
+    }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(256) jacobi_invert_kernel(const uint8_t *__restrict__ bits, double *__restrict__ invdiag, uint64_t n,
+                                                           int *__restrict__ status)
+{
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        if (!(bits == nullptr || bit_test(bits, i))) continue;
         if (KIND == NGSB_REAL) {
-            invdiag[i] = in ? 1 / (pos >= 0 ? val[pos] : 0.0) : 0.0;
+            invdiag[i] = 1 / invdiag[i];
         } else if (KIND == NGSB_COMPLEX) {
-            double2 o = make_double2(0.0, 0.0);
-            if (in) {
-                double2 a = pos >= 0 ? reinterpret_cast<const double2 *>(val)[pos] : make_double2(0.0, 0.0);
-                if (a.y == 0.0) { o.x = 1.0 / a.x; o.y = 0.0; }
-                else {
-                    double den = a.x * a.x + a.y * a.y;
-                    o.x = a.x / den;
-                    o.y = -a.y / den;
-                }
+            double2 a = reinterpret_cast<double2 *>(invdiag)[i], o;
+            if (a.y == 0.0) { o.x = 1.0 / a.x; o.y = 0.0; }
+            else {
+                double den = a.x * a.x + a.y * a.y;
+                o.x = a.x / den;
+                o.y = -a.y / den;
             }
             reinterpret_cast<double2 *>(invdiag)[i] = o;
         } else {
             double m[9];
-            for (int k = 0; k < 9; k++) m[k] = (in && pos >= 0) ? val[9 * pos + k] : 0.0;
-            if (in) {
-                if (pos < 0) atomicExch(status, 2);
-                else if (calc_inverse3(m) != 0) atomicExch(status, 1);
-            }
+            for (int k = 0; k < 9; k++) m[k] = invdiag[9 * i + k];
+            if (calc_inverse3(m) != 0) atomicExch(status, 1);
             for (int k = 0; k < 9; k++) invdiag[9 * i + k] = m[k];
         }
     }
 }
+
+int jacobi_alloc(ngsb_ctx *ctx, size_t n, int kind, const uint8_t *freebits, ngsb_jacobi **out);
 
 static int grid_for_n(ngsb_ctx *ctx, uint64_t n)
 {
@@ -159,7 +172,7 @@ int jacobi_apply(const ngsb_jacobi *J, double sr, double si, const double *x, do
 
 using namespace ngsb;
 
-static int jacobi_alloc(ngsb_ctx *ctx, size_t n, int kind, const uint8_t *freebits, ngsb_jacobi **out)
+int ngsb::jacobi_alloc(ngsb_ctx *ctx, size_t n, int kind, const uint8_t *freebits, ngsb_jacobi **out)
 {
     ngsb_jacobi *J = new ngsb_jacobi();
     J->ctx = ctx;
@@ -192,10 +205,37 @@ extern "C" int ngsb_jacobi_create(ngsb_ctx *ctx, size_t n, const void *invdiag, 
     return NGSB_OK;
 }
 
-extern "C" int ngsb_jacobi_create_from_csr(const ngsb_csr *A, const uint8_t *freebits, ngsb_jacobi **out)
+namespace ngsb {
+// phase 1 / phase 2 of the JacobiPrecond ctor on an allocated J (shared with dist.cu)
+int jacobi_extract(const ngsb_csr *A, ngsb_jacobi *J, int *d_status)
 {
-    NGSB_REQUIRE(A && out, "ngsb_jacobi_create_from_csr: NULL argument");
-    NGSB_REQUIRE(A->h == A->w, "ngsb_jacobi_create_from_csr: matrix must be square");
+    ngsb_ctx *ctx = A->ctx;
+    if (A->h == 0) return NGSB_OK;
+    SpanGuard g(ctx, KC_OTHER);
+    int grid = grid_for_n(ctx, A->h);
+    if (A->kind == NGSB_REAL) jacobi_extract_kernel<NGSB_REAL><<<grid, 256, 0, ctx->stream>>>(A->d_rowptr, A->d_col, A->d_val, J->d_bits, J->d_invdiag, A->h, d_status);
+    else if (A->kind == NGSB_COMPLEX) jacobi_extract_kernel<NGSB_COMPLEX><<<grid, 256, 0, ctx->stream>>>(A->d_rowptr, A->d_col, A->d_val, J->d_bits, J->d_invdiag, A->h, d_status);
+    else jacobi_extract_kernel<NGSB_BLOCK3><<<grid, 256, 0, ctx->stream>>>(A->d_rowptr, A->d_col, A->d_val, J->d_bits, J->d_invdiag, A->h, d_status);
+    NGSB_CUDA(cudaGetLastError());
+    return NGSB_OK;
+}
+
+int jacobi_invert(ngsb_jacobi *J, int *d_status)
+{
+    ngsb_ctx *ctx = J->ctx;
+    if (J->n == 0) return NGSB_OK;
+    SpanGuard g(ctx, KC_OTHER);
+    int grid = grid_for_n(ctx, J->n);
+    if (J->kind == NGSB_REAL) jacobi_invert_kernel<NGSB_REAL><<<grid, 256, 0, ctx->stream>>>(J->d_bits, J->d_invdiag, J->n, d_status);
+    else if (J->kind == NGSB_COMPLEX) jacobi_invert_kernel<NGSB_COMPLEX><<<grid, 256, 0, ctx->stream>>>(J->d_bits, J->d_invdiag, J->n, d_status);
+    else jacobi_invert_kernel<NGSB_BLOCK3><<<grid, 256, 0, ctx->stream>>>(J->d_bits, J->d_invdiag, J->n, d_status);
+    NGSB_CUDA(cudaGetLastError());
+    return NGSB_OK;
+}
+
+// cumulate: optional hook between the phases (distributed: neighbour exchange + add of the diagonal)
+int jacobi_build(const ngsb_csr *A, const uint8_t *freebits, int (*cumulate)(void *, double *, int), void *cum_arg, ngsb_jacobi **out)
+{
     ngsb_ctx *ctx = A->ctx;
     NGSB_CUDA(cudaSetDevice(ctx->device));
     ngsb_jacobi *J = nullptr;
@@ -203,25 +243,31 @@ extern "C" int ngsb_jacobi_create_from_csr(const ngsb_csr *A, const uint8_t *fre
     int *d_status = nullptr;
     NGSB_CUDA(cudaMalloc(&d_status, sizeof(int)));
     NGSB_CUDA(cudaMemsetAsync(d_status, 0, sizeof(int), ctx->stream));
-    if (A->h) {
-        SpanGuard g(ctx, KC_OTHER);
-        int grid = grid_for_n(ctx, A->h);
-        if (A->kind == NGSB_REAL) jacobi_setup_kernel<NGSB_REAL><<<grid, 256, 0, ctx->stream>>>(A->d_rowptr, A->d_col, A->d_val, J->d_bits, J->d_invdiag, A->h, d_status);
-        else if (A->kind == NGSB_COMPLEX) jacobi_setup_kernel<NGSB_COMPLEX><<<grid, 256, 0, ctx->stream>>>(A->d_rowptr, A->d_col, A->d_val, J->d_bits, J->d_invdiag, A->h, d_status);
-        else jacobi_setup_kernel<NGSB_BLOCK3><<<grid, 256, 0, ctx->stream>>>(A->d_rowptr, A->d_col, A->d_val, J->d_bits, J->d_invdiag, A->h, d_status);
-        NGSB_CUDA(cudaGetLastError());
-    }
+    int rc = jacobi_extract(A, J, d_status);
+    if (rc == NGSB_OK && cumulate) rc = cumulate(cum_arg, J->d_invdiag, (int)kind_matscalars(A->kind));
+    if (rc == NGSB_OK) rc = jacobi_invert(J, d_status);
     int status = 0;
-    NGSB_CUDA(cudaMemcpyAsync(&status, d_status, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    NGSB_CUDA(cudaStreamSynchronize(ctx->stream));
-    cudaFree(d_status);
-    if (status == 1) {   // reference: Exception("Inverse matrix: Matrix singular"), calcinverse.cpp:58
-        ngsb_jacobi_destroy(J);
-        set_error("Inverse matrix: Matrix singular");
-        return NGSB_ERR_INVALID;
+    if (rc == NGSB_OK) {
+        cudaError_t e = cudaMemcpyAsync(&status, d_status, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { set_error("JacobiPrecond: %s", cudaGetErrorString(e)); rc = NGSB_ERR_CUDA; }
     }
+    cudaFree(d_status);
+    if (rc == NGSB_OK && status == 1) {   // reference: Exception("Inverse matrix: Matrix singular"), calcinverse.cpp:58
+        set_error("Inverse matrix: Matrix singular");
+        rc = NGSB_ERR_INVALID;
+    }
+    if (rc != NGSB_OK) { ngsb_jacobi_destroy(J); return rc; }
     *out = J;
     return NGSB_OK;
+}
+} // namespace ngsb
+
+extern "C" int ngsb_jacobi_create_from_csr(const ngsb_csr *A, const uint8_t *freebits, ngsb_jacobi **out)
+{
+    NGSB_REQUIRE(A && out, "ngsb_jacobi_create_from_csr: NULL argument");
+    NGSB_REQUIRE(A->h == A->w, "ngsb_jacobi_create_from_csr: matrix must be square");
+    return jacobi_build(A, freebits, nullptr, nullptr, out);
 }
 
 extern "C" int ngsb_jacobi_destroy(ngsb_jacobi *J)

@@ -12,4 +12,7 @@ struct ngsb_jacobi {
 
 namespace ngsb {
 int jacobi_apply(const ngsb_jacobi *J, double sr, double si, const double *x, double *y, bool accumulate);
+// JacobiPrecond ctor; `cumulate(arg, diag, doubles_per_entry)` (may be NULL) runs between extracting the
+// diagonal and inverting it (AllReduceDofData of the distributed case, linalg/jacobi.cpp:60-61)
+int jacobi_build(const ngsb_csr *A, const uint8_t *freebits, int (*cumulate)(void *, double *, int), void *cum_arg, ngsb_jacobi **out);
 }

@@ -686,6 +686,25 @@ static int validate_host_csr(size_t h, size_t w, size_t nnz, const uint64_t *row
     return NGSB_OK;
 }
 
+// take ownership of device CSR arrays (allocated with >= 16 entries of zeroed slack behind nnz)
+int csr_adopt_device(ngsb_ctx *ctx, size_t h, size_t w, size_t nnz, uint64_t *d_rowptr, int32_t *d_col, double *d_val, int kind,
+                     ngsb_csr **out)
+{
+    NGSB_REQUIRE(ctx && d_rowptr && d_col && d_val && out, "csr_adopt_device: NULL argument");
+    NGSB_REQUIRE(w < (1ull << 31) && h < (1ull << 32) - 1024, "csr_adopt_device: dimensions exceed 32-bit indices");
+    std::vector<uint64_t> h_rowptr(h + 1);
+    NGSB_CUDA(cudaMemcpyAsync(h_rowptr.data(), d_rowptr, (h + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    NGSB_CUDA(cudaStreamSynchronize(ctx->stream));
+    NGSB_REQUIRE(h_rowptr[0] == 0 && h_rowptr[h] == nnz, "csr_adopt_device: rowptr inconsistent with nnz");
+    ngsb_csr *A = new ngsb_csr();
+    A->ctx = ctx; A->h = h; A->w = w; A->nnz = nnz; A->kind = kind;
+    A->d_rowptr = d_rowptr; A->d_col = d_col; A->d_val = d_val;
+    int rc = finish_create(A, h_rowptr.data());
+    if (rc != NGSB_OK) { A->d_rowptr = nullptr; A->d_col = nullptr; A->d_val = nullptr; ngsb_csr_destroy(A); return rc; }
+    *out = A;
+    return NGSB_OK;
+}
+
 } // namespace ngsb
 
 using namespace ngsb;

@@ -124,6 +124,8 @@ def _freebits(freedofs):
 class _Expr:
     """sum of terms  s * v   or   s * (M * v)."""
 
+    __array_ufunc__ = None          # numpy scalars defer to __rmul__ instead of broadcasting
+
     def __init__(self, terms):
         self.terms = terms          # list of (scalar, matrix or None, BaseVector)
 
@@ -216,6 +218,8 @@ class _DataProxy:
 class BaseVector:
     """Device vector with a host mirror and dirty flags: UnifiedVector,
     ngscuda/unifiedvector.hpp:8-98 (host_uptodate / dev_uptodate, UpdateHost / UpdateDevice)."""
+
+    __array_ufunc__ = None
 
     def __init__(self, arg, complex=False, entrysize=1, ctx=None, _handle=None, _parent=None):
         self.ctx = ctx or default_context()
@@ -452,6 +456,7 @@ class BaseMatrix:
     is_complex = False
     entrysize = 1
     ctx = None
+    __array_ufunc__ = None
 
     def Height(self):
         return self.height
@@ -496,11 +501,33 @@ class BaseMatrix:
             return _Expr([(1.0, self, x.Evaluate())])
         return NotImplemented
 
+    def __rmul__(self, s):
+        return _ScaledMatrix(s, self)       # VScaleMatrix, linalg/basematrix.hpp
+
     def _check(self, x, y, who):
         if x.size != self.Width():
             raise NgsbError("%s: width of matrix = %d != size of x = %d" % (who, self.Width(), x.size))
         if y.size != self.Height():
             raise NgsbError("%s: height of matrix = %d != size of y = %d" % (who, self.Height(), y.size))
+
+
+class _ScaledMatrix(BaseMatrix):
+    def __init__(self, s, m):
+        self.s, self.m = s, m
+        self.is_complex, self.entrysize, self.ctx = m.is_complex, m.entrysize, m.ctx
+
+    def Height(self):
+        return self.m.Height()
+
+    def Width(self):
+        return self.m.Width()
+
+    def Mult(self, x, y):
+        y.SetScalar(0.0)
+        self.m.MultAdd(self.s, x, y)
+
+    def MultAdd(self, s, x, y):
+        self.m.MultAdd(s * self.s, x, y)
 
 
 class SparseMatrix(BaseMatrix):

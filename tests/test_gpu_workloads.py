@@ -1,0 +1,97 @@
+"""GPU: the device assembly of the synthetic FE systems against the library's host loop (bit for
+bit), and size-independent properties of the solve path on systems far beyond what the oracle can
+check entry by entry (linearity, symmetry, constants in the kernel, CG against the oracle at a
+mid size)."""
+import numpy as np
+import pytest
+
+from oracle import pyoracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def mods():
+    import ngsolve_b200.la as la
+    from ngsolve_b200 import workloads as W
+    la.default_context()
+    return la, W
+
+
+@pytest.mark.parametrize("order,kind,n", [(3, 0, (7, 5, 6)), (4, 0, (3, 4, 3)), (2, 3, (5, 5, 4)), (4, 3, (3, 3, 3)), (3, 1, (4, 6, 5)), (1, 0, (9, 9, 9))])
+def test_device_assembly_equals_host_assembly(mods, order, kind, n):
+    la, W = mods
+    box = W.FemBox(n, order=order, kind=kind, mass=(0.4 - 0.3j) if kind == 1 else 0.25, lame=(1.2, 0.8))
+    rp, col, val, rhs = box.host_csr()
+    A, f = box.device_system()
+    dval, dcol, drp = A.CSR()
+    assert np.array_equal(drp, rp) and np.array_equal(dcol, col)
+    assert np.array_equal(dval.view(np.float64), val.view(np.float64))
+    assert np.array_equal(f.NumPy().reshape(-1).view(np.float64), rhs.view(np.float64))
+    # and the SpMV of the generated system against the oracle
+    rng = np.random.default_rng(1)
+    es = 3 if kind == 3 else 1
+    xs = rng.standard_normal(box.ndof * es) + (1j * rng.standard_normal(box.ndof * es) if kind == 1 else 0)
+    y = (A * la.BaseVector(xs, entrysize=es)).Evaluate().NumPy().reshape(-1)
+    yref = orc.Csr(rp, col, val, kind).mult(xs)
+    assert np.max(np.abs(y - yref)) <= 1e-12 * np.max(np.abs(yref))
+
+
+def test_cg_matches_oracle_on_generated_poisson(mods):
+    """~0.2 M dofs: the oracle (reference recurrences) finishes in seconds; steps within +-2."""
+    la, W = mods
+    box = W.FemBox(19, order=3)
+    rp, col, val, rhs = box.host_csr()
+    free = box.freedofs()
+    A, f = box.device_system()
+    inv = la.CGSolver(A, A.CreateSmoother(free), precision=1e-8, maxsteps=5000)
+    u = (inv * f).Evaluate().NumPy()
+    oA = orc.Csr(rp, col, val, 0)
+    ou, osteps, ohist = orc.cg_solve(oA, orc.Jacobi(oA, free.bytes), rhs, prec=1e-8, maxsteps=5000)
+    assert abs(inv.GetSteps() - osteps) <= 2, (inv.GetSteps(), osteps)
+    assert np.max(np.abs(u - ou)) <= 1e-6 * np.max(np.abs(ou))
+    k = min(len(ohist), len(inv.history), 30)
+    assert np.allclose(inv.history[:k], ohist[:k], rtol=1e-8)
+    # true residual on the free dofs went down by the requested factor (Dirichlet dofs are never touched)
+    F = np.unpackbits(free.bytes, bitorder="little")[:box.ndof].astype(bool)
+    r = rhs - oA.mult(u)
+    assert np.linalg.norm(r[F]) <= 1e-6 * np.linalg.norm(rhs[F])
+    assert not u[~F].any()
+
+
+@pytest.mark.parametrize("m", [64])
+def test_large_system_properties(mods, m):
+    """7 M dofs / 0.34 G entries (4 GB): properties that do not need an entrywise reference."""
+    la, W = mods
+    box = W.FemBox(m, order=3)
+    A, f = box.device_system()
+    n = box.ndof
+    assert n == (3 * m + 1) ** 3 and A.nze > 46 * n
+    rng = np.random.default_rng(5)
+    x, y = la.BaseVector(rng.standard_normal(n)), la.BaseVector(rng.standard_normal(n))
+    Ax, Ay = (A * x).Evaluate(), (A * y).Evaluate()
+    # symmetry of the assembled operator
+    assert la.InnerProduct(Ax, y) == pytest.approx(la.InnerProduct(x, Ay), rel=1e-10)
+    # linearity
+    z = x.CreateVector()
+    z.data = 2.0 * x - 0.5 * y
+    Az = (A * z).Evaluate()
+    Az.data -= 2.0 * Ax - 0.5 * Ay
+    assert Az.Norm() <= 1e-12 * Ax.Norm()
+    # constants are in the kernel of the stiffness matrix: vertex dofs 1, hierarchical dofs 0
+    c = np.zeros(n)
+    c[:(m + 1) ** 3] = 1.0
+    assert (A * la.BaseVector(c)).Evaluate().Norm() <= 1e-10 * Ax.Norm()
+    # both SpMV kernels agree
+    A.ctx.set_option("spmv_algo", 1)
+    Ax1 = (A * x).Evaluate()
+    A.ctx.set_option("spmv_algo", 0)
+    Ax1.data -= Ax
+    assert Ax1.Norm() <= 1e-13 * Ax.Norm()
+    # Jacobi-CG reduces <d,w> monotonically enough to converge; exact step count checked at small size
+    inv = la.CGSolver(A, A.CreateSmoother(box.freedofs()), precision=1e-6, maxsteps=3000)
+    u = (inv * f).Evaluate()
+    assert 50 < inv.GetSteps() < 3000 and inv.history[-1] <= 1e-12 * inv.history[0]
+    # ngsb_cg_solve_host (host buffers) gives the same answer as the device-vector call
+    uh, steps, _ = la.cg_solve_host(A, A.CreateSmoother(box.freedofs()), f.NumPy(), precision=1e-6, maxsteps=3000)
+    assert steps == inv.GetSteps() and np.array_equal(uh, u.NumPy())
