@@ -73,8 +73,10 @@ int ngsb_ctx_device(const ngsb_ctx *ctx, int *device, int *sm_count);
 void *ngsb_ctx_stream(ngsb_ctx *ctx);                   /* cudaStream_t */
 /* kernels of this library launched on ctx so far (bench.py's gpu_launches) */
 int ngsb_ctx_launch_count(const ngsb_ctx *ctx, uint64_t *count);
-/* tuning knobs: name in {"spmv_algo" (0 auto,1 subwarp,2 tma-stream), "cg_batch",
- * "spmv_ctas_per_sm", "timing"}; unknown names fail with NGSB_ERR_INVALID. */
+/* tuning knobs: "spmv_algo" (0 auto = 3; 1 sub-warp CSR; 2 TMA-streamed CSR; 3 SELL-32),
+ * "cg_batch", "spmv_ctas_per_sm", "timing", and -- read when a matrix is created --
+ * "sell_cap", "spmv_tile", "spmv_ncw", "spmv_stages", "spmv_subwarp" (0 = default).
+ * Unknown names fail with NGSB_ERR_INVALID. */
 int ngsb_ctx_set_option(ngsb_ctx *ctx, const char *name, long value);
 /* device time in ms of the kernels recorded since the last reset for a class
  * ("spmv", "cgupdate", "all"); only meaningful when option "timing" is 1. */
@@ -149,6 +151,9 @@ int ngsb_csr_mult(const ngsb_csr *A, const ngsb_vec *x, ngsb_vec *y);
 int ngsb_csr_reorder(const ngsb_csr *A, const uint64_t *perm, ngsb_csr **out);
 /* copy the device CSR back (pattern parity checks): any pointer may be NULL */
 int ngsb_csr_download(const ngsb_csr *A, uint64_t *rowptr, int32_t *col, void *val);
+/* device layout diagnostics: padded entries of the SELL-32 copy the default SpMV kernel streams,
+ * rows with an overflow part, and the per-row cap of the slices.  Any pointer may be NULL. */
+int ngsb_csr_layout(const ngsb_csr *A, uint64_t *sell_entries, uint32_t *overflow_rows, uint32_t *cap);
 /* algorithmic bytes of one Mult: nnz*(b*b*S+4) + 4*h + 2*N*S */
 int ngsb_csr_mult_bytes(const ngsb_csr *A, double *bytes);
 

@@ -65,6 +65,10 @@ struct ngsb_ctx {
     long spmv_algo = 0;          // 0 auto, 1 subwarp, 2 tma-stream
     long cg_batch = 16;          // iterations enqueued between two polls of the stop flag
     long spmv_ctas_per_sm = 0;   // 0 = kernel default
+    long sell_cap = 0;           // 0 = max(64, 4 * mean row length)
+    long sell_schedule = 1;      // order slices by their smallest first column (locality of the x gathers)
+    long sell_variant = 0;       // inner-loop variant of the real SELL kernel (tuning)
+    long spmv_tile = 0, spmv_ncw = 0, spmv_stages = 0, spmv_subwarp = 0;   // 0 = default; read when a matrix is created
     long timing = 0;
     // reduction workspace (partials + counters), pinned host scratch
     double *d_partials = nullptr;   // 2 * max_partials doubles
@@ -106,6 +110,8 @@ struct SpanGuard {
 };
 
 int stage_reserve(ngsb_ctx *ctx, size_t bytes);
+// in-place inclusive prefix sum of n uint64 on the context's stream
+int device_scan_u64(ngsb_ctx *ctx, uint64_t *d_a, uint64_t n);
 
 // ---- vector kernels (vec.cu), all enqueue on ctx->stream --------------------------------
 int launch_fill(ngsb_ctx *ctx, double *x, size_t N, double re, double im, bool cplx);

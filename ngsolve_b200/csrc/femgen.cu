@@ -137,41 +137,6 @@ __global__ void __launch_bounds__(256) femgen_fill_kernel(const GenTables T, con
     gen_row<true>(T, r, col + p, val + p * T.nv, rhs);
 }
 
-// in-place inclusive scan of rowlen[0..n] (three-phase, chunk per CTA)
-__global__ void __launch_bounds__(256) scan_chunks_kernel(uint64_t *a, uint64_t n, uint64_t chunk, uint64_t *sums)
-{
-    __shared__ uint64_t sh[256];
-    const uint64_t lo = (uint64_t)blockIdx.x * chunk, hi = lo + chunk < n ? lo + chunk : n;
-    const uint64_t per = (chunk + 255) / 256;
-    const uint64_t tlo = lo + threadIdx.x * per < hi ? lo + threadIdx.x * per : hi;
-    const uint64_t thi = tlo + per < hi ? tlo + per : hi;
-    uint64_t s = 0;
-    for (uint64_t i = tlo; i < thi; i++) s += a[i];
-    sh[threadIdx.x] = s;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint64_t run = 0;
-        for (int t = 0; t < 256; t++) { uint64_t v = sh[t]; sh[t] = run; run += v; }
-        sums[blockIdx.x] = run;
-    }
-    __syncthreads();
-    uint64_t run = sh[threadIdx.x];
-    for (uint64_t i = tlo; i < thi; i++) { run += a[i]; a[i] = run; }
-}
-
-__global__ void scan_sums_kernel(uint64_t *sums, int nchunks)
-{
-    uint64_t run = 0;
-    for (int i = 0; i < nchunks; i++) { uint64_t v = sums[i]; sums[i] = run; run += v; }
-}
-
-__global__ void __launch_bounds__(256) scan_add_kernel(uint64_t *a, uint64_t n, uint64_t chunk, const uint64_t *sums)
-{
-    const uint64_t lo = (uint64_t)blockIdx.x * chunk, hi = lo + chunk < n ? lo + chunk : n;
-    const uint64_t add = sums[blockIdx.x];
-    for (uint64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) a[i] += add;
-}
-
 // ------------------------------------------------------------------------------------------
 // host: polynomials in barycentric coordinates, exact integration
 // ------------------------------------------------------------------------------------------
@@ -523,7 +488,7 @@ extern "C" int ngsb_femgen_device(ngsb_ctx *ctx, const ngsb_femgen *g, ngsb_csr 
     NGSB_CUDA(cudaSetDevice(ctx->device));
     GenTables T = g->T;
     void *d_rts = nullptr, *d_tets = nullptr, *d_slots = nullptr, *d_contribs = nullptr, *d_values = nullptr, *d_rhsvals = nullptr;
-    uint64_t *d_rowptr = nullptr, *d_sums = nullptr;
+    uint64_t *d_rowptr = nullptr;
     int32_t *d_col = nullptr;
     double *d_val = nullptr;
     ngsb_vec *fv = nullptr;
@@ -547,17 +512,12 @@ extern "C" int ngsb_femgen_device(ngsb_ctx *ctx, const ngsb_femgen *g, ngsb_csr 
     const uint64_t nd = T.ndof;
     const unsigned grid = (unsigned)((nd + 255) / 256);
     uint64_t nnz = 0;
-    const uint64_t chunk = 1 << 16;
-    const int nchunks = (int)((nd + 1 + chunk - 1) / chunk);
     if (rc == NGSB_OK) fail(cudaMalloc(&d_rowptr, (nd + 1) * sizeof(uint64_t)), "cudaMalloc(rowptr)");
-    if (rc == NGSB_OK) fail(cudaMalloc(&d_sums, (size_t)nchunks * sizeof(uint64_t)), "cudaMalloc(sums)");
     if (rc == NGSB_OK) {
         femgen_count_kernel<<<grid, 256, 0, ctx->stream>>>(T, d_rowptr);
-        scan_chunks_kernel<<<nchunks, 256, 0, ctx->stream>>>(d_rowptr, nd + 1, chunk, d_sums);
-        scan_sums_kernel<<<1, 1, 0, ctx->stream>>>(d_sums, nchunks);
-        scan_add_kernel<<<nchunks, 256, 0, ctx->stream>>>(d_rowptr, nd + 1, chunk, d_sums);
-        ctx->launches += 4;
-        fail(cudaGetLastError(), "count/scan launch");
+        ctx->launches++;
+        fail(cudaGetLastError(), "count launch");
+        if (rc == NGSB_OK) rc = device_scan_u64(ctx, d_rowptr, nd + 1);
         fail(cudaMemcpyAsync(&nnz, d_rowptr + nd, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream), "read nnz");
         fail(cudaStreamSynchronize(ctx->stream), "count/scan");
     }
@@ -573,7 +533,7 @@ extern "C" int ngsb_femgen_device(ngsb_ctx *ctx, const ngsb_femgen *g, ngsb_csr 
         fail(cudaGetLastError(), "fill launch");
         fail(cudaStreamSynchronize(ctx->stream), "fill");
     }
-    cudaFree(d_rts); cudaFree(d_tets); cudaFree(d_slots); cudaFree(d_contribs); cudaFree(d_values); cudaFree(d_rhsvals); cudaFree(d_sums);
+    cudaFree(d_rts); cudaFree(d_tets); cudaFree(d_slots); cudaFree(d_contribs); cudaFree(d_values); cudaFree(d_rhsvals);
     if (rc == NGSB_OK) {
         rc = csr_adopt_device(ctx, nd, nd, nnz, d_rowptr, d_col, d_val, g->desc.kind, A);
         if (rc == NGSB_OK) { d_rowptr = nullptr; d_col = nullptr; d_val = nullptr; }

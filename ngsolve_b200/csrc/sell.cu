@@ -1,0 +1,550 @@
+// sell.cu -- sliced-ELLPACK (SELL-32) SpMV: the default kernel behind SparseMatrix<TM>::MultAdd.
+//
+// Why not vector-CSR: ncu on the sub-warp-per-row CSR kernel (profiles/r1_ncu_spmv_subwarp.txt)
+// shows it bound by the L1TEX data pipe (l1tex__data_pipe_lsu_wavefronts 86 % of peak, DRAM only
+// 64 %): with W lanes per row every warp-wide load touches G = 32/W different rows, so the value
+// and column loads split into G wavefronts each and the x gather into one wavefront per distinct
+// 128-byte line (about 13 for FE rows) -- 0.66 wavefronts per entry, 1 wavefront/clk/SM = 5.1 TB/s
+// ceiling.  Staging the matrix stream through TMA does not change that count.
+//
+// SELL-32 removes the split: a slice is 32 consecutive rows, lane l owns row 32 s + l and walks it
+// sequentially; the slice is stored entry-major ([j][lane]), so one warp-wide load of values
+// (16 B per lane: packets of two entries) or columns is fully coalesced, and because
+// neighbouring dofs of a finite-element numbering couple to neighbouring dofs, the 32 gathers of
+// one step fall into few lines.  Each lane accumulates its row in storage order with one
+// accumulator -- the reference's own summation order (RowTimesVector, linalg/sparsematrix.hpp:
+// 625-632).  Rows are padded to the slice width with (val 0, col = last column of the row); rows
+// longer than `cap` keep their first cap entries in the slice and the rest in a small overflow CSR
+// that a second kernel reduces beforehand.
+//
+// The kernel is persistent (grid = SMs x resident CTAs, 8 slices per CTA step, interleaved so that
+// the CTAs sweep the matrix as one moving window and x lines are shared through L1/L2) and fuses
+// y = s A x (+ y), the dot <dotvec, result> and the CG scalar step (deterministic last-block finish).
+#include "spmv.cuh"
+
+#include <cub/device/device_radix_sort.cuh>
+
+#include <algorithm>
+
+namespace ngsb {
+
+int device_scan_u64(ngsb_ctx *ctx, uint64_t *d_a, uint64_t n);   // vec.cu
+
+struct SellParams {
+    const uint64_t *slice_off;
+    const uint32_t *slice_src;    // slice t of the schedule holds rows 32*slice_src[t] .. +31
+    const int32_t *scol;
+    const double *sval;
+    const int32_t *slice_ovf;     // per slice: first overflow entry of this slice or -1 (NULL: none)
+    const uint32_t *ovf_rows;
+    const double *ovf_sum;        // raw overflow sums, es doubles per overflow row
+    uint32_t novf;
+    uint32_t nslices;
+    uint64_t nrows;
+    const double *x;
+    double *y;
+    double sr, si;
+    int accumulate, epi, dot_conj;
+    const double *dotvec;
+    double *dot_out;
+    CgState *state;
+    double *partials;
+    unsigned int *counter;
+};
+
+__device__ __forceinline__ double2 ldg_stream_d2(const double2 *p)
+{
+    double2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ int2 ldg_stream_i2(const int2 *p)
+{
+    int2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.s32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ double ldg_stream_d(const double *p)
+{
+    double v;
+    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ int ldg_stream_i(const int *p)
+{
+    int v;
+    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
+__device__ __forceinline__ double warp_sum_s(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// VAR (tuning variants of the real-valued inner loop): 0 = 4 packets per step; 1 = 2 packets per step;
+// 2 = 4 packets per step with the next step's values/columns prefetched before the gathers of this one
+template <int KIND, int VAR, int MINB>
+__global__ void __launch_bounds__(256, MINB) sell_spmv_kernel(const SellParams p)
+{
+    __shared__ double red[64];
+    __shared__ int s_last;
+    if (p.state != nullptr && p.state->done) return;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    double dr = 0.0, di = 0.0;
+    for (uint64_t s = (uint64_t)blockIdx.x * 8 + wid; s < p.nslices; s += (uint64_t)gridDim.x * 8) {
+        const uint64_t off = p.slice_off[s];
+        const uint32_t width = (uint32_t)((p.slice_off[s + 1] - off) >> 5);     // entries per lane
+        const uint64_t src = p.slice_src[s];
+        const uint64_t row = src * 32 + lane;
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+        if (KIND == NGSB_REAL) {
+            const double2 *v2 = reinterpret_cast<const double2 *>(p.sval + off) + lane;
+            const int2 *c2 = reinterpret_cast<const int2 *>(p.scol + off) + lane;
+            const uint32_t np = width >> 1;
+            uint32_t q = 0;
+            if (VAR == 2 && np >= 4) {
+                double2 va = ldg_stream_d2(v2), vb = ldg_stream_d2(v2 + 32), vc = ldg_stream_d2(v2 + 64), vd = ldg_stream_d2(v2 + 96);
+                int2 ca = ldg_stream_i2(c2), cb = ldg_stream_i2(c2 + 32), cc = ldg_stream_i2(c2 + 64), cd = ldg_stream_i2(c2 + 96);
+                for (q = 4; q + 4 <= np; q += 4) {
+                    double x0 = __ldg(p.x + ca.x), x1 = __ldg(p.x + ca.y), x2 = __ldg(p.x + cb.x), x3 = __ldg(p.x + cb.y);
+                    double x4 = __ldg(p.x + cc.x), x5 = __ldg(p.x + cc.y), x6 = __ldg(p.x + cd.x), x7 = __ldg(p.x + cd.y);
+                    double2 na = ldg_stream_d2(v2 + (q + 0) * 32), nb = ldg_stream_d2(v2 + (q + 1) * 32);
+                    double2 nc = ldg_stream_d2(v2 + (q + 2) * 32), nd = ldg_stream_d2(v2 + (q + 3) * 32);
+                    int2 ea = ldg_stream_i2(c2 + (q + 0) * 32), eb = ldg_stream_i2(c2 + (q + 1) * 32);
+                    int2 ec = ldg_stream_i2(c2 + (q + 2) * 32), ed = ldg_stream_i2(c2 + (q + 3) * 32);
+                    s0 = fma(va.x, x0, s0); s0 = fma(va.y, x1, s0); s0 = fma(vb.x, x2, s0); s0 = fma(vb.y, x3, s0);
+                    s0 = fma(vc.x, x4, s0); s0 = fma(vc.y, x5, s0); s0 = fma(vd.x, x6, s0); s0 = fma(vd.y, x7, s0);
+                    va = na; vb = nb; vc = nc; vd = nd; ca = ea; cb = eb; cc = ec; cd = ed;
+                }
+                double x0 = __ldg(p.x + ca.x), x1 = __ldg(p.x + ca.y), x2 = __ldg(p.x + cb.x), x3 = __ldg(p.x + cb.y);
+                double x4 = __ldg(p.x + cc.x), x5 = __ldg(p.x + cc.y), x6 = __ldg(p.x + cd.x), x7 = __ldg(p.x + cd.y);
+                s0 = fma(va.x, x0, s0); s0 = fma(va.y, x1, s0); s0 = fma(vb.x, x2, s0); s0 = fma(vb.y, x3, s0);
+                s0 = fma(vc.x, x4, s0); s0 = fma(vc.y, x5, s0); s0 = fma(vd.x, x6, s0); s0 = fma(vd.y, x7, s0);
+            }
+            if (VAR == 1)
+                for (; q + 2 <= np; q += 2) {
+                    double2 va = ldg_stream_d2(v2 + (q + 0) * 32), vb = ldg_stream_d2(v2 + (q + 1) * 32);
+                    int2 ca = ldg_stream_i2(c2 + (q + 0) * 32), cb = ldg_stream_i2(c2 + (q + 1) * 32);
+                    double x0 = __ldg(p.x + ca.x), x1 = __ldg(p.x + ca.y), x2 = __ldg(p.x + cb.x), x3 = __ldg(p.x + cb.y);
+                    s0 = fma(va.x, x0, s0); s0 = fma(va.y, x1, s0); s0 = fma(vb.x, x2, s0); s0 = fma(vb.y, x3, s0);
+                }
+            if (VAR == 0)
+            for (; q + 4 <= np; q += 4) {
+                double2 va = ldg_stream_d2(v2 + (q + 0) * 32), vb = ldg_stream_d2(v2 + (q + 1) * 32);
+                double2 vc = ldg_stream_d2(v2 + (q + 2) * 32), vd = ldg_stream_d2(v2 + (q + 3) * 32);
+                int2 ca = ldg_stream_i2(c2 + (q + 0) * 32), cb = ldg_stream_i2(c2 + (q + 1) * 32);
+                int2 cc = ldg_stream_i2(c2 + (q + 2) * 32), cd = ldg_stream_i2(c2 + (q + 3) * 32);
+                double x0 = __ldg(p.x + ca.x), x1 = __ldg(p.x + ca.y), x2 = __ldg(p.x + cb.x), x3 = __ldg(p.x + cb.y);
+                double x4 = __ldg(p.x + cc.x), x5 = __ldg(p.x + cc.y), x6 = __ldg(p.x + cd.x), x7 = __ldg(p.x + cd.y);
+                s0 = fma(va.x, x0, s0); s0 = fma(va.y, x1, s0); s0 = fma(vb.x, x2, s0); s0 = fma(vb.y, x3, s0);
+                s0 = fma(vc.x, x4, s0); s0 = fma(vc.y, x5, s0); s0 = fma(vd.x, x6, s0); s0 = fma(vd.y, x7, s0);
+            }
+            for (; q < np; q++) {
+                double2 va = ldg_stream_d2(v2 + q * 32);
+                int2 ca = ldg_stream_i2(c2 + q * 32);
+                s0 = fma(va.x, __ldg(p.x + ca.x), s0);
+                s0 = fma(va.y, __ldg(p.x + ca.y), s0);
+            }
+        } else if (KIND == NGSB_COMPLEX) {
+            const double2 *v2 = reinterpret_cast<const double2 *>(p.sval) + off + lane;
+            const int *c1 = p.scol + off + lane;
+            const double2 *x2 = reinterpret_cast<const double2 *>(p.x);
+            uint32_t q = 0;
+            for (; q + 2 <= width; q += 2) {
+                double2 va = ldg_stream_d2(v2 + (q + 0) * 32), vb = ldg_stream_d2(v2 + (q + 1) * 32);
+                int ca = ldg_stream_i(c1 + (q + 0) * 32), cb = ldg_stream_i(c1 + (q + 1) * 32);
+                double2 xa = __ldg(x2 + ca), xb = __ldg(x2 + cb);
+                s0 += va.x * xa.x - va.y * xa.y;
+                s1 += va.x * xa.y + va.y * xa.x;
+                s0 += vb.x * xb.x - vb.y * xb.y;
+                s1 += vb.x * xb.y + vb.y * xb.x;
+            }
+            for (; q < width; q++) {
+                double2 va = ldg_stream_d2(v2 + q * 32);
+                double2 xa = __ldg(x2 + ldg_stream_i(c1 + q * 32));
+                s0 += va.x * xa.x - va.y * xa.y;
+                s1 += va.x * xa.y + va.y * xa.x;
+            }
+        } else {
+            // 3x3 blocks: nine component planes per entry, [j][k][lane]
+            const double *v = p.sval + off * 9 + lane;
+            const int *c1 = p.scol + off + lane;
+            for (uint32_t q = 0; q < width; q++) {
+                const double *m = v + (size_t)q * 9 * 32;
+                const double *xv = p.x + 3 * (size_t)ldg_stream_i(c1 + q * 32);
+                double m0 = ldg_stream_d(m), m1 = ldg_stream_d(m + 32), m2 = ldg_stream_d(m + 64);
+                double m3 = ldg_stream_d(m + 96), m4 = ldg_stream_d(m + 128), m5 = ldg_stream_d(m + 160);
+                double m6 = ldg_stream_d(m + 192), m7 = ldg_stream_d(m + 224), m8 = ldg_stream_d(m + 256);
+                double x0 = __ldg(xv), x1 = __ldg(xv + 1), x2 = __ldg(xv + 2);
+                s0 += m0 * x0 + m1 * x1 + m2 * x2;
+                s1 += m3 * x0 + m4 * x1 + m5 * x2;
+                s2 += m6 * x0 + m7 * x1 + m8 * x2;
+            }
+        }
+        if (p.slice_ovf != nullptr) {
+            int k = p.slice_ovf[src];
+            if (k >= 0)
+                for (; (uint32_t)k < p.novf && (p.ovf_rows[k] >> 5) == src; k++)
+                    if (p.ovf_rows[k] == row) {
+                        if (KIND == NGSB_REAL) s0 += p.ovf_sum[k];
+                        else if (KIND == NGSB_COMPLEX) { s0 += p.ovf_sum[2 * k]; s1 += p.ovf_sum[2 * k + 1]; }
+                        else { s0 += p.ovf_sum[3 * k]; s1 += p.ovf_sum[3 * k + 1]; s2 += p.ovf_sum[3 * k + 2]; }
+                    }
+        }
+        if (row < p.nrows) {
+            // y = s*sum (+ y) and this row's share of the fused dot
+            if (KIND == NGSB_REAL) {
+                double r = p.sr * s0;
+                if (p.accumulate) r += p.y[row];
+                p.y[row] = r;
+                if (p.epi) dr = fma(p.dotvec[row], r, dr);
+            } else if (KIND == NGSB_COMPLEX) {
+                double2 *y2 = reinterpret_cast<double2 *>(p.y);
+                double rr = p.sr * s0 - p.si * s1, ri = p.sr * s1 + p.si * s0;
+                if (p.accumulate) { double2 o = y2[row]; rr += o.x; ri += o.y; }
+                y2[row] = make_double2(rr, ri);
+                if (p.epi) {
+                    double2 v = reinterpret_cast<const double2 *>(p.dotvec)[row];
+                    double ci = p.dot_conj ? -ri : ri;
+                    dr += v.x * rr - v.y * ci;
+                    di += v.x * ci + v.y * rr;
+                }
+            } else {
+                double r0 = p.sr * s0, r1 = p.sr * s1, r2 = p.sr * s2;
+                double *yy = p.y + 3 * row;
+                if (p.accumulate) { r0 += yy[0]; r1 += yy[1]; r2 += yy[2]; }
+                yy[0] = r0; yy[1] = r1; yy[2] = r2;
+                if (p.epi) {
+                    const double *v = p.dotvec + 3 * row;
+                    dr += v[0] * r0 + v[1] * r1 + v[2] * r2;
+                }
+            }
+        }
+    }
+    if (!p.epi) return;
+    // deterministic grid-wide finish of the fused dot (+ scalar step of CG)
+    dr = warp_sum_s(dr);
+    di = warp_sum_s(di);
+    if (lane == 0) { red[wid] = dr; red[32 + wid] = di; }
+    __syncthreads();
+    if (wid == 0) {
+        const int nw = blockDim.x >> 5;
+        dr = lane < nw ? red[lane] : 0.0;
+        di = lane < nw ? red[32 + lane] : 0.0;
+        dr = warp_sum_s(dr);
+        di = warp_sum_s(di);
+        if (lane == 0) {
+            p.partials[2 * blockIdx.x] = dr;
+            p.partials[2 * blockIdx.x + 1] = di;
+            __threadfence();
+            s_last = (atomicAdd(p.counter, 1u) == gridDim.x - 1);
+        }
+    }
+    __syncthreads();
+    if (!s_last || threadIdx.x >= 32) return;
+    __threadfence();
+    double a = 0.0, b = 0.0;
+    for (unsigned int k = threadIdx.x; k < gridDim.x; k += 32) {
+        a += __ldcg(&p.partials[2 * k]);
+        b += __ldcg(&p.partials[2 * k + 1]);
+    }
+    a = warp_sum_s(a);
+    b = warp_sum_s(b);
+    if (threadIdx.x == 0) {
+        *p.counter = 0;
+        if (p.epi == EPI_DOT_OUT) { p.dot_out[0] = a; p.dot_out[1] = b; }
+        else if (p.epi == EPI_CG_KSS) cg_finalize_kss(p.state, make_double2(a, b));
+    }
+}
+
+// overflow part of long rows: one CTA per row, raw sum of val*x over the entries behind `cap`
+template <int KIND>
+__global__ void __launch_bounds__(256) sell_overflow_kernel(const uint64_t *__restrict__ optr, const int32_t *__restrict__ ocol,
+                                                           const double *__restrict__ oval, const double *__restrict__ x,
+                                                           double *__restrict__ osum, const CgState *state)
+{
+    __shared__ double red[3][8];
+    if (state != nullptr && state->done) return;
+    const uint32_t k = blockIdx.x;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    for (uint64_t j = optr[k] + threadIdx.x; j < optr[k + 1]; j += blockDim.x) {
+        const int c = ocol[j];
+        if (KIND == NGSB_REAL) s0 = fma(oval[j], __ldg(x + c), s0);
+        else if (KIND == NGSB_COMPLEX) {
+            double2 v = reinterpret_cast<const double2 *>(oval)[j];
+            double2 xv = __ldg(reinterpret_cast<const double2 *>(x) + c);
+            s0 += v.x * xv.x - v.y * xv.y;
+            s1 += v.x * xv.y + v.y * xv.x;
+        } else {
+            const double *m = oval + 9 * j;
+            const double *xv = x + 3 * (size_t)c;
+            double x0 = __ldg(xv), x1 = __ldg(xv + 1), x2 = __ldg(xv + 2);
+            s0 += m[0] * x0 + m[1] * x1 + m[2] * x2;
+            s1 += m[3] * x0 + m[4] * x1 + m[5] * x2;
+            s2 += m[6] * x0 + m[7] * x1 + m[8] * x2;
+        }
+    }
+    s0 = warp_sum_s(s0); s1 = warp_sum_s(s1); s2 = warp_sum_s(s2);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) { red[0][wid] = s0; red[1][wid] = s1; red[2][wid] = s2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t0 = 0, t1 = 0, t2 = 0;
+        for (int w = 0; w < 8; w++) { t0 += red[0][w]; t1 += red[1][w]; t2 += red[2][w]; }
+        if (KIND == NGSB_REAL) osum[k] = t0;
+        else if (KIND == NGSB_COMPLEX) { osum[2 * k] = t0; osum[2 * k + 1] = t1; }
+        else { osum[3 * k] = t0; osum[3 * k + 1] = t1; osum[3 * k + 2] = t2; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// conversion CSR -> SELL-32 on the device
+// ------------------------------------------------------------------------------------------
+// per slice: padded length (entries) and the schedule key = smallest first column of its rows.  In a
+// finite-element numbering (vertices | edges | faces | cells) every row starts with a vertex dof of
+// its patch, so the key places slices of all entity blocks on one spatial axis.
+__global__ void __launch_bounds__(256) sell_width_kernel(const uint64_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+                                                        uint64_t nrows, uint32_t nslices, uint32_t cap, int even,
+                                                        uint32_t *__restrict__ slice_len, uint32_t *__restrict__ slice_key)
+{
+    const uint64_t s = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (s >= nslices) return;
+    const uint64_t row = s * 32 + lane;
+    uint32_t len = 0, key = 0xffffffffu;
+    if (row < nrows) {
+        const uint64_t a = rowptr[row];
+        uint64_t l = rowptr[row + 1] - a;
+        len = l > cap ? cap : (uint32_t)l;
+        key = l > 0 ? (uint32_t)col[a] : (uint32_t)row;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        len = max(len, __shfl_xor_sync(0xffffffffu, len, o));
+        key = min(key, __shfl_xor_sync(0xffffffffu, key, o));
+    }
+    if (even) len = (len + 1u) & ~1u;
+    if (lane == 0) { slice_len[s] = len * 32u; slice_key[s] = key; }
+}
+
+// slice_off[t+1] = padded entries of the slice scheduled at position t (then scanned in place)
+__global__ void __launch_bounds__(256) sell_gather_len_kernel(const uint32_t *__restrict__ slice_len, const uint32_t *__restrict__ slice_src,
+                                                             uint32_t nslices, uint64_t *__restrict__ slice_off)
+{
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < nslices) slice_off[t + 1] = slice_len[slice_src[t]];
+    if (t == 0) slice_off[0] = 0;
+}
+
+__global__ void __launch_bounds__(256) iota_kernel(uint32_t *a, uint32_t n)
+{
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) a[t] = t;
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(256) sell_fill_kernel(const uint64_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+                                                       const double *__restrict__ val, uint64_t nrows, uint32_t nslices, uint32_t cap,
+                                                       const uint64_t *__restrict__ slice_off, const uint32_t *__restrict__ slice_src,
+                                                       int32_t *__restrict__ scol, double *__restrict__ sval)
+{
+    const uint64_t s = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (s >= nslices) return;
+    const uint64_t off = slice_off[s];
+    const uint32_t width = (uint32_t)((slice_off[s + 1] - off) >> 5);
+    const uint64_t row = (uint64_t)slice_src[s] * 32 + lane;
+    uint64_t a = 0;
+    uint32_t len = 0;
+    if (row < nrows) {
+        a = rowptr[row];
+        uint64_t l = rowptr[row + 1] - a;
+        len = l > cap ? cap : (uint32_t)l;
+    }
+    const int32_t padcol = len > 0 ? col[a + len - 1] : 0;
+    for (uint32_t j = 0; j < width; j++) {
+        const bool real = j < len;
+        const int32_t c = real ? col[a + j] : padcol;
+        if (KIND == NGSB_REAL) {
+            const uint64_t pos = off + ((uint64_t)(j >> 1) * 32 + lane) * 2 + (j & 1);
+            scol[pos] = c;
+            sval[pos] = real ? val[a + j] : 0.0;
+        } else if (KIND == NGSB_COMPLEX) {
+            const uint64_t pos = off + (uint64_t)j * 32 + lane;
+            scol[pos] = c;
+            sval[2 * pos] = real ? val[2 * (a + j)] : 0.0;
+            sval[2 * pos + 1] = real ? val[2 * (a + j) + 1] : 0.0;
+        } else {
+            scol[off + (uint64_t)j * 32 + lane] = c;
+#pragma unroll
+            for (int k = 0; k < 9; k++) sval[off * 9 + ((uint64_t)j * 9 + k) * 32 + lane] = real ? val[9 * (a + j) + k] : 0.0;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) sell_ovf_copy_kernel(const uint64_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+                                                           const double *__restrict__ val, const uint32_t *__restrict__ orows,
+                                                           const uint64_t *__restrict__ optr, uint32_t cap, int ms,
+                                                           int32_t *__restrict__ ocol, double *__restrict__ oval)
+{
+    const uint32_t k = blockIdx.x;
+    const uint64_t src = rowptr[orows[k]] + cap, n = optr[k + 1] - optr[k], dst = optr[k];
+    for (uint64_t j = threadIdx.x; j < n; j += blockDim.x) {
+        ocol[dst + j] = col[src + j];
+        for (int c = 0; c < ms; c++) oval[(dst + j) * ms + c] = val[(src + j) * ms + c];
+    }
+}
+
+int sell_build(ngsb_csr *A, const uint64_t *h_rowptr)
+{
+    ngsb_ctx *ctx = A->ctx;
+    const size_t ms = kind_matscalars(A->kind);
+    A->nslices = (uint32_t)((A->h + 31) / 32);
+    // rows longer than cap keep their tail in the overflow CSR
+    uint32_t cap = (uint32_t)std::max<double>(64.0, 4.0 * A->mean_row + 0.5);
+    if (ctx->sell_cap > 0) cap = (uint32_t)ctx->sell_cap;
+    cap = (cap + 1u) & ~1u;
+    A->sell_cap = cap;
+    std::vector<uint32_t> orows;
+    std::vector<uint64_t> optr(1, 0);
+    std::vector<int32_t> slice_ovf;
+    for (size_t r = 0; r < A->h; r++) {
+        const uint64_t len = h_rowptr[r + 1] - h_rowptr[r];
+        if (len > cap) {
+            if (slice_ovf.empty()) slice_ovf.assign(A->nslices, -1);
+            if (slice_ovf[r >> 5] < 0) slice_ovf[r >> 5] = (int32_t)orows.size();
+            orows.push_back((uint32_t)r);
+            optr.push_back(optr.back() + (len - cap));
+        }
+    }
+    A->novf = (uint32_t)orows.size();
+    NGSB_CUDA(cudaMalloc(&A->d_slice_off, ((size_t)A->nslices + 1) * sizeof(uint64_t)));
+    NGSB_CUDA(cudaMalloc(&A->d_slice_src, std::max<size_t>(1, A->nslices) * sizeof(uint32_t)));
+    if (A->nslices) {
+        const uint32_t ns = A->nslices;
+        const unsigned grid = (unsigned)(((uint64_t)ns * 32 + 255) / 256), grid1 = (ns + 255) / 256;
+        uint32_t *d_len = nullptr, *d_key = nullptr, *d_key2 = nullptr, *d_id = nullptr;
+        void *d_tmp = nullptr;
+        auto cleanup = [&]() { cudaFree(d_len); cudaFree(d_key); cudaFree(d_key2); cudaFree(d_id); cudaFree(d_tmp); };
+        cudaError_t e1 = cudaMalloc(&d_len, ns * sizeof(uint32_t));
+        if (e1 == cudaSuccess) e1 = cudaMalloc(&d_key, ns * sizeof(uint32_t));
+        if (e1 == cudaSuccess) e1 = cudaMalloc(&d_key2, ns * sizeof(uint32_t));
+        if (e1 == cudaSuccess) e1 = cudaMalloc(&d_id, ns * sizeof(uint32_t));
+        if (e1 != cudaSuccess) { cleanup(); set_error("SELL build: %s", cudaGetErrorString(e1)); return NGSB_ERR_NOMEM; }
+        sell_width_kernel<<<grid, 256, 0, ctx->stream>>>(A->d_rowptr, A->d_col, A->h, ns, cap, A->kind == NGSB_REAL ? 1 : 0, d_len, d_key);
+        iota_kernel<<<grid1, 256, 0, ctx->stream>>>(d_id, ns);
+        // 3x3 blocks: measured slower with the schedule on B200 (x is a small share of the traffic), keep natural order
+        const bool schedule = ctx->sell_schedule == 1 ? A->kind != NGSB_BLOCK3 : ctx->sell_schedule == 2;
+        if (schedule) {
+            // schedule: slices ordered by key (stable radix sort keeps the natural order among equal keys)
+            size_t tmp_bytes = 0;
+            cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_key, d_key2, d_id, A->d_slice_src, (int)ns, 0, 32, ctx->stream);
+            e1 = cudaMalloc(&d_tmp, tmp_bytes);
+            if (e1 == cudaSuccess) e1 = cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_key, d_key2, d_id, A->d_slice_src, (int)ns, 0, 32, ctx->stream);
+        } else {
+            e1 = cudaMemcpyAsync(A->d_slice_src, d_id, ns * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream);
+        }
+        if (e1 == cudaSuccess) {
+            sell_gather_len_kernel<<<grid1, 256, 0, ctx->stream>>>(d_len, A->d_slice_src, ns, A->d_slice_off);
+            e1 = cudaGetLastError();
+        }
+        int rc = e1 == cudaSuccess ? device_scan_u64(ctx, A->d_slice_off, (uint64_t)ns + 1) : NGSB_ERR_CUDA;
+        if (rc == NGSB_OK) {
+            e1 = cudaMemcpyAsync(&A->sell_entries, A->d_slice_off + ns, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream);
+            if (e1 == cudaSuccess) e1 = cudaStreamSynchronize(ctx->stream);
+        }
+        cleanup();
+        if (e1 != cudaSuccess) { set_error("SELL build (schedule): %s", cudaGetErrorString(e1)); return NGSB_ERR_CUDA; }
+        if (rc != NGSB_OK) return rc;
+    } else {
+        NGSB_CUDA(cudaMemsetAsync(A->d_slice_off, 0, sizeof(uint64_t), ctx->stream));
+        A->sell_entries = 0;
+    }
+    cudaError_t e = cudaMalloc(&A->d_scol, std::max<size_t>(16, A->sell_entries * sizeof(int32_t)));
+    if (e == cudaSuccess) e = cudaMalloc(&A->d_sval, std::max<size_t>(16, A->sell_entries * ms * sizeof(double)));
+    if (e != cudaSuccess) { set_error("SELL build: cudaMalloc of %llu entries failed: %s", (unsigned long long)A->sell_entries, cudaGetErrorString(e)); return NGSB_ERR_NOMEM; }
+    if (A->nslices) {
+        const unsigned grid = (unsigned)(((uint64_t)A->nslices * 32 + 255) / 256);
+        if (A->kind == NGSB_REAL) sell_fill_kernel<NGSB_REAL><<<grid, 256, 0, ctx->stream>>>(A->d_rowptr, A->d_col, A->d_val, A->h, A->nslices, cap, A->d_slice_off, A->d_slice_src, A->d_scol, A->d_sval);
+        else if (A->kind == NGSB_COMPLEX) sell_fill_kernel<NGSB_COMPLEX><<<grid, 256, 0, ctx->stream>>>(A->d_rowptr, A->d_col, A->d_val, A->h, A->nslices, cap, A->d_slice_off, A->d_slice_src, A->d_scol, A->d_sval);
+        else sell_fill_kernel<NGSB_BLOCK3><<<grid, 256, 0, ctx->stream>>>(A->d_rowptr, A->d_col, A->d_val, A->h, A->nslices, cap, A->d_slice_off, A->d_slice_src, A->d_scol, A->d_sval);
+        NGSB_CUDA(cudaGetLastError());
+    }
+    if (A->novf) {
+        const uint64_t on = optr.back();
+        NGSB_CUDA(cudaMalloc(&A->d_ovf_rows, orows.size() * sizeof(uint32_t)));
+        NGSB_CUDA(cudaMalloc(&A->d_ovf_ptr, optr.size() * sizeof(uint64_t)));
+        NGSB_CUDA(cudaMalloc(&A->d_slice_ovf, slice_ovf.size() * sizeof(int32_t)));
+        NGSB_CUDA(cudaMalloc(&A->d_ovf_col, on * sizeof(int32_t)));
+        NGSB_CUDA(cudaMalloc(&A->d_ovf_val, on * ms * sizeof(double)));
+        NGSB_CUDA(cudaMalloc(&A->d_ovf_sum, orows.size() * 3 * sizeof(double)));
+        NGSB_CUDA(cudaMemcpyAsync(A->d_ovf_rows, orows.data(), orows.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+        NGSB_CUDA(cudaMemcpyAsync(A->d_ovf_ptr, optr.data(), optr.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+        NGSB_CUDA(cudaMemcpyAsync(A->d_slice_ovf, slice_ovf.data(), slice_ovf.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+        sell_ovf_copy_kernel<<<A->novf, 256, 0, ctx->stream>>>(A->d_rowptr, A->d_col, A->d_val, A->d_ovf_rows, A->d_ovf_ptr, cap, (int)ms, A->d_ovf_col, A->d_ovf_val);
+        NGSB_CUDA(cudaGetLastError());
+    }
+    NGSB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return NGSB_OK;
+}
+
+void sell_free(ngsb_csr *A)
+{
+    cudaFree(A->d_slice_off); cudaFree(A->d_slice_src); cudaFree(A->d_scol); cudaFree(A->d_sval);
+    cudaFree(A->d_ovf_rows); cudaFree(A->d_ovf_ptr); cudaFree(A->d_slice_ovf);
+    cudaFree(A->d_ovf_col); cudaFree(A->d_ovf_val); cudaFree(A->d_ovf_sum);
+}
+
+int sell_launch(const SpmvArgs &a)
+{
+    const ngsb_csr *A = a.A;
+    ngsb_ctx *ctx = A->ctx;
+    SellParams p;
+    memset(&p, 0, sizeof(p));
+    p.slice_off = A->d_slice_off; p.slice_src = A->d_slice_src; p.scol = A->d_scol; p.sval = A->d_sval;
+    p.slice_ovf = A->novf ? A->d_slice_ovf : nullptr;
+    p.ovf_rows = A->d_ovf_rows; p.ovf_sum = A->d_ovf_sum; p.novf = A->novf;
+    p.nslices = A->nslices; p.nrows = A->h;
+    p.x = a.x; p.y = a.y; p.sr = a.sr; p.si = A->kind == NGSB_COMPLEX ? a.si : 0.0;
+    p.accumulate = a.accumulate ? 1 : 0; p.epi = a.epi; p.dot_conj = a.dot_conj;
+    p.dotvec = a.dotvec; p.dot_out = a.dot_out; p.state = a.state;
+    p.partials = ctx->d_partials; p.counter = ctx->d_counter;
+    if (A->novf) {
+        SpanGuard g(ctx, KC_SPMV);
+        if (A->kind == NGSB_REAL) sell_overflow_kernel<NGSB_REAL><<<A->novf, 256, 0, ctx->stream>>>(A->d_ovf_ptr, A->d_ovf_col, A->d_ovf_val, a.x, A->d_ovf_sum, a.state);
+        else if (A->kind == NGSB_COMPLEX) sell_overflow_kernel<NGSB_COMPLEX><<<A->novf, 256, 0, ctx->stream>>>(A->d_ovf_ptr, A->d_ovf_col, A->d_ovf_val, a.x, A->d_ovf_sum, a.state);
+        else sell_overflow_kernel<NGSB_BLOCK3><<<A->novf, 256, 0, ctx->stream>>>(A->d_ovf_ptr, A->d_ovf_col, A->d_ovf_val, a.x, A->d_ovf_sum, a.state);
+        NGSB_CUDA(cudaGetLastError());
+    }
+    // grid = resident CTAs (occupancy query) unless overridden: every CTA stays on its SM for the whole sweep
+    typedef void (*kern_t)(const SellParams);
+    kern_t kern;
+    const long var = ctx->sell_variant;
+    if (A->kind == NGSB_REAL) {
+        // default (0): software-pipelined loop, 64 registers, 4 resident CTAs, grid of 8 CTAs per SM --
+        // best of the variants swept on B200 at 6-101 M rows (profiles/r1_sweep_sell_variants.txt)
+        switch (var) {
+        case 1: kern = sell_spmv_kernel<NGSB_REAL, 0, 5>; break;
+        case 2: kern = sell_spmv_kernel<NGSB_REAL, 1, 8>; break;
+        default: kern = sell_spmv_kernel<NGSB_REAL, 2, 4>; break;
+        }
+    } else if (A->kind == NGSB_COMPLEX) kern = sell_spmv_kernel<NGSB_COMPLEX, 0, 6>;
+    else kern = sell_spmv_kernel<NGSB_BLOCK3, 0, 5>;
+    int occ = 0;
+    NGSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, 0));
+    long cps = ctx->spmv_ctas_per_sm > 0 ? ctx->spmv_ctas_per_sm : (A->kind == NGSB_REAL && var == 0 ? 8 : (occ > 0 ? occ : 4));
+    uint64_t grid = (uint64_t)ctx->sm_count * (uint64_t)cps;
+    const uint64_t need = ((uint64_t)A->nslices + 7) / 8;
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    if (grid > (uint64_t)MAX_PARTIALS - 8) grid = MAX_PARTIALS - 8;
+    SpanGuard g(ctx, KC_SPMV);
+    kern<<<(unsigned)grid, 256, 0, ctx->stream>>>(p);
+    NGSB_CUDA(cudaGetLastError());
+    return NGSB_OK;
+}
+
+} // namespace ngsb

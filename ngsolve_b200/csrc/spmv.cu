@@ -26,29 +26,31 @@ namespace ngsb {
 // configuration per entry kind
 // ------------------------------------------------------------------------------------------
 template <int KIND> struct KindCfg;
-template <> struct KindCfg<NGSB_REAL>    { static constexpr int VB = 8;  static constexpr int TILE = 2048; static constexpr int XS = 1; };
-template <> struct KindCfg<NGSB_COMPLEX> { static constexpr int VB = 16; static constexpr int TILE = 1024; static constexpr int XS = 2; };
-template <> struct KindCfg<NGSB_BLOCK3>  { static constexpr int VB = 72; static constexpr int TILE = 512;  static constexpr int XS = 3; };
+template <> struct KindCfg<NGSB_REAL>    { static constexpr int VB = 8;  static constexpr int XS = 1; };
+template <> struct KindCfg<NGSB_COMPLEX> { static constexpr int VB = 16; static constexpr int XS = 2; };
+template <> struct KindCfg<NGSB_BLOCK3>  { static constexpr int VB = 72; static constexpr int XS = 3; };
 
-static constexpr int STAGES = 4;
-static constexpr int NCW = 8;              // consumer warps per CTA
+static constexpr int MAX_STAGES = 8;
 static constexpr int RMAX = 504;           // max rows per block (row-offset slot holds RMAX+8 uint16)
-static constexpr int NTHREADS = (NCW + 1) * 32;
 
-template <int KIND> struct StageLayout {
-    using C = KindCfg<KIND>;
-    static constexpr int VALS = 0;
-    static constexpr int COLS = C::TILE * C::VB;
-    static constexpr int ROFF = COLS + C::TILE * 4;
-    static constexpr int HDR = ROFF + (RMAX + 8) * 2;
-    static constexpr int BYTES = ((HDR + 16 + 127) / 128) * 128;
-    static constexpr int SMEM = 128 + STAGES * BYTES;
+// shared-memory layout of one stage, fixed per matrix at creation (tile = entries per stage)
+struct StageLayout {
+    int cols, roff, hdr, bytes;
+    __host__ __device__ StageLayout(int tile, int vb)
+    {
+        cols = tile * vb;
+        roff = cols + tile * 4;
+        hdr = roff + (RMAX + 8) * 2;
+        bytes = ((hdr + 16 + 127) / 128) * 128;
+    }
 };
 
-static int tile_entries(int kind)
+static int default_tile(int kind)
 {
-    return kind == NGSB_REAL ? KindCfg<NGSB_REAL>::TILE : (kind == NGSB_COMPLEX ? KindCfg<NGSB_COMPLEX>::TILE : KindCfg<NGSB_BLOCK3>::TILE);
+    return kind == NGSB_REAL ? 2048 : (kind == NGSB_COMPLEX ? 1024 : 512);
 }
+
+static int kind_vb(int kind) { return kind == NGSB_REAL ? 8 : (kind == NGSB_COMPLEX ? 16 : 72); }
 
 // ------------------------------------------------------------------------------------------
 // PTX helpers: mbarrier + 1-D bulk TMA
@@ -132,6 +134,7 @@ struct SpmvParams {
     unsigned int *counter;
     uint32_t block_begin, block_end;
     uint64_t nrows;
+    int tile, stages;
 };
 
 // store one finished row; returns this row's contribution to the fused dot in (dr, di)
@@ -218,18 +221,20 @@ __device__ __forceinline__ void dot_epilogue(const SpmvParams &p, double dr, dou
 // TMA-streamed kernel
 // ------------------------------------------------------------------------------------------
 template <int KIND, int W>
-__global__ void __launch_bounds__(NTHREADS) spmv_stream_kernel(const SpmvParams p)
+__global__ void __launch_bounds__(544) spmv_stream_kernel(const SpmvParams p)
 {
     using C = KindCfg<KIND>;
-    using L = StageLayout<KIND>;
     constexpr int G = 32 / W;   // rows per warp step
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ double red[64];
 
     if (p.state != nullptr && p.state->done) return;   // uniform: CG already finished
 
+    const StageLayout L(p.tile, C::VB);
+    const int STAGES = p.stages;
+    const int NCW = (int)(blockDim.x >> 5) - 1;        // consumer warps; the last warp is the producer
     uint64_t *full = reinterpret_cast<uint64_t *>(smem);
-    uint64_t *empty = full + STAGES;
+    uint64_t *empty = full + MAX_STAGES;
     unsigned char *stages = smem + 128;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -248,14 +253,13 @@ __global__ void __launch_bounds__(NTHREADS) spmv_stream_kernel(const SpmvParams 
     if (warp == NCW) {
         // ---------------- producer ----------------
         if (lane == 0) {
-            uint32_t it = 0;
-            for (uint32_t b = b0; b < b1; ++b, ++it) {
-                const int s = it % STAGES;
-                const uint32_t k = it / STAGES;
+            int s = 0;
+            uint32_t k = 0;
+            for (uint32_t b = b0; b < b1; ++b) {
                 if (k > 0) mbar_wait(&empty[s], (k & 1) ^ 1);
                 const SpmvBlock d = p.blocks[b];
-                unsigned char *st = stages + (size_t)s * L::BYTES;
-                uint32_t *hdr = reinterpret_cast<uint32_t *>(st + L::HDR);
+                unsigned char *st = stages + (size_t)s * L.bytes;
+                uint32_t *hdr = reinterpret_cast<uint32_t *>(st + L.hdr);
                 hdr[0] = d.row_begin;
                 hdr[1] = d.nrows;
                 hdr[2] = d.flags;
@@ -267,12 +271,13 @@ __global__ void __launch_bounds__(NTHREADS) spmv_stream_kernel(const SpmvParams 
                     const uint32_t bytes = nwin * (uint32_t)C::VB + nwin * 4u + roff_bytes;
                     mbar_arrive_expect_tx(&full[s], bytes);
                     if (nwin) {   // a block of empty rows has no entries to stream
-                        tma_bulk_g2s(st + L::VALS, reinterpret_cast<const unsigned char *>(p.val) + d.nnz_base * (uint64_t)C::VB,
+                        tma_bulk_g2s(st, reinterpret_cast<const unsigned char *>(p.val) + d.nnz_base * (uint64_t)C::VB,
                                      nwin * (uint32_t)C::VB, &full[s]);
-                        tma_bulk_g2s(st + L::COLS, p.col + d.nnz_base, nwin * 4u, &full[s]);
+                        tma_bulk_g2s(st + L.cols, p.col + d.nnz_base, nwin * 4u, &full[s]);
                     }
-                    tma_bulk_g2s(st + L::ROFF, p.rowoff + d.roff_base, roff_bytes, &full[s]);
+                    tma_bulk_g2s(st + L.roff, p.rowoff + d.roff_base, roff_bytes, &full[s]);
                 }
+                if (++s == STAGES) { s = 0; ++k; }
             }
         }
     } else {
@@ -280,18 +285,17 @@ __global__ void __launch_bounds__(NTHREADS) spmv_stream_kernel(const SpmvParams 
         const int grp = lane / W;      // row slot inside the warp step
         const int gl = lane % W;       // lane inside the group
         uint32_t rr = 0;               // round-robin offset: groups handed out so far (mod NCW)
-        uint32_t it = 0;
-        for (uint32_t b = b0; b < b1; ++b, ++it) {
-            const int s = it % STAGES;
-            const uint32_t k = it / STAGES;
+        int s = 0;
+        uint32_t k = 0;
+        for (uint32_t b = b0; b < b1; ++b) {
             mbar_wait(&full[s], k & 1);
-            const unsigned char *st = stages + (size_t)s * L::BYTES;
-            const uint32_t *hdr = reinterpret_cast<const uint32_t *>(st + L::HDR);
+            const unsigned char *st = stages + (size_t)s * L.bytes;
+            const uint32_t *hdr = reinterpret_cast<const uint32_t *>(st + L.hdr);
             const uint32_t row_begin = hdr[0], nrows = hdr[1], flags = hdr[2];
             const uint32_t ngroups = (nrows + G - 1) / G;
             if (flags & 1u) {
                 // long row: y[row] already final (long-row kernel ran first); only the dot part
-                if (p.epi && ((rr % NCW) == (uint32_t)warp) && lane == 0) {
+                if (p.epi && (rr == (uint32_t)warp) && lane == 0) {
                     const uint64_t row = row_begin;
                     if (KIND == NGSB_REAL) dr += p.dotvec[row] * p.y[row];
                     else if (KIND == NGSB_COMPLEX) {
@@ -306,9 +310,9 @@ __global__ void __launch_bounds__(NTHREADS) spmv_stream_kernel(const SpmvParams 
                     }
                 }
             } else {
-                const uint16_t *roff = reinterpret_cast<const uint16_t *>(st + L::ROFF);
-                const int32_t *cs = reinterpret_cast<const int32_t *>(st + L::COLS);
-                uint32_t q = ((uint32_t)warp + NCW - (rr % NCW)) % NCW;
+                const uint16_t *roff = reinterpret_cast<const uint16_t *>(st + L.roff);
+                const int32_t *cs = reinterpret_cast<const int32_t *>(st + L.cols);
+                uint32_t q = (uint32_t)warp >= rr ? (uint32_t)warp - rr : (uint32_t)warp + NCW - rr;
                 for (; q < ngroups; q += NCW) {
                     const uint32_t rl = q * G + grp;
                     const bool valid = rl < nrows;
@@ -316,7 +320,7 @@ __global__ void __launch_bounds__(NTHREADS) spmv_stream_kernel(const SpmvParams 
                     if (valid) { o0 = roff[rl]; o1 = roff[rl + 1]; }
                     double s0 = 0.0, s1 = 0.0, s2 = 0.0;
                     if (KIND == NGSB_REAL) {
-                        const double *vs = reinterpret_cast<const double *>(st + L::VALS);
+                        const double *vs = reinterpret_cast<const double *>(st);
                         int j = o0 + gl;
                         for (; j + 3 * W < o1; j += 4 * W) {
                             int c0 = cs[j], c1 = cs[j + W], c2 = cs[j + 2 * W], c3 = cs[j + 3 * W];
@@ -330,7 +334,7 @@ __global__ void __launch_bounds__(NTHREADS) spmv_stream_kernel(const SpmvParams 
                         s0 = group_sum<W>(s0 + s1);
                         s1 = 0.0;
                     } else if (KIND == NGSB_COMPLEX) {
-                        const double2 *vs = reinterpret_cast<const double2 *>(st + L::VALS);
+                        const double2 *vs = reinterpret_cast<const double2 *>(st);
                         const double2 *x2 = reinterpret_cast<const double2 *>(p.x);
                         int j = o0 + gl;
                         for (; j + W < o1; j += 2 * W) {
@@ -351,7 +355,7 @@ __global__ void __launch_bounds__(NTHREADS) spmv_stream_kernel(const SpmvParams 
                         s0 = group_sum<W>(s0);
                         s1 = group_sum<W>(s1);
                     } else {
-                        const double *vs = reinterpret_cast<const double *>(st + L::VALS);
+                        const double *vs = reinterpret_cast<const double *>(st);
                         for (int j = o0 + gl; j < o1; j += W) {
                             const double *m = vs + 9 * j;
                             const double *xv = p.x + 3 * (size_t)cs[j];
@@ -367,9 +371,10 @@ __global__ void __launch_bounds__(NTHREADS) spmv_stream_kernel(const SpmvParams 
                     if (valid && gl == 0) finish_row<KIND>(p, (uint64_t)row_begin + rl, s0, s1, s2, dr, di);
                 }
             }
-            rr += (flags & 1u) ? 1u : ngroups;
+            rr = (rr + ((flags & 1u) ? 1u : ngroups)) % (uint32_t)NCW;
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[s]);
+            if (++s == STAGES) { s = 0; ++k; }
         }
     }
 
@@ -467,28 +472,29 @@ __global__ void __launch_bounds__(256) spmv_subwarp_kernel(const SpmvParams p)
 // host side
 // ------------------------------------------------------------------------------------------
 template <int KIND, int W>
-static int launch_stream(ngsb_ctx *ctx, const SpmvParams &p, int grid)
+static int launch_stream(ngsb_ctx *ctx, const SpmvParams &p, int grid, int ncw)
 {
-    using L = StageLayout<KIND>;
-    static bool configured[64] = {false};
+    const StageLayout L(p.tile, KindCfg<KIND>::VB);
+    const int smem = 128 + p.stages * L.bytes;
+    static int configured[64] = {0};
     NGSB_REQUIRE(ctx->device < 64, "device index too large");
-    if (!configured[ctx->device]) {
-        NGSB_CUDA(cudaFuncSetAttribute(spmv_stream_kernel<KIND, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM));
-        configured[ctx->device] = true;
+    if (configured[ctx->device] < smem) {
+        NGSB_CUDA(cudaFuncSetAttribute(spmv_stream_kernel<KIND, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured[ctx->device] = smem;
     }
-    spmv_stream_kernel<KIND, W><<<grid, NTHREADS, L::SMEM, ctx->stream>>>(p);
+    spmv_stream_kernel<KIND, W><<<grid, (ncw + 1) * 32, smem, ctx->stream>>>(p);
     NGSB_CUDA(cudaGetLastError());
     return NGSB_OK;
 }
 
 template <int KIND>
-static int dispatch_stream(ngsb_ctx *ctx, const SpmvParams &p, int grid, int W)
+static int dispatch_stream(ngsb_ctx *ctx, const SpmvParams &p, int grid, int W, int ncw)
 {
     switch (W) {
-    case 4: return launch_stream<KIND, 4>(ctx, p, grid);
-    case 8: return launch_stream<KIND, 8>(ctx, p, grid);
-    case 16: return launch_stream<KIND, 16>(ctx, p, grid);
-    default: return launch_stream<KIND, 32>(ctx, p, grid);
+    case 4: return launch_stream<KIND, 4>(ctx, p, grid, ncw);
+    case 8: return launch_stream<KIND, 8>(ctx, p, grid, ncw);
+    case 16: return launch_stream<KIND, 16>(ctx, p, grid, ncw);
+    default: return launch_stream<KIND, 32>(ctx, p, grid, ncw);
     }
 }
 
@@ -543,7 +549,10 @@ int spmv_launch(const SpmvArgs &a)
     p.nrows = A->h;
     p.block_begin = a.use_range ? a.block_begin : 0;
     p.block_end = a.use_range ? a.block_end : A->nblocks;
+    p.tile = A->tile;
+    p.stages = A->stages;
 
+    if ((ctx->spmv_algo == 0 || ctx->spmv_algo == 3) && !a.use_range) return sell_launch(a);
     const bool stream = ctx->spmv_algo != 1;
     if (stream) {
         if (A->nlong > 0 && !a.use_range) {
@@ -553,15 +562,15 @@ int spmv_launch(const SpmvArgs &a)
             else spmv_longrow_kernel<NGSB_BLOCK3><<<A->nlong, 256, 0, ctx->stream>>>(p, A->d_longrows);
             NGSB_CUDA(cudaGetLastError());
         }
-        long cps = ctx->spmv_ctas_per_sm > 0 ? ctx->spmv_ctas_per_sm : (A->kind == NGSB_BLOCK3 ? 1 : 2);
+        long cps = ctx->spmv_ctas_per_sm > 0 ? ctx->spmv_ctas_per_sm : A->ctas_per_sm;
         uint64_t nb = p.block_end - p.block_begin;
         uint64_t grid = (uint64_t)ctx->sm_count * (uint64_t)cps;
         if (grid > nb) grid = nb;
         if (grid < 1) grid = 1;
         SpanGuard g(ctx, KC_SPMV);
-        if (A->kind == NGSB_REAL) return dispatch_stream<NGSB_REAL>(ctx, p, (int)grid, A->subwarp);
-        if (A->kind == NGSB_COMPLEX) return dispatch_stream<NGSB_COMPLEX>(ctx, p, (int)grid, A->subwarp);
-        return dispatch_stream<NGSB_BLOCK3>(ctx, p, (int)grid, A->subwarp);
+        if (A->kind == NGSB_REAL) return dispatch_stream<NGSB_REAL>(ctx, p, (int)grid, A->subwarp, A->ncw);
+        if (A->kind == NGSB_COMPLEX) return dispatch_stream<NGSB_COMPLEX>(ctx, p, (int)grid, A->subwarp, A->ncw);
+        return dispatch_stream<NGSB_BLOCK3>(ctx, p, (int)grid, A->subwarp, A->ncw);
     }
     // subwarp kernel: dot not fused
     {
@@ -586,10 +595,10 @@ int spmv_launch(const SpmvArgs &a)
 }
 
 // ---- block builder --------------------------------------------------------------------------
-static void build_blocks(const uint64_t *rowptr, size_t h, int kind, int W, std::vector<SpmvBlock> &blocks,
+static void build_blocks(const uint64_t *rowptr, size_t h, int tile, int NCW, int W, std::vector<SpmvBlock> &blocks,
                          std::vector<uint16_t> &rowoff, std::vector<uint32_t> &longrows)
 {
-    const uint64_t TILE = (uint64_t)tile_entries(kind);
+    const uint64_t TILE = (uint64_t)tile;
     const int G = 32 / W;
     // rows per block: a multiple of the rows one CTA step covers, bounded by RMAX
     const size_t target_rows = std::min<size_t>(RMAX / (NCW * G) * (NCW * G), (size_t)NCW * G * 2);
@@ -643,11 +652,23 @@ static int finish_create(ngsb_csr *A, const uint64_t *h_rowptr)
     size_t mx = 0;
     for (size_t i = 0; i < A->h; i++) mx = std::max<size_t>(mx, h_rowptr[i + 1] - h_rowptr[i]);
     A->max_row = mx;
-    A->subwarp = pick_subwarp(A->kind, A->mean_row);
+    A->subwarp = ctx->spmv_subwarp > 0 ? (int)ctx->spmv_subwarp : pick_subwarp(A->kind, A->mean_row);
+    A->tile = ctx->spmv_tile > 0 ? (int)ctx->spmv_tile : default_tile(A->kind);
+    A->ncw = ctx->spmv_ncw > 0 ? (int)ctx->spmv_ncw : 8;
+    A->stages = ctx->spmv_stages > 0 ? (int)ctx->spmv_stages : 4;
+    {
+        // resident CTAs per SM the shared-memory footprint allows (227 KB usable)
+        const StageLayout L(A->tile, kind_vb(A->kind));
+        const int smem = 128 + A->stages * L.bytes + 1024;
+        NGSB_REQUIRE(smem <= 227 * 1024, "spmv tile/stages do not fit shared memory");
+        int fit = (227 * 1024) / smem;
+        int by_threads = 2048 / ((A->ncw + 1) * 32);
+        A->ctas_per_sm = std::max(1, std::min(fit, by_threads));
+    }
     std::vector<SpmvBlock> blocks;
     std::vector<uint16_t> rowoff;
     std::vector<uint32_t> longrows;
-    build_blocks(h_rowptr, A->h, A->kind, A->subwarp, blocks, rowoff, longrows);
+    build_blocks(h_rowptr, A->h, A->tile, A->ncw, A->subwarp, blocks, rowoff, longrows);
     NGSB_REQUIRE(blocks.size() < (1ull << 32), "too many row blocks");
     A->nblocks = (uint32_t)blocks.size();
     A->nlong = (uint32_t)longrows.size();
@@ -658,7 +679,7 @@ static int finish_create(ngsb_csr *A, const uint64_t *h_rowptr)
     if (!rowoff.empty()) NGSB_CUDA(cudaMemcpyAsync(A->d_rowoff, rowoff.data(), rowoff.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream));
     if (!longrows.empty()) NGSB_CUDA(cudaMemcpyAsync(A->d_longrows, longrows.data(), longrows.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
     NGSB_CUDA(cudaStreamSynchronize(ctx->stream));
-    return NGSB_OK;
+    return sell_build(A, h_rowptr);
 }
 
 static int alloc_csr(ngsb_csr *A)
@@ -783,6 +804,7 @@ extern "C" int ngsb_csr_destroy(ngsb_csr *A)
     cudaFree(A->d_blocks);
     cudaFree(A->d_rowoff);
     cudaFree(A->d_longrows);
+    sell_free(A);
     delete A;
     return NGSB_OK;
 }
@@ -842,6 +864,15 @@ extern "C" int ngsb_csr_download(const ngsb_csr *A, uint64_t *rowptr, int32_t *c
     if (col && A->nnz) NGSB_CUDA(cudaMemcpyAsync(col, A->d_col, A->nnz * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     if (val && A->nnz) NGSB_CUDA(cudaMemcpyAsync(val, A->d_val, A->nnz * ms * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     NGSB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return NGSB_OK;
+}
+
+extern "C" int ngsb_csr_layout(const ngsb_csr *A, uint64_t *sell_entries, uint32_t *overflow_rows, uint32_t *cap)
+{
+    NGSB_REQUIRE(A, "ngsb_csr_layout: A is NULL");
+    if (sell_entries) *sell_entries = A->sell_entries;
+    if (overflow_rows) *overflow_rows = A->novf;
+    if (cap) *cap = A->sell_cap;
     return NGSB_OK;
 }
 

@@ -29,6 +29,25 @@ struct ngsb_csr {
     uint32_t *d_longrows = nullptr;
     uint32_t nlong = 0;
     int subwarp = 8;                // lanes per row
+    int tile = 2048;                // entries per streamed stage
+    int ncw = 8;                    // consumer warps per CTA
+    int stages = 4;                 // ring depth
+    int ctas_per_sm = 2;
+    // SELL-32 copy (sell.cu): slices of 32 rows stored entry-major, default SpMV layout
+    uint32_t nslices = 0;
+    uint64_t sell_entries = 0;      // padded entries
+    uint32_t sell_cap = 0;          // longest row part kept in a slice; the rest lives in the overflow CSR
+    uint64_t *d_slice_off = nullptr;
+    uint32_t *d_slice_src = nullptr;   // schedule: position t -> original slice
+    int32_t *d_scol = nullptr;
+    double *d_sval = nullptr;
+    uint32_t novf = 0;
+    uint32_t *d_ovf_rows = nullptr;
+    uint64_t *d_ovf_ptr = nullptr;
+    int32_t *d_slice_ovf = nullptr;
+    int32_t *d_ovf_col = nullptr;
+    double *d_ovf_val = nullptr;
+    double *d_ovf_sum = nullptr;
     double mean_row = 0.0;
     size_t max_row = 0;
 };
@@ -55,5 +74,8 @@ struct SpmvArgs {
 };
 
 int spmv_launch(const SpmvArgs &a);
+int sell_build(ngsb_csr *A, const uint64_t *h_rowptr);
+void sell_free(ngsb_csr *A);
+int sell_launch(const SpmvArgs &a);
 
 } // namespace ngsb

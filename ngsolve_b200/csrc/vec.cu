@@ -338,6 +338,60 @@ int launch_dot(ngsb_ctx *ctx, const double *x, const double *y, size_t N, int mo
     return NGSB_OK;
 }
 
+// in-place inclusive scan of rowlen[0..n] (three-phase, chunk per CTA)
+__global__ void __launch_bounds__(256) scan_chunks_kernel(uint64_t *a, uint64_t n, uint64_t chunk, uint64_t *sums)
+{
+    __shared__ uint64_t sh[256];
+    const uint64_t lo = (uint64_t)blockIdx.x * chunk, hi = lo + chunk < n ? lo + chunk : n;
+    const uint64_t per = (chunk + 255) / 256;
+    const uint64_t tlo = lo + threadIdx.x * per < hi ? lo + threadIdx.x * per : hi;
+    const uint64_t thi = tlo + per < hi ? tlo + per : hi;
+    uint64_t s = 0;
+    for (uint64_t i = tlo; i < thi; i++) s += a[i];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint64_t run = 0;
+        for (int t = 0; t < 256; t++) { uint64_t v = sh[t]; sh[t] = run; run += v; }
+        sums[blockIdx.x] = run;
+    }
+    __syncthreads();
+    uint64_t run = sh[threadIdx.x];
+    for (uint64_t i = tlo; i < thi; i++) { run += a[i]; a[i] = run; }
+}
+
+__global__ void scan_sums_kernel(uint64_t *sums, int nchunks)
+{
+    uint64_t run = 0;
+    for (int i = 0; i < nchunks; i++) { uint64_t v = sums[i]; sums[i] = run; run += v; }
+}
+
+__global__ void __launch_bounds__(256) scan_add_kernel(uint64_t *a, uint64_t n, uint64_t chunk, const uint64_t *sums)
+{
+    const uint64_t lo = (uint64_t)blockIdx.x * chunk, hi = lo + chunk < n ? lo + chunk : n;
+    const uint64_t add = sums[blockIdx.x];
+    for (uint64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) a[i] += add;
+}
+
+
+int device_scan_u64(ngsb_ctx *ctx, uint64_t *d_a, uint64_t n)
+{
+    if (n == 0) return NGSB_OK;
+    const uint64_t chunk = 1 << 16;
+    const int nchunks = (int)((n + chunk - 1) / chunk);
+    uint64_t *d_sums = nullptr;
+    NGSB_CUDA(cudaMalloc(&d_sums, (size_t)nchunks * sizeof(uint64_t)));
+    scan_chunks_kernel<<<nchunks, 256, 0, ctx->stream>>>(d_a, n, chunk, d_sums);
+    scan_sums_kernel<<<1, 1, 0, ctx->stream>>>(d_sums, nchunks);
+    scan_add_kernel<<<nchunks, 256, 0, ctx->stream>>>(d_a, n, chunk, d_sums);
+    ctx->launches += 3;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_sums);
+    if (e != cudaSuccess) { set_error("device_scan_u64: %s", cudaGetErrorString(e)); return NGSB_ERR_CUDA; }
+    return NGSB_OK;
+}
+
 // scalar expression kernels (ngscuda/unifiedvector.hpp:126-135)
 __global__ void scalar_op_kernel(double *out, const double *a, const double *b, int op)
 {
@@ -442,10 +496,17 @@ extern "C" int ngsb_ctx_launch_count(const ngsb_ctx *ctx, uint64_t *count)
 extern "C" int ngsb_ctx_set_option(ngsb_ctx *ctx, const char *name, long value)
 {
     NGSB_REQUIRE(ctx && name, "ngsb_ctx_set_option: NULL argument");
-    if (!strcmp(name, "spmv_algo")) { NGSB_REQUIRE(value >= 0 && value <= 2, "spmv_algo must be 0,1,2"); ctx->spmv_algo = value; }
+    if (!strcmp(name, "spmv_algo")) { NGSB_REQUIRE(value >= 0 && value <= 3, "spmv_algo must be 0 (auto = SELL), 1 (sub-warp CSR), 2 (TMA-streamed CSR), 3 (SELL)"); ctx->spmv_algo = value; }
     else if (!strcmp(name, "cg_batch")) { NGSB_REQUIRE(value >= 1 && value <= 4096, "cg_batch out of range"); ctx->cg_batch = value; }
-    else if (!strcmp(name, "spmv_ctas_per_sm")) { NGSB_REQUIRE(value >= 0 && value <= 8, "spmv_ctas_per_sm out of range"); ctx->spmv_ctas_per_sm = value; }
+    else if (!strcmp(name, "spmv_ctas_per_sm")) { NGSB_REQUIRE(value >= 0 && value <= 16, "spmv_ctas_per_sm out of range"); ctx->spmv_ctas_per_sm = value; }
     else if (!strcmp(name, "timing")) { ctx->timing = value ? 1 : 0; }
+    else if (!strcmp(name, "sell_variant")) { NGSB_REQUIRE(value >= 0 && value <= 8, "sell_variant out of range"); ctx->sell_variant = value; }
+    else if (!strcmp(name, "sell_schedule")) { NGSB_REQUIRE(value >= 0 && value <= 2, "sell_schedule must be 0 (off), 1 (auto), 2 (on)"); ctx->sell_schedule = value; }
+    else if (!strcmp(name, "sell_cap")) { NGSB_REQUIRE(value >= 0 && value <= (1 << 20), "sell_cap out of range"); ctx->sell_cap = value; }
+    else if (!strcmp(name, "spmv_tile")) { NGSB_REQUIRE(value == 0 || (value >= 256 && value <= 8192 && value % 256 == 0), "spmv_tile out of range"); ctx->spmv_tile = value; }
+    else if (!strcmp(name, "spmv_ncw")) { NGSB_REQUIRE(value >= 0 && value <= 16, "spmv_ncw out of range"); ctx->spmv_ncw = value; }
+    else if (!strcmp(name, "spmv_stages")) { NGSB_REQUIRE(value >= 0 && value <= 8, "spmv_stages out of range"); ctx->spmv_stages = value; }
+    else if (!strcmp(name, "spmv_subwarp")) { NGSB_REQUIRE(value == 0 || value == 4 || value == 8 || value == 16 || value == 32, "spmv_subwarp must be 0,4,8,16,32"); ctx->spmv_subwarp = value; }
     else { set_error("ngsb_ctx_set_option: unknown option '%s'", name); return NGSB_ERR_INVALID; }
     return NGSB_OK;
 }

@@ -633,6 +633,12 @@ class DevSparseMatrix(BaseMatrix):
         check(_capi.lib().ngsb_csr_download(self.handle, _np_ptr(rowptr), _np_ptr(col), _np_ptr(val)))
         return val, col, rowptr
 
+    def Layout(self):
+        """(padded SELL entries, rows with an overflow part, slice cap)"""
+        e, o, c = C.c_uint64(), C.c_uint32(), C.c_uint32()
+        check(_capi.lib().ngsb_csr_layout(self.handle, C.byref(e), C.byref(o), C.byref(c)))
+        return e.value, o.value, c.value
+
     def MultBytes(self):
         b = C.c_double()
         check(_capi.lib().ngsb_csr_mult_bytes(self.handle, C.byref(b)))

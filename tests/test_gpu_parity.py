@@ -39,7 +39,7 @@ def sysm(request, la):
     return request.param, g, A, dev
 
 
-@pytest.mark.parametrize("algo", [2, 1])
+@pytest.mark.parametrize("algo", [3, 2, 1])
 def test_mult_multadd(la, sysm, algo):
     name, g, A, dev = sysm
     dev.ctx.set_option("spmv_algo", algo)
@@ -282,7 +282,7 @@ def _random_csr(rng, n, rowlens, kind, width=None):
 
 
 @pytest.mark.parametrize("kind", [0, 1, 3])
-@pytest.mark.parametrize("algo", [2, 1])
+@pytest.mark.parametrize("algo", [3, 2, 1])
 def test_ragged_and_long_rows(la, kind, algo):
     """empty rows, rows longer than one streamed tile, a rectangular matrix, very short rows."""
     rng = np.random.default_rng(7 + kind)
@@ -309,6 +309,8 @@ def test_ragged_and_long_rows(la, kind, algo):
         assert relerr(y.NumPy().reshape(-1), yref) <= SPMV_TOL
         dev.Mult(x, y)
         assert relerr(y.NumPy().reshape(-1), oA.mult(xs)) <= SPMV_TOL
+        entries, novf, cap = dev.Layout()
+        assert novf == 3 and cap < 2200 and entries >= 32 * 40        # the three long rows overflow their slices
     finally:
         ctx.set_option("spmv_algo", 0)
 
