@@ -177,6 +177,10 @@ def run_b200(args):
     from ngsolve_b200 import la, workloads as W, _capi
     from ngsolve_b200 import parallel as par
 
+    # NCCL prints its version banner to stdout when NCCL_DEBUG=VERSION is in the environment; stdout carries
+    # exactly one JSON line
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
