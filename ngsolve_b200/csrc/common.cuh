@@ -67,6 +67,7 @@ struct ngsb_ctx {
     long spmv_ctas_per_sm = 0;   // 0 = kernel default
     long sell_cap = 0;           // 0 = max(64, 4 * mean row length)
     long sell_schedule = 1;      // order slices by their smallest first column (locality of the x gathers)
+    long sell_sigma = -1;        // rows sorted by length inside windows of sigma rows; -1 = 4096, 0/1 = off
     long sell_variant = 0;       // inner-loop variant of the real SELL kernel (tuning)
     long spmv_tile = 0, spmv_ncw = 0, spmv_stages = 0, spmv_subwarp = 0;   // 0 = default; read when a matrix is created
     long timing = 0;

@@ -32,11 +32,12 @@ int device_scan_u64(ngsb_ctx *ctx, uint64_t *d_a, uint64_t n);   // vec.cu
 
 struct SellParams {
     const uint64_t *slice_off;
-    const uint32_t *slice_src;    // slice t of the schedule holds rows 32*slice_src[t] .. +31
+    const uint32_t *slice_src;    // slice t of the schedule is slice slice_src[t] of the sigma-sorted row order
+    const uint32_t *row_of;       // slot (= 32*slice + lane) -> matrix row, 0xffffffff for the padding of the last slice
     const int32_t *scol;
     const double *sval;
     const int32_t *slice_ovf;     // per slice: first overflow entry of this slice or -1 (NULL: none)
-    const uint32_t *ovf_rows;
+    const uint32_t *ovf_slot;     // slots of the rows with an overflow part, ascending
     const double *ovf_sum;        // raw overflow sums, es doubles per overflow row
     uint32_t novf;
     uint32_t nslices;
@@ -98,7 +99,8 @@ __global__ void __launch_bounds__(256, MINB) sell_spmv_kernel(const SellParams p
         const uint64_t off = p.slice_off[s];
         const uint32_t width = (uint32_t)((p.slice_off[s + 1] - off) >> 5);     // entries per lane
         const uint64_t src = p.slice_src[s];
-        const uint64_t row = src * 32 + lane;
+        const uint32_t slot = (uint32_t)(src * 32 + lane);
+        const uint32_t row = p.row_of[slot];
         double s0 = 0.0, s1 = 0.0, s2 = 0.0;
         if (KIND == NGSB_REAL) {
             const double2 *v2 = reinterpret_cast<const double2 *>(p.sval + off) + lane;
@@ -153,6 +155,29 @@ __global__ void __launch_bounds__(256, MINB) sell_spmv_kernel(const SellParams p
             const int *c1 = p.scol + off + lane;
             const double2 *x2 = reinterpret_cast<const double2 *>(p.x);
             uint32_t q = 0;
+            if (VAR == 2 && width >= 4) {
+                // software pipeline: the next four entries are in flight while this step's x gathers resolve
+                double2 va = ldg_stream_d2(v2), vb = ldg_stream_d2(v2 + 32), vc = ldg_stream_d2(v2 + 64), vd = ldg_stream_d2(v2 + 96);
+                int ca = ldg_stream_i(c1), cb = ldg_stream_i(c1 + 32), cc = ldg_stream_i(c1 + 64), cd = ldg_stream_i(c1 + 96);
+                for (q = 4; q + 4 <= width; q += 4) {
+                    double2 xa = __ldg(x2 + ca), xb = __ldg(x2 + cb), xc = __ldg(x2 + cc), xd = __ldg(x2 + cd);
+                    double2 na = ldg_stream_d2(v2 + (q + 0) * 32), nb = ldg_stream_d2(v2 + (q + 1) * 32);
+                    double2 nc = ldg_stream_d2(v2 + (q + 2) * 32), nd = ldg_stream_d2(v2 + (q + 3) * 32);
+                    int ea = ldg_stream_i(c1 + (q + 0) * 32), eb = ldg_stream_i(c1 + (q + 1) * 32);
+                    int ec = ldg_stream_i(c1 + (q + 2) * 32), ed = ldg_stream_i(c1 + (q + 3) * 32);
+                    s0 += va.x * xa.x - va.y * xa.y; s1 += va.x * xa.y + va.y * xa.x;
+                    s0 += vb.x * xb.x - vb.y * xb.y; s1 += vb.x * xb.y + vb.y * xb.x;
+                    s0 += vc.x * xc.x - vc.y * xc.y; s1 += vc.x * xc.y + vc.y * xc.x;
+                    s0 += vd.x * xd.x - vd.y * xd.y; s1 += vd.x * xd.y + vd.y * xd.x;
+                    va = na; vb = nb; vc = nc; vd = nd; ca = ea; cb = eb; cc = ec; cd = ed;
+                }
+                double2 xa = __ldg(x2 + ca), xb = __ldg(x2 + cb), xc = __ldg(x2 + cc), xd = __ldg(x2 + cd);
+                s0 += va.x * xa.x - va.y * xa.y; s1 += va.x * xa.y + va.y * xa.x;
+                s0 += vb.x * xb.x - vb.y * xb.y; s1 += vb.x * xb.y + vb.y * xb.x;
+                s0 += vc.x * xc.x - vc.y * xc.y; s1 += vc.x * xc.y + vc.y * xc.x;
+                s0 += vd.x * xd.x - vd.y * xd.y; s1 += vd.x * xd.y + vd.y * xd.x;
+            }
+            if (VAR != 2)
             for (; q + 2 <= width; q += 2) {
                 double2 va = ldg_stream_d2(v2 + (q + 0) * 32), vb = ldg_stream_d2(v2 + (q + 1) * 32);
                 int ca = ldg_stream_i(c1 + (q + 0) * 32), cb = ldg_stream_i(c1 + (q + 1) * 32);
@@ -187,14 +212,14 @@ __global__ void __launch_bounds__(256, MINB) sell_spmv_kernel(const SellParams p
         if (p.slice_ovf != nullptr) {
             int k = p.slice_ovf[src];
             if (k >= 0)
-                for (; (uint32_t)k < p.novf && (p.ovf_rows[k] >> 5) == src; k++)
-                    if (p.ovf_rows[k] == row) {
+                for (; (uint32_t)k < p.novf && (p.ovf_slot[k] >> 5) == src; k++)
+                    if (p.ovf_slot[k] == slot) {
                         if (KIND == NGSB_REAL) s0 += p.ovf_sum[k];
                         else if (KIND == NGSB_COMPLEX) { s0 += p.ovf_sum[2 * k]; s1 += p.ovf_sum[2 * k + 1]; }
                         else { s0 += p.ovf_sum[3 * k]; s1 += p.ovf_sum[3 * k + 1]; s2 += p.ovf_sum[3 * k + 2]; }
                     }
         }
-        if (row < p.nrows) {
+        if (row != 0xffffffffu) {
             // y = s*sum (+ y) and this row's share of the fused dot
             if (KIND == NGSB_REAL) {
                 double r = p.sr * s0;
@@ -214,11 +239,11 @@ __global__ void __launch_bounds__(256, MINB) sell_spmv_kernel(const SellParams p
                 }
             } else {
                 double r0 = p.sr * s0, r1 = p.sr * s1, r2 = p.sr * s2;
-                double *yy = p.y + 3 * row;
+                double *yy = p.y + 3 * (size_t)row;
                 if (p.accumulate) { r0 += yy[0]; r1 += yy[1]; r2 += yy[2]; }
                 yy[0] = r0; yy[1] = r1; yy[2] = r2;
                 if (p.epi) {
-                    const double *v = p.dotvec + 3 * row;
+                    const double *v = p.dotvec + 3 * (size_t)row;
                     dr += v[0] * r0 + v[1] * r1 + v[2] * r2;
                 }
             }
@@ -303,23 +328,42 @@ __global__ void __launch_bounds__(256) sell_overflow_kernel(const uint64_t *__re
 // ------------------------------------------------------------------------------------------
 // conversion CSR -> SELL-32 on the device
 // ------------------------------------------------------------------------------------------
+// sigma-sort key of a row: (window of sigma consecutive rows, cap - min(len, cap)); a stable sort by it puts
+// the longest rows of every window first and keeps the natural order among rows of equal length
+__global__ void __launch_bounds__(256) sell_rowkey_kernel(const uint64_t *__restrict__ rowptr, uint64_t nrows, uint32_t cap, uint32_t sigma,
+                                                         uint64_t *__restrict__ key, uint32_t *__restrict__ id)
+{
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nrows) return;
+    const uint64_t l = rowptr[r + 1] - rowptr[r];
+    const uint32_t len = l > cap ? cap : (uint32_t)l;
+    key[r] = ((r / sigma) << 32) | (uint64_t)(cap - len);
+    id[r] = (uint32_t)r;
+}
+
+__global__ void __launch_bounds__(256) fill_u32_kernel(uint32_t *a, uint64_t begin, uint64_t end, uint32_t v, int iota)
+{
+    const uint64_t t = begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < end) a[t] = iota ? (uint32_t)t : v;
+}
+
 // per slice: padded length (entries) and the schedule key = smallest first column of its rows.  In a
 // finite-element numbering (vertices | edges | faces | cells) every row starts with a vertex dof of
 // its patch, so the key places slices of all entity blocks on one spatial axis.
 __global__ void __launch_bounds__(256) sell_width_kernel(const uint64_t *__restrict__ rowptr, const int32_t *__restrict__ col,
-                                                        uint64_t nrows, uint32_t nslices, uint32_t cap, int even,
+                                                        const uint32_t *__restrict__ row_of, uint32_t nslices, uint32_t cap, int even,
                                                         uint32_t *__restrict__ slice_len, uint32_t *__restrict__ slice_key)
 {
     const uint64_t s = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (s >= nslices) return;
-    const uint64_t row = s * 32 + lane;
+    const uint32_t row = row_of[s * 32 + lane];
     uint32_t len = 0, key = 0xffffffffu;
-    if (row < nrows) {
+    if (row != 0xffffffffu) {
         const uint64_t a = rowptr[row];
         uint64_t l = rowptr[row + 1] - a;
         len = l > cap ? cap : (uint32_t)l;
-        key = l > 0 ? (uint32_t)col[a] : (uint32_t)row;
+        key = l > 0 ? (uint32_t)col[a] : row;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -339,27 +383,22 @@ __global__ void __launch_bounds__(256) sell_gather_len_kernel(const uint32_t *__
     if (t == 0) slice_off[0] = 0;
 }
 
-__global__ void __launch_bounds__(256) iota_kernel(uint32_t *a, uint32_t n)
-{
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < n) a[t] = t;
-}
-
 template <int KIND>
 __global__ void __launch_bounds__(256) sell_fill_kernel(const uint64_t *__restrict__ rowptr, const int32_t *__restrict__ col,
-                                                       const double *__restrict__ val, uint64_t nrows, uint32_t nslices, uint32_t cap,
+                                                       const double *__restrict__ val, uint32_t nslices, uint32_t cap,
                                                        const uint64_t *__restrict__ slice_off, const uint32_t *__restrict__ slice_src,
-                                                       int32_t *__restrict__ scol, double *__restrict__ sval)
+                                                       const uint32_t *__restrict__ row_of, int32_t *__restrict__ scol,
+                                                       double *__restrict__ sval)
 {
     const uint64_t s = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (s >= nslices) return;
     const uint64_t off = slice_off[s];
     const uint32_t width = (uint32_t)((slice_off[s + 1] - off) >> 5);
-    const uint64_t row = (uint64_t)slice_src[s] * 32 + lane;
+    const uint32_t row = row_of[(uint64_t)slice_src[s] * 32 + lane];
     uint64_t a = 0;
     uint32_t len = 0;
-    if (row < nrows) {
+    if (row != 0xffffffffu) {
         a = rowptr[row];
         uint64_t l = rowptr[row + 1] - a;
         len = l > cap ? cap : (uint32_t)l;
@@ -385,6 +424,21 @@ __global__ void __launch_bounds__(256) sell_fill_kernel(const uint64_t *__restri
     }
 }
 
+// slots whose row is longer than cap -> (slot, row) list (order fixed afterwards by a host sort)
+__global__ void __launch_bounds__(256) sell_ovf_collect_kernel(const uint64_t *__restrict__ rowptr, const uint32_t *__restrict__ row_of,
+                                                              uint64_t nslots, uint32_t cap, uint32_t *__restrict__ list, uint32_t *__restrict__ count)
+{
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nslots) return;
+    const uint32_t row = row_of[t];
+    if (row == 0xffffffffu) return;
+    if (rowptr[row + 1] - rowptr[row] > cap) {
+        const uint32_t k = atomicAdd(count, 1u);
+        list[2 * k] = (uint32_t)t;
+        list[2 * k + 1] = row;
+    }
+}
+
 __global__ void __launch_bounds__(256) sell_ovf_copy_kernel(const uint64_t *__restrict__ rowptr, const int32_t *__restrict__ col,
                                                            const double *__restrict__ val, const uint32_t *__restrict__ orows,
                                                            const uint64_t *__restrict__ optr, uint32_t cap, int ms,
@@ -402,56 +456,96 @@ int sell_build(ngsb_csr *A, const uint64_t *h_rowptr)
 {
     ngsb_ctx *ctx = A->ctx;
     const size_t ms = kind_matscalars(A->kind);
-    A->nslices = (uint32_t)((A->h + 31) / 32);
+    const uint32_t ns = (uint32_t)((A->h + 31) / 32);
+    const uint64_t nslots = (uint64_t)ns * 32;
+    A->nslices = ns;
     // rows longer than cap keep their tail in the overflow CSR
     uint32_t cap = (uint32_t)std::max<double>(64.0, 4.0 * A->mean_row + 0.5);
     if (ctx->sell_cap > 0) cap = (uint32_t)ctx->sell_cap;
     cap = (cap + 1u) & ~1u;
     A->sell_cap = cap;
-    std::vector<uint32_t> orows;
-    std::vector<uint64_t> optr(1, 0);
-    std::vector<int32_t> slice_ovf;
-    for (size_t r = 0; r < A->h; r++) {
-        const uint64_t len = h_rowptr[r + 1] - h_rowptr[r];
-        if (len > cap) {
-            if (slice_ovf.empty()) slice_ovf.assign(A->nslices, -1);
-            if (slice_ovf[r >> 5] < 0) slice_ovf[r >> 5] = (int32_t)orows.size();
-            orows.push_back((uint32_t)r);
-            optr.push_back(optr.back() + (len - cap));
+    uint32_t novf = 0;
+    uint64_t natural_entries = 0;      // padded size of the natural (unsorted) slices
+    for (size_t r0 = 0; r0 < A->h; r0 += 32) {
+        uint64_t w = 0;
+        for (size_t r = r0; r < std::min<size_t>(A->h, r0 + 32); r++) {
+            const uint64_t len = h_rowptr[r + 1] - h_rowptr[r];
+            if (len > cap) novf++;
+            w = std::max<uint64_t>(w, std::min<uint64_t>(len, cap));
         }
+        natural_entries += 32 * w;
     }
-    A->novf = (uint32_t)orows.size();
-    NGSB_CUDA(cudaMalloc(&A->d_slice_off, ((size_t)A->nslices + 1) * sizeof(uint64_t)));
-    NGSB_CUDA(cudaMalloc(&A->d_slice_src, std::max<size_t>(1, A->nslices) * sizeof(uint32_t)));
-    if (A->nslices) {
-        const uint32_t ns = A->nslices;
-        const unsigned grid = (unsigned)(((uint64_t)ns * 32 + 255) / 256), grid1 = (ns + 255) / 256;
+    A->novf = novf;
+    // sigma-sorting pays when neighbouring rows differ in length (unstructured meshes: 30-60 % padding);
+    // where the natural slices are already tight (structured numberings) it only scatters the y writes (-5 %)
+    const bool tight = (double)natural_entries <= 1.05 * (double)std::max<size_t>(1, A->nnz);
+    NGSB_CUDA(cudaMalloc(&A->d_slice_off, ((size_t)ns + 1) * sizeof(uint64_t)));
+    NGSB_CUDA(cudaMalloc(&A->d_slice_src, std::max<size_t>(1, ns) * sizeof(uint32_t)));
+    NGSB_CUDA(cudaMalloc(&A->d_row_of, std::max<uint64_t>(32, nslots) * sizeof(uint32_t)));
+    if (ns == 0) {
+        NGSB_CUDA(cudaMemsetAsync(A->d_slice_off, 0, sizeof(uint64_t), ctx->stream));
+        A->sell_entries = 0;
+        NGSB_CUDA(cudaMalloc(&A->d_scol, 16));
+        NGSB_CUDA(cudaMalloc(&A->d_sval, 16));
+        NGSB_CUDA(cudaStreamSynchronize(ctx->stream));
+        return NGSB_OK;
+    }
+    const unsigned grid_rows = (unsigned)((A->h + 255) / 256), grid_slots = (unsigned)((nslots + 255) / 256), grid_sl = (ns + 255) / 256;
+    std::vector<void *> temps;
+    auto tmalloc = [&](void **p, size_t bytes) { cudaError_t e = cudaMalloc(p, bytes ? bytes : 16); if (e == cudaSuccess) temps.push_back(*p); return e; };
+    auto cleanup = [&]() { for (void *p : temps) cudaFree(p); temps.clear(); };
+    cudaError_t e1 = cudaSuccess;
+    int rc = NGSB_OK;
+    // ---- 1. row order: sigma-sort by length inside windows (SELL-C-sigma), identity when sigma <= 1
+    const uint32_t sigma = ctx->sell_sigma >= 0 ? (uint32_t)ctx->sell_sigma : (tight ? 0u : 4096u);
+    fill_u32_kernel<<<grid_slots, 256, 0, ctx->stream>>>(A->d_row_of, A->h, nslots, 0xffffffffu, 0);
+    if (sigma > 1) {
+        uint64_t *d_k = nullptr, *d_k2 = nullptr;
+        uint32_t *d_id = nullptr;
+        void *d_tmp = nullptr;
+        e1 = tmalloc((void **)&d_k, A->h * sizeof(uint64_t));
+        if (e1 == cudaSuccess) e1 = tmalloc((void **)&d_k2, A->h * sizeof(uint64_t));
+        if (e1 == cudaSuccess) e1 = tmalloc((void **)&d_id, A->h * sizeof(uint32_t));
+        if (e1 == cudaSuccess) {
+            sell_rowkey_kernel<<<grid_rows, 256, 0, ctx->stream>>>(A->d_rowptr, A->h, cap, sigma, d_k, d_id);
+            size_t tmp_bytes = 0;
+            cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_k, d_k2, d_id, A->d_row_of, (int)A->h, 0, 64, ctx->stream);
+            e1 = tmalloc(&d_tmp, tmp_bytes);
+            if (e1 == cudaSuccess) e1 = cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_k, d_k2, d_id, A->d_row_of, (int)A->h, 0, 64, ctx->stream);
+        }
+        if (e1 == cudaSuccess) e1 = cudaStreamSynchronize(ctx->stream);
+        cleanup();
+    } else {
+        fill_u32_kernel<<<grid_rows, 256, 0, ctx->stream>>>(A->d_row_of, 0, A->h, 0, 1);
+    }
+    if (e1 != cudaSuccess) { set_error("SELL build (row order): %s", cudaGetErrorString(e1)); return NGSB_ERR_CUDA; }
+    // ---- 2. slice widths, schedule, offsets
+    {
         uint32_t *d_len = nullptr, *d_key = nullptr, *d_key2 = nullptr, *d_id = nullptr;
         void *d_tmp = nullptr;
-        auto cleanup = [&]() { cudaFree(d_len); cudaFree(d_key); cudaFree(d_key2); cudaFree(d_id); cudaFree(d_tmp); };
-        cudaError_t e1 = cudaMalloc(&d_len, ns * sizeof(uint32_t));
-        if (e1 == cudaSuccess) e1 = cudaMalloc(&d_key, ns * sizeof(uint32_t));
-        if (e1 == cudaSuccess) e1 = cudaMalloc(&d_key2, ns * sizeof(uint32_t));
-        if (e1 == cudaSuccess) e1 = cudaMalloc(&d_id, ns * sizeof(uint32_t));
+        e1 = tmalloc((void **)&d_len, ns * sizeof(uint32_t));
+        if (e1 == cudaSuccess) e1 = tmalloc((void **)&d_key, ns * sizeof(uint32_t));
+        if (e1 == cudaSuccess) e1 = tmalloc((void **)&d_key2, ns * sizeof(uint32_t));
+        if (e1 == cudaSuccess) e1 = tmalloc((void **)&d_id, ns * sizeof(uint32_t));
         if (e1 != cudaSuccess) { cleanup(); set_error("SELL build: %s", cudaGetErrorString(e1)); return NGSB_ERR_NOMEM; }
-        sell_width_kernel<<<grid, 256, 0, ctx->stream>>>(A->d_rowptr, A->d_col, A->h, ns, cap, A->kind == NGSB_REAL ? 1 : 0, d_len, d_key);
-        iota_kernel<<<grid1, 256, 0, ctx->stream>>>(d_id, ns);
+        sell_width_kernel<<<grid_slots, 256, 0, ctx->stream>>>(A->d_rowptr, A->d_col, A->d_row_of, ns, cap, A->kind == NGSB_REAL ? 1 : 0, d_len, d_key);
+        fill_u32_kernel<<<grid_sl, 256, 0, ctx->stream>>>(d_id, 0, ns, 0, 1);
         // 3x3 blocks: measured slower with the schedule on B200 (x is a small share of the traffic), keep natural order
         const bool schedule = ctx->sell_schedule == 1 ? A->kind != NGSB_BLOCK3 : ctx->sell_schedule == 2;
         if (schedule) {
             // schedule: slices ordered by key (stable radix sort keeps the natural order among equal keys)
             size_t tmp_bytes = 0;
             cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_key, d_key2, d_id, A->d_slice_src, (int)ns, 0, 32, ctx->stream);
-            e1 = cudaMalloc(&d_tmp, tmp_bytes);
+            e1 = tmalloc(&d_tmp, tmp_bytes);
             if (e1 == cudaSuccess) e1 = cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_key, d_key2, d_id, A->d_slice_src, (int)ns, 0, 32, ctx->stream);
         } else {
             e1 = cudaMemcpyAsync(A->d_slice_src, d_id, ns * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream);
         }
         if (e1 == cudaSuccess) {
-            sell_gather_len_kernel<<<grid1, 256, 0, ctx->stream>>>(d_len, A->d_slice_src, ns, A->d_slice_off);
+            sell_gather_len_kernel<<<grid_sl, 256, 0, ctx->stream>>>(d_len, A->d_slice_src, ns, A->d_slice_off);
             e1 = cudaGetLastError();
         }
-        int rc = e1 == cudaSuccess ? device_scan_u64(ctx, A->d_slice_off, (uint64_t)ns + 1) : NGSB_ERR_CUDA;
+        rc = e1 == cudaSuccess ? device_scan_u64(ctx, A->d_slice_off, (uint64_t)ns + 1) : NGSB_ERR_CUDA;
         if (rc == NGSB_OK) {
             e1 = cudaMemcpyAsync(&A->sell_entries, A->d_slice_off + ns, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream);
             if (e1 == cudaSuccess) e1 = cudaStreamSynchronize(ctx->stream);
@@ -459,33 +553,54 @@ int sell_build(ngsb_csr *A, const uint64_t *h_rowptr)
         cleanup();
         if (e1 != cudaSuccess) { set_error("SELL build (schedule): %s", cudaGetErrorString(e1)); return NGSB_ERR_CUDA; }
         if (rc != NGSB_OK) return rc;
-    } else {
-        NGSB_CUDA(cudaMemsetAsync(A->d_slice_off, 0, sizeof(uint64_t), ctx->stream));
-        A->sell_entries = 0;
     }
-    cudaError_t e = cudaMalloc(&A->d_scol, std::max<size_t>(16, A->sell_entries * sizeof(int32_t)));
-    if (e == cudaSuccess) e = cudaMalloc(&A->d_sval, std::max<size_t>(16, A->sell_entries * ms * sizeof(double)));
-    if (e != cudaSuccess) { set_error("SELL build: cudaMalloc of %llu entries failed: %s", (unsigned long long)A->sell_entries, cudaGetErrorString(e)); return NGSB_ERR_NOMEM; }
-    if (A->nslices) {
-        const unsigned grid = (unsigned)(((uint64_t)A->nslices * 32 + 255) / 256);
-        if (A->kind == NGSB_REAL) sell_fill_kernel<NGSB_REAL><<<grid, 256, 0, ctx->stream>>>(A->d_rowptr, A->d_col, A->d_val, A->h, A->nslices, cap, A->d_slice_off, A->d_slice_src, A->d_scol, A->d_sval);
-        else if (A->kind == NGSB_COMPLEX) sell_fill_kernel<NGSB_COMPLEX><<<grid, 256, 0, ctx->stream>>>(A->d_rowptr, A->d_col, A->d_val, A->h, A->nslices, cap, A->d_slice_off, A->d_slice_src, A->d_scol, A->d_sval);
-        else sell_fill_kernel<NGSB_BLOCK3><<<grid, 256, 0, ctx->stream>>>(A->d_rowptr, A->d_col, A->d_val, A->h, A->nslices, cap, A->d_slice_off, A->d_slice_src, A->d_scol, A->d_sval);
-        NGSB_CUDA(cudaGetLastError());
-    }
-    if (A->novf) {
+    // ---- 3. fill
+    e1 = cudaMalloc(&A->d_scol, std::max<size_t>(16, A->sell_entries * sizeof(int32_t)));
+    if (e1 == cudaSuccess) e1 = cudaMalloc(&A->d_sval, std::max<size_t>(16, A->sell_entries * ms * sizeof(double)));
+    if (e1 != cudaSuccess) { set_error("SELL build: cudaMalloc of %llu entries failed: %s", (unsigned long long)A->sell_entries, cudaGetErrorString(e1)); return NGSB_ERR_NOMEM; }
+    if (A->kind == NGSB_REAL) sell_fill_kernel<NGSB_REAL><<<grid_slots, 256, 0, ctx->stream>>>(A->d_rowptr, A->d_col, A->d_val, ns, cap, A->d_slice_off, A->d_slice_src, A->d_row_of, A->d_scol, A->d_sval);
+    else if (A->kind == NGSB_COMPLEX) sell_fill_kernel<NGSB_COMPLEX><<<grid_slots, 256, 0, ctx->stream>>>(A->d_rowptr, A->d_col, A->d_val, ns, cap, A->d_slice_off, A->d_slice_src, A->d_row_of, A->d_scol, A->d_sval);
+    else sell_fill_kernel<NGSB_BLOCK3><<<grid_slots, 256, 0, ctx->stream>>>(A->d_rowptr, A->d_col, A->d_val, ns, cap, A->d_slice_off, A->d_slice_src, A->d_row_of, A->d_scol, A->d_sval);
+    NGSB_CUDA(cudaGetLastError());
+    // ---- 4. overflow CSR of the rows longer than cap
+    if (novf) {
+        uint32_t *d_list = nullptr, *d_count = nullptr;
+        NGSB_CUDA(cudaMalloc(&d_list, (size_t)novf * 2 * sizeof(uint32_t)));
+        NGSB_CUDA(cudaMalloc(&d_count, sizeof(uint32_t)));
+        NGSB_CUDA(cudaMemsetAsync(d_count, 0, sizeof(uint32_t), ctx->stream));
+        sell_ovf_collect_kernel<<<grid_slots, 256, 0, ctx->stream>>>(A->d_rowptr, A->d_row_of, nslots, cap, d_list, d_count);
+        std::vector<uint32_t> list((size_t)novf * 2);
+        NGSB_CUDA(cudaMemcpyAsync(list.data(), d_list, list.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        NGSB_CUDA(cudaStreamSynchronize(ctx->stream));
+        cudaFree(d_list);
+        cudaFree(d_count);
+        std::vector<std::pair<uint32_t, uint32_t>> pairs(novf);
+        for (uint32_t k = 0; k < novf; k++) pairs[k] = std::make_pair(list[2 * k], list[2 * k + 1]);
+        std::sort(pairs.begin(), pairs.end());
+        std::vector<uint32_t> oslot(novf), orows(novf);
+        std::vector<uint64_t> optr(1, 0);
+        std::vector<int32_t> slice_ovf(ns, -1);
+        for (uint32_t k = 0; k < novf; k++) {
+            oslot[k] = pairs[k].first;
+            orows[k] = pairs[k].second;
+            if (slice_ovf[oslot[k] >> 5] < 0) slice_ovf[oslot[k] >> 5] = (int32_t)k;
+            optr.push_back(optr.back() + (h_rowptr[orows[k] + 1] - h_rowptr[orows[k]] - cap));
+        }
         const uint64_t on = optr.back();
-        NGSB_CUDA(cudaMalloc(&A->d_ovf_rows, orows.size() * sizeof(uint32_t)));
+        NGSB_CUDA(cudaMalloc(&A->d_ovf_slot, novf * sizeof(uint32_t)));
+        NGSB_CUDA(cudaMalloc(&A->d_ovf_rows, novf * sizeof(uint32_t)));
         NGSB_CUDA(cudaMalloc(&A->d_ovf_ptr, optr.size() * sizeof(uint64_t)));
         NGSB_CUDA(cudaMalloc(&A->d_slice_ovf, slice_ovf.size() * sizeof(int32_t)));
         NGSB_CUDA(cudaMalloc(&A->d_ovf_col, on * sizeof(int32_t)));
         NGSB_CUDA(cudaMalloc(&A->d_ovf_val, on * ms * sizeof(double)));
-        NGSB_CUDA(cudaMalloc(&A->d_ovf_sum, orows.size() * 3 * sizeof(double)));
-        NGSB_CUDA(cudaMemcpyAsync(A->d_ovf_rows, orows.data(), orows.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+        NGSB_CUDA(cudaMalloc(&A->d_ovf_sum, (size_t)novf * 3 * sizeof(double)));
+        NGSB_CUDA(cudaMemcpyAsync(A->d_ovf_slot, oslot.data(), novf * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+        NGSB_CUDA(cudaMemcpyAsync(A->d_ovf_rows, orows.data(), novf * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
         NGSB_CUDA(cudaMemcpyAsync(A->d_ovf_ptr, optr.data(), optr.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
         NGSB_CUDA(cudaMemcpyAsync(A->d_slice_ovf, slice_ovf.data(), slice_ovf.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
-        sell_ovf_copy_kernel<<<A->novf, 256, 0, ctx->stream>>>(A->d_rowptr, A->d_col, A->d_val, A->d_ovf_rows, A->d_ovf_ptr, cap, (int)ms, A->d_ovf_col, A->d_ovf_val);
+        sell_ovf_copy_kernel<<<novf, 256, 0, ctx->stream>>>(A->d_rowptr, A->d_col, A->d_val, A->d_ovf_rows, A->d_ovf_ptr, cap, (int)ms, A->d_ovf_col, A->d_ovf_val);
         NGSB_CUDA(cudaGetLastError());
+        NGSB_CUDA(cudaStreamSynchronize(ctx->stream));
     }
     NGSB_CUDA(cudaStreamSynchronize(ctx->stream));
     return NGSB_OK;
@@ -493,7 +608,7 @@ int sell_build(ngsb_csr *A, const uint64_t *h_rowptr)
 
 void sell_free(ngsb_csr *A)
 {
-    cudaFree(A->d_slice_off); cudaFree(A->d_slice_src); cudaFree(A->d_scol); cudaFree(A->d_sval);
+    cudaFree(A->d_slice_off); cudaFree(A->d_slice_src); cudaFree(A->d_row_of); cudaFree(A->d_ovf_slot); cudaFree(A->d_scol); cudaFree(A->d_sval);
     cudaFree(A->d_ovf_rows); cudaFree(A->d_ovf_ptr); cudaFree(A->d_slice_ovf);
     cudaFree(A->d_ovf_col); cudaFree(A->d_ovf_val); cudaFree(A->d_ovf_sum);
 }
@@ -504,9 +619,9 @@ int sell_launch(const SpmvArgs &a)
     ngsb_ctx *ctx = A->ctx;
     SellParams p;
     memset(&p, 0, sizeof(p));
-    p.slice_off = A->d_slice_off; p.slice_src = A->d_slice_src; p.scol = A->d_scol; p.sval = A->d_sval;
+    p.slice_off = A->d_slice_off; p.slice_src = A->d_slice_src; p.row_of = A->d_row_of; p.scol = A->d_scol; p.sval = A->d_sval;
     p.slice_ovf = A->novf ? A->d_slice_ovf : nullptr;
-    p.ovf_rows = A->d_ovf_rows; p.ovf_sum = A->d_ovf_sum; p.novf = A->novf;
+    p.ovf_slot = A->d_ovf_slot; p.ovf_sum = A->d_ovf_sum; p.novf = A->novf;
     p.nslices = A->nslices; p.nrows = A->h;
     p.x = a.x; p.y = a.y; p.sr = a.sr; p.si = A->kind == NGSB_COMPLEX ? a.si : 0.0;
     p.accumulate = a.accumulate ? 1 : 0; p.epi = a.epi; p.dot_conj = a.dot_conj;
@@ -531,11 +646,11 @@ int sell_launch(const SpmvArgs &a)
         case 2: kern = sell_spmv_kernel<NGSB_REAL, 1, 8>; break;
         default: kern = sell_spmv_kernel<NGSB_REAL, 2, 4>; break;
         }
-    } else if (A->kind == NGSB_COMPLEX) kern = sell_spmv_kernel<NGSB_COMPLEX, 0, 6>;
+    } else if (A->kind == NGSB_COMPLEX) kern = var == 1 ? sell_spmv_kernel<NGSB_COMPLEX, 0, 5> : sell_spmv_kernel<NGSB_COMPLEX, 2, 4>;
     else kern = sell_spmv_kernel<NGSB_BLOCK3, 0, 5>;
     int occ = 0;
     NGSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, 0));
-    long cps = ctx->spmv_ctas_per_sm > 0 ? ctx->spmv_ctas_per_sm : (A->kind == NGSB_REAL && var == 0 ? 8 : (occ > 0 ? occ : 4));
+    long cps = ctx->spmv_ctas_per_sm > 0 ? ctx->spmv_ctas_per_sm : (A->kind != NGSB_BLOCK3 && var == 0 ? 8 : (occ > 0 ? occ : 4));
     uint64_t grid = (uint64_t)ctx->sm_count * (uint64_t)cps;
     const uint64_t need = ((uint64_t)A->nslices + 7) / 8;
     if (grid > need) grid = need;

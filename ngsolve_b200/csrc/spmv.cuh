@@ -38,7 +38,9 @@ struct ngsb_csr {
     uint64_t sell_entries = 0;      // padded entries
     uint32_t sell_cap = 0;          // longest row part kept in a slice; the rest lives in the overflow CSR
     uint64_t *d_slice_off = nullptr;
-    uint32_t *d_slice_src = nullptr;   // schedule: position t -> original slice
+    uint32_t *d_slice_src = nullptr;   // schedule: position t -> slice of the sigma-sorted row order
+    uint32_t *d_row_of = nullptr;      // slot -> row (sigma-sorted), 0xffffffff = padding
+    uint32_t *d_ovf_slot = nullptr;
     int32_t *d_scol = nullptr;
     double *d_sval = nullptr;
     uint32_t novf = 0;

@@ -281,6 +281,25 @@ def _random_csr(rng, n, rowlens, kind, width=None):
     return rowptr, cols.astype(np.int32), val
 
 
+def test_sell_sigma_sorting_cuts_padding(la):
+    """netgen-mesh fixture (row lengths 20..273 in natural order): sorting rows by length inside windows
+    (SELL-C-sigma) must not change results and must remove most of the slice padding."""
+    g = load_golden("poisson_h1p3")
+    ctx = la.default_context()
+    x = la.BaseVector(np.asarray(g["x"]))
+    ys, pads = [], []
+    for sigma in (0, -1):
+        ctx.set_option("sell_sigma", sigma)
+        try:
+            dev = host_matrix(la, g).CreateDeviceMatrix()
+        finally:
+            ctx.set_option("sell_sigma", -1)
+        ys.append((dev * x).Evaluate().NumPy())
+        pads.append(dev.Layout()[0] / dev.nze - 1.0)
+        assert relerr(ys[-1], g["y_mult"]) <= SPMV_TOL
+    assert pads[1] < 0.12 < pads[0], pads
+
+
 @pytest.mark.parametrize("kind", [0, 1, 3])
 @pytest.mark.parametrize("algo", [3, 2, 1])
 def test_ragged_and_long_rows(la, kind, algo):

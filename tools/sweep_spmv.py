@@ -36,7 +36,7 @@ def run(tag, reps=20, **opts):
     results.append(dict(tag=tag, ms=ms, gbs=gbs, **opts))
     print("%-40s %8.3f ms %8.1f GB/s  %s" % (tag, ms, gbs, opts), flush=True)
     for k in opts:
-        ctx.set_option(k, 1 if k == "sell_schedule" else 0)
+        ctx.set_option(k, 1 if k == "sell_schedule" else (-1 if k == "sell_sigma" else 0))
     del A, y
 
 
@@ -44,6 +44,14 @@ print("system: m=%d order=%d kind=%d ndof=%d" % (m, order, kind, box.ndof))
 if mode == "ncu":
     run("sell", reps=2, spmv_algo=3)
     run("stream default", reps=2, spmv_algo=2)
+    sys.exit(0)
+if mode == "sigma":
+    for sigma in (-1, 0):
+        run("sell sigma=%d" % sigma, reps=10, spmv_algo=3, sell_sigma=sigma)
+    ctx.set_option("sell_sigma", -1)
+    if kind == 3:
+        for sched in (2, 0):
+            run("sell block3 sched=%d" % sched, reps=10, spmv_algo=3, sell_schedule=sched)
     sys.exit(0)
 if mode == "schedncu":
     for sched in (1, 0):
