@@ -38,7 +38,8 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--size", type=int, default=155, help="cubes per axis of the global grid; dofs = (3*size+1)^3")
+    ap.add_argument("--size", type=int, default=160, help="cubes per axis of the global grid; dofs = (3*size+1)^3 "
+                    "(160 -> 111 M dofs; divisible by 8 so that the z-slabs of the multi-GPU runs are equal)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-full-solve", action="store_true")

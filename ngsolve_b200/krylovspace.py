@@ -11,7 +11,7 @@ from math import sqrt
 
 import numpy as np
 
-from .la import BaseMatrix, BaseVector, Norm  # noqa: F401
+from .la import BaseMatrix, BaseVector, Norm, Projector  # noqa: F401
 
 
 class LinearSolver(BaseMatrix):
@@ -20,9 +20,10 @@ class LinearSolver(BaseMatrix):
     def __init__(self, mat, pre=None, freedofs=None, tol=None, maxiter=100, atol=None, callback=None, printrates=False):
         if atol is None and tol is None:
             tol = 1e-12
-        if pre is None:
-            raise ValueError("a preconditioner is required (the Projector path is not part of this package yet)")
+        assert (freedofs is None) != (pre is None)      # either pre or freedofs must be given (python/krylovspace.py:78)
         self.mat = mat.CreateDeviceMatrix()
+        if pre is None:
+            pre = Projector(freedofs, True, ctx=self.mat.ctx)
         self.pre = pre.CreateDeviceMatrix() if hasattr(pre, "CreateDeviceMatrix") else pre
         self.tol, self.atol, self.maxiter, self.callback, self.printrates = tol, atol, maxiter, callback, printrates
         self.residuals, self.iterations = [], 0

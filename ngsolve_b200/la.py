@@ -23,9 +23,9 @@ import numpy as np
 from . import _capi
 from ._capi import NgsbError, check, scal2, REAL, COMPLEX, BLOCK3
 
-__all__ = ["NgsbError", "Context", "default_context", "BaseVector", "UnifiedVector", "BaseMatrix", "SparseMatrix",
-           "DevSparseMatrix", "JacobiPrecond", "DevJacobiMatrix", "CGSolver", "DevCGSolver", "GMRESSolver",
-           "CreateDevMatrix", "InnerProduct", "Norm", "BitArray"]
+__all__ = ["NgsbError", "Context", "default_context", "BaseVector", "UnifiedVector", "UnifiedScalar", "BaseMatrix",
+           "SparseMatrix", "DevSparseMatrix", "JacobiPrecond", "DevJacobiMatrix", "DiagonalMatrix", "Projector", "CGSolver",
+           "DevCGSolver", "GMRESSolver", "CreateDevMatrix", "InnerProduct", "Norm", "BitArray"]
 
 
 def _np_ptr(a):
@@ -350,7 +350,10 @@ class BaseVector:
 
     def Scale(self, s):
         self._dev_write()
-        check(_capi.lib().ngsb_vec_scale(self.handle, scal2(s)))
+        if isinstance(s, UnifiedScalar):
+            check(_capi.lib().ngsb_vec_scale_dev(self.handle, s.handle))
+        else:
+            check(_capi.lib().ngsb_vec_scale(self.handle, scal2(s)))
         return self
 
     def Set(self, s, x):
@@ -362,13 +365,24 @@ class BaseVector:
     def Add(self, s, x):
         x._dev_read()
         self._dev_write()
-        check(_capi.lib().ngsb_vec_axpy(self.handle, scal2(s), x.handle))
+        if isinstance(s, UnifiedScalar):          # BaseVector::Add(BaseScalar&, v), linalg/basevector.cpp:292-298
+            check(_capi.lib().ngsb_vec_axpy_dev(self.handle, s.handle, x.handle))
+        else:
+            check(_capi.lib().ngsb_vec_axpy(self.handle, scal2(s), x.handle))
         return self
 
-    def InnerProduct(self, other, conjugate=True):
+    def CreateScalar(self):
+        return UnifiedScalar(ctx=self.ctx)
+
+    def InnerProduct(self, other, scal=None, conjugate=True):
+        if isinstance(scal, bool):                # InnerProduct(other, conjugate) positional form
+            scal, conjugate = None, scal
         other = _as_vec(other)
         self._dev_read()
         other._dev_read()
+        if scal is not None:                      # InnerProduct(v2, BaseScalar&): result stays on the device
+            check(_capi.lib().ngsb_vec_dot_dev(self.handle, other.handle, 1 if (conjugate and self.is_complex) else 0, scal.handle))
+            return scal
         out = (C.c_double * 2)()
         check(_capi.lib().ngsb_vec_dot(self.handle, other.handle, 1 if (conjugate and self.is_complex) else 0, out))
         return complex(out[0], out[1]) if self.is_complex else out[0]
@@ -431,6 +445,42 @@ class BaseVector:
         return s * _as_expr(self)
 
     def Evaluate(self):
+        return self
+
+
+class UnifiedScalar:
+    """Device-resident scalar: ngscuda UnifiedScalar / BaseScalar (ngscuda/unifiedvector.hpp:107-136,
+    linalg/basescalar.hpp:17-29).  Lets a solver keep alpha = rz/pq etc. on the device:
+    `x.InnerProduct(y, scal)`, `y.Add(scal, x)`, `x.Scale(scal)`, `a.Div(b, c)`, `a.Neg(b)`."""
+
+    def __init__(self, value=0.0, ctx=None):
+        self.ctx = ctx or default_context()
+        h = C.c_void_p()
+        check(_capi.lib().ngsb_scalar_create(self.ctx.handle, C.byref(h)))
+        self.handle = h
+        self._fin = weakref.finalize(self, _capi.lib().ngsb_scalar_destroy, h)
+        self.Set(value)
+
+    def Set(self, v):
+        check(_capi.lib().ngsb_scalar_set(self.handle, scal2(v)))
+
+    def Get(self):
+        out = (C.c_double * 2)()
+        check(_capi.lib().ngsb_scalar_get(self.handle, out))
+        return complex(out[0], out[1]) if out[1] != 0.0 else out[0]
+
+    GetD = Get
+
+    def Div(self, a, b):          # self = a / b
+        check(_capi.lib().ngsb_scalar_div(self.handle, a.handle, b.handle))
+        return self
+
+    def Neg(self, a):             # self = -a
+        check(_capi.lib().ngsb_scalar_neg(self.handle, a.handle))
+        return self
+
+    def Copy(self, a):
+        check(_capi.lib().ngsb_scalar_copy(self.handle, a.handle))
         return self
 
 
@@ -690,6 +740,8 @@ class DevJacobiMatrix(BaseMatrix):
             inv = np.ascontiguousarray(invdiag)
             self.is_complex, self.entrysize = np.iscomplexobj(inv), entrysize
             n = inv.size // (entrysize * entrysize)
+            if bits is not None and len(bits) < (n + 7) // 8:
+                raise NgsbError("Projector/DiagonalMatrix: BitArray of %d bits for %d dofs" % (8 * len(bits), n))
             inv = inv.astype(np.complex128 if self.is_complex else np.float64).reshape(-1)
             check(_capi.lib().ngsb_jacobi_create(self.ctx.handle, n, _np_ptr(inv), _kind(self.is_complex, entrysize),
                                                  _np_ptr(bits) if bits is not None else None, C.byref(h)))
@@ -713,6 +765,23 @@ class DevJacobiMatrix(BaseMatrix):
         out = np.empty(self.height * ms, dtype=np.complex128 if self.is_complex else np.float64)
         check(_capi.lib().ngsb_jacobi_download(self.handle, _np_ptr(out)))
         return out
+
+
+def DiagonalMatrix(diag, ctx=None):
+    """DiagonalMatrix<double|Complex> on the device (linalg/diagonalmatrix.hpp:12-80; DevDiagonalMatrix,
+    ngscuda/cuda_linalg.cpp:117-123, 321-366): y = diag .* x"""
+    d = diag.NumPy() if isinstance(diag, BaseVector) else np.asarray(diag)
+    return DevJacobiMatrix(invdiag=d, ctx=ctx)
+
+
+def Projector(mask, range=True, ctx=None):
+    """Projector(mask, range): keeps (range=True) or clears (range=False) the dofs of the BitArray
+    (linalg/special_matrix.hpp; DevProjector, ngscuda/cuda_linalg.cpp:887-967).  It is what
+    python/krylovspace.py:79 puts in place of a missing preconditioner: Projector(freedofs, True)."""
+    b = mask if isinstance(mask, BitArray) else BitArray(mask)
+    n = b.n
+    bits = b.bytes if range else np.bitwise_not(b.bytes)
+    return DevJacobiMatrix(invdiag=np.ones(n), freedofs=BitArray(bits), ctx=ctx)
 
 
 # ------------------------------------------------------------------------------------------------

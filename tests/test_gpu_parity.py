@@ -408,3 +408,61 @@ def test_dots_are_deterministic(la):
     vals = {x.InnerProduct(y) for _ in range(5)}
     assert len(vals) == 1
     assert abs(vals.pop() - orc.inner(a, b)) <= 1e-12 * np.linalg.norm(a) * np.linalg.norm(b)
+
+
+def test_device_scalars_drive_a_cg_iteration(la):
+    """UnifiedScalar / BaseScalar hooks: the DevCGSolver formulation with every scalar on
+    the device (ngscuda/cuda_krylov.cpp:88-140) gives the same iterates as host scalars."""
+    g = load_golden("poisson_h1p3")
+    dev = host_matrix(la, g).CreateDeviceMatrix()
+    jac = dev.CreateSmoother(la.BitArray(g["freebits"]))
+    f = vec(la, g, g["f"])
+    x, r, p, z, ap = (f.CreateVector() for _ in range(5))
+    rz, rz_old, pq, alpha, neg_alpha, beta = (f.CreateScalar() for _ in range(6))
+    x[:] = 0
+    r.data = f
+    z.data = jac * r
+    p.data = z
+    r.InnerProduct(z, rz)
+    for _ in range(25):
+        ap.data = dev * p
+        p.InnerProduct(ap, pq)
+        alpha.Div(rz, pq)
+        neg_alpha.Neg(alpha)
+        x.Add(alpha, p)
+        r.Add(neg_alpha, ap)
+        z.data = jac * r
+        rz_old.Copy(rz)
+        r.InnerProduct(z, rz)
+        beta.Div(rz, rz_old)
+        p.Scale(beta)
+        p.data += z
+    inv = la.CGSolver(dev, jac, precision=1e-30, maxsteps=25)
+    u = (inv * f).Evaluate()
+    assert relerr(x.NumPy(), u.NumPy()) <= 1e-12
+    assert abs(rz.Get() - inv.history[-1]) <= 1e-10 * inv.history[0]
+
+
+def test_projector_and_diagonal_matrix(la):
+    """Projector(freedofs, True) as the default 'preconditioner' of the python solvers and
+    DiagonalMatrix, both as device operators."""
+    from ngsolve_b200 import krylovspace
+    g = load_golden("poisson_h1p3")
+    n = int(g["n"])
+    free = np.unpackbits(g["freebits"], bitorder="little")[:n].astype(bool)
+    x = np.asarray(g["x"])
+    P = la.Projector(la.BitArray(free), True)
+    Q = la.Projector(la.BitArray(free), False)
+    xv = la.BaseVector(x)
+    assert np.array_equal((P * xv).Evaluate().NumPy(), np.where(free, x, 0.0))
+    assert np.array_equal((Q * xv).Evaluate().NumPy(), np.where(free, 0.0, x))
+    D = la.DiagonalMatrix(np.asarray(g["y0"]))
+    assert relerr((D * xv).Evaluate().NumPy(), np.asarray(g["y0"]) * x) <= 1e-16
+    # unpreconditioned python CG: freedofs instead of pre (python/krylovspace.py:78-79)
+    dev = host_matrix(la, g).CreateDeviceMatrix()
+    inv = krylovspace.CGSolver(dev, freedofs=la.BitArray(free), tol=1e-8, maxiter=3000)
+    u = inv.Solve(rhs=vec(la, g, g["f"]))
+    oA = orc.Csr(g["rowptr"], g["col"], g["val"], 0)
+    r = np.asarray(g["f"]) - oA.mult(u.NumPy())
+    assert np.linalg.norm(r[free]) <= 1e-6 * np.linalg.norm(np.asarray(g["f"])[free])
+    assert 10 < inv.iterations < 3000

@@ -95,3 +95,30 @@ def test_large_system_properties(mods, m):
     # ngsb_cg_solve_host (host buffers) gives the same answer as the device-vector call
     uh, steps, _ = la.cg_solve_host(A, A.CreateSmoother(box.freedofs()), f.NumPy(), precision=1e-6, maxsteps=3000)
     assert steps == inv.GetSteps() and np.array_equal(uh, u.NumPy())
+
+
+def test_elasticity_cg_and_helmholtz_gmres_match_oracle_on_generated_systems(mods):
+    """configs 2 and 5 in small: 3x3-block elasticity CG and complex GMRes on generated systems, steps within
+    +-2 of the oracle's restatement of the reference solvers."""
+    la, W = mods
+    box = W.FemBox((8, 8, 8), order=3, kind=W.BLOCK3, lame=(1.0, 0.7))
+    rp, col, val, rhs = box.host_csr()
+    free = box.freedofs()
+    A, f = box.device_system()
+    inv = la.CGSolver(A, A.CreateSmoother(free), precision=1e-8, maxsteps=5000)
+    u = (inv * f).Evaluate().NumPy().reshape(-1)
+    oA = orc.Csr(rp, col, val, 3)
+    ou, osteps, ohist = orc.cg_solve(oA, orc.Jacobi(oA, free.bytes), rhs, prec=1e-8, maxsteps=5000)
+    assert abs(inv.GetSteps() - osteps) <= 2, (inv.GetSteps(), osteps)
+    assert np.max(np.abs(u - ou)) <= 1e-6 * np.max(np.abs(ou))
+    # complex shifted Laplace (definite enough for GMRes to converge quickly)
+    boxc = W.FemBox((7, 7, 7), order=3, kind=W.COMPLEX, mass=5.0 + 3.0j)
+    rp, col, val, rhs = boxc.host_csr()
+    freec = boxc.freedofs()
+    Ac, fc = boxc.device_system()
+    g = la.GMRESSolver(Ac, Ac.CreateSmoother(freec), precision=1e-8, maxsteps=150)
+    x = (g * fc).Evaluate().NumPy()
+    oAc = orc.Csr(rp, col, val, 1)
+    ox, osteps, _ = orc.gmres_solve(oAc, orc.Jacobi(oAc, freec.bytes), rhs, prec=1e-8, maxsteps=150)
+    assert abs(g.GetSteps() - osteps) <= 2, (g.GetSteps(), osteps)
+    assert np.max(np.abs(x - ox)) <= 1e-6 * np.max(np.abs(ox))
