@@ -126,7 +126,7 @@ def run_reference(args):
         "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": dt,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -353,7 +353,9 @@ def run_b200(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(Wm, 3), "ms_per_step": ms / K,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(m), "global_dofs": global_ndof, "nnz_total": nnz_sum, "rows_per_gpu": ndof_local,
-                       "precond": "Jacobi (freedofs-masked)", "partition": "1 box" if world == 1 else "%d z-slabs of elements, NCCL halo" % world,
+                       "precond": "Jacobi (freedofs-masked)",
+                       "partition": "1 box" if world == 1 else "%d z-slabs of elements, %s" % (world, "interface exchange + scalar all-reduces by P2P stores "
+                                    "into peer memory inside the solver kernels (no NCCL call per iteration)" if pmat.peer_memory else "NCCL send/recv halo + NCCL all-reduce"),
                        "l2": "inputs (%.1f GB per GPU) far larger than the 126 MB L2" % (b_spmv / 1e9),
                        "setup_s": setup_s, "full_solve": full,
                        "cg_gbs_per_gpu": b_cg * value / 1e9, "cg_bytes_per_iteration_per_gpu": b_cg,
@@ -369,13 +371,27 @@ def run_b200(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """the one JSON line, on the process's original stdout"""
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (json.dumps(line) + "\n").encode())
+
+
 def main():
+    # stdout carries exactly one JSON line: native libraries (the NCCL version banner, ...) write to fd 1 directly, so
+    # fd 1 is pointed at stderr for the whole run and the line goes to a saved duplicate of the original stdout
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     args = parse()
     if args.impl == "reference":
         run_reference(args)

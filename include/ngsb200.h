@@ -193,17 +193,41 @@ int ngsb_gmres_solve(const ngsb_csr *A, const ngsb_jacobi *C, const ngsb_vec *f,
                      int *steps, double *history, int hist_cap, int *nhist);
 
 /* ---- distributed: ParallelDofs / ParallelMatrix / Cumulate on one GPU per process -------
- * linalg/paralleldofs.cpp:20-108, parallel/parallelvvector.cpp:247-331,
- * parallel/parallel_matrices.cpp:519-536.  uid is an ncclUniqueId (128 bytes) created by
- * rank 0 with ngsb_comm_unique_id and distributed by the caller (torch.distributed). */
+ * linalg/paralleldofs.cpp:20-108, parallel/parallelvvector.cpp:247-358,
+ * parallel/parallel_matrices.cpp:519-536.
+ *
+ * Data path.  Default ("peer memory"): every rank exports a mailbox and its interface
+ * receive areas with CUDA IPC; the kernels of the solve loop store straight into the
+ * neighbours' memory over NVLink and signal with sequence-numbered flags -- Cumulate and
+ * the scalar all-reduces are part of the solver's own kernels, no library collective and
+ * no host round trip per iteration (csrc/peer.cuh).  If the GPUs cannot map each other
+ * the same calls run over NCCL (ncclSend/Recv + ncclAllReduce).  NGSB_COMM=nccl|p2p in the
+ * environment forces one of them.
+ *
+ * Bootstrap (setup only).  Either an ncclUniqueId (128 bytes, from ngsb_comm_unique_id on
+ * rank 0, distributed by the caller) -- then NCCL also carries the IPC handles -- or a
+ * caller-supplied all-gather (the role MPI_Allgather on the NgMPI_Comm plays in
+ * ParallelDofs, linalg/paralleldofs.cpp:29-44): it must copy `bytes_per_rank` bytes from
+ * every rank's `send` into `recv` in rank order and return 0.  The callback is used only
+ * during the create call it is passed to. */
+typedef int (*ngsb_allgather_fn)(void *user, const void *send, void *recv, size_t bytes_per_rank);
 int ngsb_comm_unique_id(void *uid128);
 int ngsb_comm_create(ngsb_ctx *ctx, int nranks, int rank, const void *uid128, ngsb_comm **out);
+/* p2p_mode: -1 auto, 0 NCCL only, 1 peer memory required.  uid128 may be NULL if allgather is given. */
+int ngsb_comm_create_ex(ngsb_ctx *ctx, int nranks, int rank, const void *uid128, ngsb_allgather_fn allgather,
+                        void *user, int p2p_mode, ngsb_comm **out);
+int ngsb_comm_info(const ngsb_comm *comm, int *nranks, int *rank, int *peer_memory, int *has_nccl);
 int ngsb_comm_destroy(ngsb_comm *comm);
 /* local matrix + exchange tables: exchangedofs as a CSR table over ranks
- * (ex_first[nranks+1], ex_dofs ascending local dofs), exactly ParallelDofs::exchangedofs. */
+ * (ex_first[nranks+1], ex_dofs ascending local dofs), exactly ParallelDofs::exchangedofs.
+ * Collective.  The _ex form takes the bootstrap all-gather of a communicator without NCCL. */
 int ngsb_parmat_create(ngsb_comm *comm, const ngsb_csr *local, const uint64_t *ex_first,
                        const int32_t *ex_dofs, ngsb_parmat **out);
+int ngsb_parmat_create_ex(ngsb_comm *comm, const ngsb_csr *local, const uint64_t *ex_first,
+                          const int32_t *ex_dofs, ngsb_allgather_fn allgather, void *user, ngsb_parmat **out);
 int ngsb_parmat_destroy(ngsb_parmat *P);
+int ngsb_parmat_info(const ngsb_parmat *P, int *peer_memory, int *n_neighbours, size_t *n_exchange,
+                     size_t *n_interface);
 /* masterdofs bytes as the reference derives them (lowest rank owns), n entries */
 int ngsb_parmat_masterdofs(const ngsb_parmat *P, uint8_t *ismaster);
 /* JacobiPrecond of a ParallelMatrix: diagonal summed over the sharing ranks, then inverted
@@ -214,14 +238,20 @@ int ngsb_parmat_cumulate(const ngsb_parmat *P, ngsb_vec *v);
 /* ParallelMatrix::MultAdd (C2D): x cumulated in, y distributed out */
 int ngsb_parmat_mult(const ngsb_parmat *P, const ngsb_vec *x, ngsb_vec *y);
 /* global inner product of a CUMULATED and a DISTRIBUTED vector (local dot + AllReduce),
- * or of two CUMULATED vectors (masked by master dofs), parallelvvector.cpp:289-331 */
+ * or of two CUMULATED vectors (masked by master dofs), parallelvvector.cpp:289-358.
+ * out = (re, im); conjugate (complex only) conjugates the argument y. */
 int ngsb_parmat_dot(const ngsb_parmat *P, const ngsb_vec *x, const ngsb_vec *y, int both_cumulated,
-                    double *out);
+                    int conjugate, double out[2]);
 /* distributed Jacobi-PCG: f DISTRIBUTED in, u CUMULATED out; C holds the cumulated
- * inverse diagonal (linalg/jacobi.cpp:60-61). */
+ * inverse diagonal (linalg/jacobi.cpp:60-61).  ip_mode as in ngsb_cg_solve. */
 int ngsb_parmat_cg_solve(const ngsb_parmat *P, const ngsb_jacobi *C, const ngsb_vec *f, ngsb_vec *u,
-                         double prec, int maxsteps, int *steps, double *history, int hist_cap,
-                         int *nhist);
+                         double prec, int maxsteps, int ip_mode, int *steps, double *history,
+                         int hist_cap, int *nhist);
+/* distributed GMRES (GMRESSolver<IPTYPE>::Mult on parallel vectors): f DISTRIBUTED in,
+ * x CUMULATED out; every Krylov vector is CUMULATED, inner products are master-masked. */
+int ngsb_parmat_gmres_solve(const ngsb_parmat *P, const ngsb_jacobi *C, const ngsb_vec *f, ngsb_vec *x,
+                            double prec, int maxsteps, int *steps, double *history, int hist_cap,
+                            int *nhist);
 
 #ifdef __cplusplus
 }

@@ -77,16 +77,24 @@ PROTOTYPES = {
     "ngsb_gmres_solve": [_vp, _vp, _vp, _vp, _d, _i, _i, C.POINTER(_i), _vp, _i, C.POINTER(_i)],
     "ngsb_comm_unique_id": [_vp],
     "ngsb_comm_create": [_vp, _i, _i, _vp, _pvp],
+    "ngsb_comm_create_ex": [_vp, _i, _i, _vp, _vp, _vp, _i, _pvp],
+    "ngsb_comm_info": [_vp, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)],
     "ngsb_comm_destroy": [_vp],
     "ngsb_parmat_create": [_vp, _vp, _vp, _vp, _pvp],
+    "ngsb_parmat_create_ex": [_vp, _vp, _vp, _vp, _vp, _vp, _pvp],
+    "ngsb_parmat_info": [_vp, C.POINTER(_i), C.POINTER(_i), C.POINTER(_sz), C.POINTER(_sz)],
     "ngsb_parmat_destroy": [_vp],
     "ngsb_parmat_masterdofs": [_vp, _vp],
     "ngsb_parmat_jacobi_create": [_vp, _vp, _pvp],
     "ngsb_parmat_cumulate": [_vp, _vp],
     "ngsb_parmat_mult": [_vp, _vp, _vp],
-    "ngsb_parmat_dot": [_vp, _vp, _vp, _i, C.POINTER(_d)],
-    "ngsb_parmat_cg_solve": [_vp, _vp, _vp, _vp, _d, _i, C.POINTER(_i), _vp, _i, C.POINTER(_i)],
+    "ngsb_parmat_dot": [_vp, _vp, _vp, _i, _i, C.POINTER(_d)],
+    "ngsb_parmat_cg_solve": [_vp, _vp, _vp, _vp, _d, _i, _i, C.POINTER(_i), _vp, _i, C.POINTER(_i)],
+    "ngsb_parmat_gmres_solve": [_vp, _vp, _vp, _vp, _d, _i, C.POINTER(_i), _vp, _i, C.POINTER(_i)],
 }
+# bootstrap all-gather callback (ngsb_allgather_fn)
+ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t)
+
 _SPECIAL = {
     "ngsb_last_error": ([], C.c_char_p),
     "ngsb_version": ([], C.c_char_p),

@@ -126,5 +126,8 @@ int launch_scale_dev(ngsb_ctx *ctx, double *x, size_t N, const double *ds, bool 
 // deterministic dot: out (device, 2 doubles) = sum x_i * (conj? conj(y_i) : y_i)
 // mode: 0 real, 1 complex bilinear, 2 complex conj(y), 3 real sum of squares of x (norm^2)
 int launch_dot(ngsb_ctx *ctx, const double *x, const double *y, size_t N, int mode, double *d_out);
+// the same over the entries whose mask byte (index i / mask_div) is set; mask == NULL: all
+int launch_dot_masked(ngsb_ctx *ctx, const double *x, const double *y, size_t N, int mode, double *d_out, const uint8_t *mask,
+                      unsigned mask_div);
 
 } // namespace ngsb

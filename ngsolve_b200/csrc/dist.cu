@@ -19,6 +19,7 @@
 // WaitAny order).  NCCL is bound at run time (dlopen) so that the single-GPU path of the
 // library has no NCCL dependency.
 #include "krylov.cuh"
+#include "peer.cuh"
 
 #include <dlfcn.h>
 #include <nccl.h>
@@ -28,8 +29,16 @@
 struct ngsb_comm {
     ngsb_ctx *ctx = nullptr;
     int nranks = 1, rank = 0;
-    ncclComm_t comm = nullptr;
-    double *d_red = nullptr;      // 2 doubles: all-reduce slot
+    ncclComm_t comm = nullptr;    // NULL: no NCCL (bootstrap by callback, peer-memory data path only)
+    int (*boot_allgather)(void *, const void *, void *, size_t) = nullptr;
+    void *boot_user = nullptr;
+    double *d_red = nullptr;      // 2 doubles: local dot / all-reduce slot
+    // peer-memory mode (peer.cuh)
+    bool p2p = false;
+    char *mailbox = nullptr;                      // local, exported with CUDA IPC
+    char *peer_mailbox[NGSB_MAX_RANKS] = {};      // mapped mailboxes of the other ranks
+    PeerReduce *d_R = nullptr;                    // device copy of the reduce descriptor
+    int *d_err = nullptr;                         // inside the mailbox
 };
 
 struct ngsb_parmat {
@@ -37,11 +46,12 @@ struct ngsb_parmat {
     const ngsb_csr *local = nullptr;
     size_t n = 0;                 // local dofs
     int es = 1;                   // scalars per entry
+    int esmax = 1;                // scalars per matrix value: what the Jacobi constructor cumulates
     std::vector<int> peers;       // neighbour ranks (ascending)
     std::vector<size_t> peer_off; // offset (in dofs) of each neighbour's slice in the packed lists
     size_t nex = 0;               // total exchange entries (sum over neighbours)
     int32_t *d_exdofs = nullptr;  // nex local dof indices, neighbour-major
-    double *d_send = nullptr, *d_recv = nullptr;   // nex * es doubles each
+    double *d_send = nullptr, *d_recv = nullptr;   // nex * es doubles each (NCCL mode)
     // dof-major view for the deterministic add: interface dof k (nif of them) has the
     // received copies d_recv[if_pos[if_first[k] .. if_first[k+1])] in ascending rank order
     size_t nif = 0;
@@ -50,9 +60,30 @@ struct ngsb_parmat {
     uint32_t *d_if_pos = nullptr;
     uint8_t *d_master = nullptr;  // n bytes
     std::vector<uint8_t> h_master;
+    // peer-memory mode
+    bool p2p = false;
+    char *halo_mem = nullptr;                     // local, exported: flags | receive area (2 parities)
+    char *peer_halo[NGSB_MAX_RANKS] = {};         // mapped, per neighbour index
+    char *d_local = nullptr;                      // local only: sequence number + CTA counters
+    PeerHalo *d_H = nullptr;
+    // cached CUDA graph of one batch of CG iterations (peer-memory mode)
+    cudaGraphExec_t graph_exec = nullptr;
+    const void *g_key[8] = {};
+    long g_batch = 0;
 };
 
 namespace ngsb {
+
+// mailbox layout (bytes)
+static const size_t MB_SLOTS = 0;                 // PeerSlot[2][NGSB_MAX_RANKS]
+static const size_t MB_SEQ = 4096;                // unsigned long long
+static const size_t MB_ERR = 4096 + 64;           // int
+static const size_t MB_MAGIC = 8192;              // unsigned long long, checked through the mapping
+static const size_t MB_BYTES = 2u << 20;          // own 2 MiB block: the IPC handle maps exactly this allocation
+// halo block layout
+static const size_t HB_FLAGS = 0;                 // unsigned long long[2][NGSB_MAX_RANKS]
+static const size_t HB_MAGIC = 1024;
+static const size_t HB_DATA = 4096;
 
 // ---- NCCL binding -------------------------------------------------------------------------
 struct NcclApi {
@@ -61,6 +92,7 @@ struct NcclApi {
     ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
@@ -87,6 +119,7 @@ static int nccl_load()
     NGSB_SYM(CommInitRank, "ncclCommInitRank")
     NGSB_SYM(CommDestroy, "ncclCommDestroy")
     NGSB_SYM(AllReduce, "ncclAllReduce")
+    NGSB_SYM(AllGather, "ncclAllGather")
     NGSB_SYM(Send, "ncclSend")
     NGSB_SYM(Recv, "ncclRecv")
     NGSB_SYM(GroupStart, "ncclGroupStart")
@@ -106,41 +139,86 @@ static int nccl_load()
         }                                                                                        \
     } while (0)
 
-// ---- kernels --------------------------------------------------------------------------------
-template <int ES>
-__global__ void __launch_bounds__(256) pack_kernel(const double *__restrict__ v, const int32_t *__restrict__ exdofs,
-                                                  double *__restrict__ send, size_t nex)
+// out-of-band all-gather of `bytes` per rank (setup only): the caller's callback, else NCCL
+static int boot_allgather(ngsb_comm *c, const void *send, void *recv, size_t bytes)
 {
-    size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= nex) return;
-    const size_t dof = (size_t)exdofs[k];
-#pragma unroll
-    for (int c = 0; c < ES; c++) send[ES * k + c] = v[ES * dof + c];
-}
-
-// AddRecvValues for all neighbours at once, one thread per interface dof
-template <int ES>
-__global__ void __launch_bounds__(256) unpack_add_kernel(double *__restrict__ v, const int32_t *__restrict__ if_dof,
-                                                        const uint32_t *__restrict__ if_first, const uint32_t *__restrict__ if_pos,
-                                                        const double *__restrict__ recv, size_t nif)
-{
-    size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= nif) return;
-    const size_t dof = (size_t)if_dof[k];
-    double acc[ES];
-#pragma unroll
-    for (int c = 0; c < ES; c++) acc[c] = v[ES * dof + c];
-    for (uint32_t q = if_first[k]; q < if_first[k + 1]; q++) {
-        const size_t p = if_pos[q];
-#pragma unroll
-        for (int c = 0; c < ES; c++) acc[c] += recv[ES * p + c];
+    if (c->nranks == 1) { memcpy(recv, send, bytes); return NGSB_OK; }
+    if (c->boot_allgather) {
+        int rc = c->boot_allgather(c->boot_user, send, recv, bytes);
+        if (rc != 0) { set_error("bootstrap all-gather callback failed (%d)", rc); return NGSB_ERR_COMM; }
+        return NGSB_OK;
     }
-#pragma unroll
-    for (int c = 0; c < ES; c++) v[ES * dof + c] = acc[c];
+    NGSB_REQUIRE(c->comm, "communicator has neither NCCL nor a bootstrap all-gather");
+    ngsb_ctx *ctx = c->ctx;
+    char *d_s = nullptr, *d_r = nullptr;
+    NGSB_CUDA(cudaMalloc(&d_s, bytes));
+    NGSB_CUDA(cudaMalloc(&d_r, bytes * c->nranks));
+    NGSB_CUDA(cudaMemcpyAsync(d_s, send, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    ncclResult_t r = g_nccl.AllGather(d_s, d_r, bytes, ncclChar, c->comm, ctx->stream);
+    cudaError_t e = cudaMemcpyAsync(recv, d_r, bytes * c->nranks, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_s);
+    cudaFree(d_r);
+    if (r != ncclSuccess) { set_error("ncclAllGather (bootstrap) failed: %s", g_nccl.GetErrorString(r)); return NGSB_ERR_COMM; }
+    if (e != cudaSuccess) { set_error("bootstrap all-gather: %s", cudaGetErrorString(e)); return NGSB_ERR_CUDA; }
+    return NGSB_OK;
 }
 
-// run-time entry size versions (setup only: the 9-double diagonal blocks of the Jacobi ctor)
-__global__ void pack_rt_kernel(const double *__restrict__ v, const int32_t *__restrict__ exdofs, double *__restrict__ send, size_t nex, int es)
+// all ranks agree: true only if `mine` is true everywhere
+static int boot_all_ok(ngsb_comm *c, bool mine, bool *all)
+{
+    std::vector<unsigned char> buf(c->nranks);
+    unsigned char m = mine ? 1 : 0;
+    NGSB_TRY(boot_allgather(c, &m, buf.data(), 1));
+    *all = true;
+    for (int p = 0; p < c->nranks; p++) *all = *all && buf[p] != 0;
+    return NGSB_OK;
+}
+
+// export `mem` (its own cudaMalloc block, magic already written at `magic_off`), gather every rank's handle,
+// map the blocks of the ranks in `want` (NULL: all) and check the magic through the mapping.
+// ok = false (no error) when this rank could not export / map; collective.
+static int ipc_exchange(ngsb_comm *c, char *mem, size_t magic_off, const std::vector<int> *want, char **mapped, bool *ok)
+{
+    cudaIpcMemHandle_t mine;
+    memset(&mine, 0, sizeof(mine));
+    bool good = mem != nullptr && cudaIpcGetMemHandle(&mine, mem) == cudaSuccess;
+    if (!good) cudaGetLastError();
+    std::vector<cudaIpcMemHandle_t> all(c->nranks);
+    NGSB_TRY(boot_allgather(c, &mine, all.data(), sizeof(mine)));
+    bool everyone = false;
+    NGSB_TRY(boot_all_ok(c, good, &everyone));
+    if (everyone) {
+        for (int p = 0; p < c->nranks && good; p++) {
+            if (p == c->rank) { mapped[p] = mem; continue; }
+            if (want && std::find(want->begin(), want->end(), p) == want->end()) continue;
+            void *ptr = nullptr;
+            if (cudaIpcOpenMemHandle(&ptr, all[p], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); good = false; break; }
+            mapped[p] = (char *)ptr;
+            unsigned long long magic = 0;
+            if (cudaMemcpy(&magic, mapped[p] + magic_off, sizeof(magic), cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); good = false; break; }
+            if (magic != (0x4e47534232303000ull | (unsigned long long)p)) good = false;
+        }
+        NGSB_TRY(boot_all_ok(c, good, &everyone));
+    }
+    if (!everyone)
+        for (int p = 0; p < c->nranks; p++)
+            if (p != c->rank && mapped[p]) { cudaIpcCloseMemHandle(mapped[p]); mapped[p] = nullptr; }
+    *ok = everyone;
+    return NGSB_OK;
+}
+
+static int write_magic(ngsb_ctx *ctx, char *mem, size_t off, int rank)
+{
+    unsigned long long magic = 0x4e47534232303000ull | (unsigned long long)rank;
+    NGSB_CUDA(cudaMemcpy(mem + off, &magic, sizeof(magic), cudaMemcpyHostToDevice));
+    return NGSB_OK;
+}
+
+// ---- kernels --------------------------------------------------------------------------------
+// NCCL mode: gather the interface values into one send buffer ...
+__global__ void __launch_bounds__(256) pack_kernel(const double *__restrict__ v, const int32_t *__restrict__ exdofs, double *__restrict__ send,
+                                                  size_t nex, int es)
 {
     size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= nex) return;
@@ -148,8 +226,10 @@ __global__ void pack_rt_kernel(const double *__restrict__ v, const int32_t *__re
     for (int c = 0; c < es; c++) send[es * k + c] = v[es * dof + c];
 }
 
-__global__ void unpack_add_rt_kernel(double *__restrict__ v, const int32_t *__restrict__ if_dof, const uint32_t *__restrict__ if_first,
-                                     const uint32_t *__restrict__ if_pos, const double *__restrict__ recv, size_t nif, int es)
+// ... and AddRecvValues for all neighbours at once, one thread per interface dof, copies added in ascending rank order
+__global__ void __launch_bounds__(256) unpack_add_kernel(double *__restrict__ v, const int32_t *__restrict__ if_dof,
+                                                        const uint32_t *__restrict__ if_first, const uint32_t *__restrict__ if_pos,
+                                                        const double *__restrict__ recv, size_t nif, int es)
 {
     size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= nif) return;
@@ -161,78 +241,128 @@ __global__ void unpack_add_rt_kernel(double *__restrict__ v, const int32_t *__re
     }
 }
 
+// Peer-memory mode, first half of Cumulate: store my interface values into the neighbours' receive areas (P2P stores
+// over NVLink), then the last CTA publishes the sequence number to every neighbour.  Thread (0,0) also publishes this
+// rank's partial of the pending scalar reduction (`red`), so that it travels while the exchange is in flight.
+__global__ void __launch_bounds__(256) halo_push_kernel(const PeerHalo *__restrict__ H, const double *__restrict__ v,
+                                                       const int32_t *__restrict__ exdofs, size_t nex, int es, const CgState *st,
+                                                       const PeerReduce *R, const double *red)
+{
+    if (st && st->done) return;
+    const unsigned long long s = *(volatile unsigned long long *)H->seq + 1;
+    const unsigned long long par = s & 1;
+    if (R && blockIdx.x == 0 && threadIdx.x == 0) pr_push(*R, red[0], red[1]);
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < nex; k += stride) {
+        int q = 0;
+        while (k >= H->peer_off[q + 1]) q++;
+        const size_t dof = (size_t)exdofs[k];
+        double *dst = H->peer_recv[q] + par * H->peer_stride[q] + (H->peer_my_off[q] + (k - H->peer_off[q])) * (size_t)es;
+        for (int c = 0; c < es; c++) dst[c] = v[es * dof + c];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(&H->counter[0], 1u);
+        if (t == gridDim.x - 1) {
+            H->counter[0] = 0;
+            __threadfence_system();
+            for (int q = 0; q < H->npeers; q++) st_release_sys(H->peer_flags[q] + par * NGSB_MAX_RANKS + H->rank, s);
+        }
+    }
+}
+
+// second half: wait for the neighbours' flags, add the received copies (ascending rank order per dof).  The last CTA
+// completes the exchange and, inside the CG loop (fin = 1), finishes kss = <s, A s>: all-reduce + al = wd / kss.
+__global__ void __launch_bounds__(256) halo_unpack_kernel(const PeerHalo *__restrict__ H, double *__restrict__ v,
+                                                         const int32_t *__restrict__ if_dof, const uint32_t *__restrict__ if_first,
+                                                         const uint32_t *__restrict__ if_pos, size_t nif, int es, CgState *st,
+                                                         const PeerReduce *R, int fin)
+{
+    if (st && st->done) return;
+    const unsigned long long s = *(volatile unsigned long long *)H->seq + 1;
+    const unsigned long long par = s & 1;
+    if ((int)threadIdx.x < H->npeers) peer_wait(H->flags + par * NGSB_MAX_RANKS + H->peer_rank[threadIdx.x], s, H->err);
+    __syncthreads();
+    const double *recv = H->recv + par * H->stride;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < nif; k += stride) {
+        const size_t dof = (size_t)if_dof[k];
+        for (int c = 0; c < es; c++) {
+            double acc = v[es * dof + c];
+            for (uint32_t q = if_first[k]; q < if_first[k + 1]; q++) acc += __ldcg(recv + (size_t)es * if_pos[q] + c);
+            v[es * dof + c] = acc;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned int t = atomicAdd(&H->counter[1], 1u);
+        if (t == gridDim.x - 1) {
+            H->counter[1] = 0;
+            *(volatile unsigned long long *)H->seq = s;
+            if (fin == 1 && R && st) {
+                double2 tot = pr_wait_sum(*R);
+                cg_finalize_kss(st, tot);
+            }
+        }
+    }
+}
+
+// buf(re,im) <- sum over ranks, one thread (API-level inner products)
+__global__ void peer_allreduce_kernel(const PeerReduce *R, double *buf) { pr_allreduce_inplace(*R, buf); }
+
 static int all_reduce2(ngsb_comm *comm, double *d_buf)
 {
     if (comm->nranks == 1) return NGSB_OK;
     comm->ctx->launches++;
+    if (comm->p2p) {
+        peer_allreduce_kernel<<<1, 1, 0, comm->ctx->stream>>>(comm->d_R, d_buf);
+        NGSB_CUDA(cudaGetLastError());
+        return NGSB_OK;
+    }
     NGSB_NCCL(g_nccl.AllReduce(d_buf, d_buf, 2, ncclDouble, ncclSum, comm->comm, comm->ctx->stream));
     return NGSB_OK;
 }
 
-static int cumulate_raw(const ngsb_parmat *P, double *v)
+static unsigned halo_grid(const ngsb_ctx *ctx, size_t n)
+{
+    size_t b = (n + 255) / 256, cap = (size_t)ctx->sm_count * 2;
+    return (unsigned)std::max<size_t>(1, std::min(b, cap));
+}
+
+// Cumulate of a raw local array with `es` doubles per dof (es <= P->esmax).  Inside the CG loop `st`, `R`, `red`, `fin`
+// fuse the kss reduction into the two kernels (peer-memory mode only).
+static int cumulate_es(const ngsb_parmat *P, double *v, int es, CgState *st = nullptr, const double *red = nullptr, int fin = 0)
 {
     ngsb_comm *comm = P->comm;
     ngsb_ctx *ctx = comm->ctx;
-    if (P->nex == 0 || comm->nranks == 1) return NGSB_OK;
-    const int es = P->es;
-    {
+    if (comm->nranks == 1) return NGSB_OK;
+    if (P->p2p) {
+        // no early-out on nex == 0: a rank without neighbours still takes part in the fused reduction
         SpanGuard g(ctx, KC_OTHER);
-        unsigned grid = (unsigned)((P->nex + 255) / 256);
-        if (es == 1) pack_kernel<1><<<grid, 256, 0, ctx->stream>>>(v, P->d_exdofs, P->d_send, P->nex);
-        else if (es == 2) pack_kernel<2><<<grid, 256, 0, ctx->stream>>>(v, P->d_exdofs, P->d_send, P->nex);
-        else pack_kernel<3><<<grid, 256, 0, ctx->stream>>>(v, P->d_exdofs, P->d_send, P->nex);
+        const PeerReduce *R = fin ? comm->d_R : nullptr;
+        halo_push_kernel<<<halo_grid(ctx, P->nex), 256, 0, ctx->stream>>>(P->d_H, v, P->d_exdofs, P->nex, es, st, R, red);
+        halo_unpack_kernel<<<halo_grid(ctx, P->nif), 256, 0, ctx->stream>>>(P->d_H, v, P->d_if_dof, P->d_if_first, P->d_if_pos, P->nif, es, st, R, fin);
+        ctx->launches += 2;
         NGSB_CUDA(cudaGetLastError());
+        return NGSB_OK;
     }
-    ctx->launches++;
-    NGSB_NCCL(g_nccl.GroupStart());
-    for (size_t q = 0; q < P->peers.size(); q++) {
-        const size_t off = P->peer_off[q] * es, cnt = (P->peer_off[q + 1] - P->peer_off[q]) * es;
-        NGSB_NCCL(g_nccl.Send(P->d_send + off, cnt, ncclDouble, P->peers[q], comm->comm, ctx->stream));
-        NGSB_NCCL(g_nccl.Recv(P->d_recv + off, cnt, ncclDouble, P->peers[q], comm->comm, ctx->stream));
+    if (P->nex == 0) return NGSB_OK;
+    double *send = P->d_send, *recv = P->d_recv;
+    const bool own = es > P->es;         // setup path (diagonal blocks): temporary buffers
+    if (own) {
+        NGSB_CUDA(cudaMalloc(&send, P->nex * es * sizeof(double)));
+        NGSB_CUDA(cudaMalloc(&recv, P->nex * es * sizeof(double)));
     }
-    NGSB_NCCL(g_nccl.GroupEnd());
-    {
-        SpanGuard g(ctx, KC_OTHER);
-        unsigned grid = (unsigned)((P->nif + 255) / 256);
-        if (es == 1) unpack_add_kernel<1><<<grid, 256, 0, ctx->stream>>>(v, P->d_if_dof, P->d_if_first, P->d_if_pos, P->d_recv, P->nif);
-        else if (es == 2) unpack_add_kernel<2><<<grid, 256, 0, ctx->stream>>>(v, P->d_if_dof, P->d_if_first, P->d_if_pos, P->d_recv, P->nif);
-        else unpack_add_kernel<3><<<grid, 256, 0, ctx->stream>>>(v, P->d_if_dof, P->d_if_first, P->d_if_pos, P->d_recv, P->nif);
-        NGSB_CUDA(cudaGetLastError());
-    }
-    return NGSB_OK;
-}
-
-__global__ void mask_zero_kernel(double *v, const uint8_t *master, size_t n, int es)
-{
-    size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-        if (!master[i])
-            for (int c = 0; c < es; c++) v[es * i + c] = 0.0;
-}
-int launch_mask_zero(ngsb_ctx *ctx, double *v, const uint8_t *master, size_t n, int es)
-{
-    if (n == 0) return NGSB_OK;
-    SpanGuard g(ctx, KC_VEC);
-    size_t blocks = std::min<size_t>((n + 255) / 256, (size_t)ctx->sm_count * 8);
-    mask_zero_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(v, master, n, es);
-    NGSB_CUDA(cudaGetLastError());
-    return NGSB_OK;
-}
-
-// Cumulate of an array with `es` doubles per dof through temporary buffers (setup path)
-static int cumulate_any(void *arg, double *v, int es)
-{
-    const ngsb_parmat *P = (const ngsb_parmat *)arg;
-    ngsb_comm *comm = P->comm;
-    ngsb_ctx *ctx = comm->ctx;
-    if (P->nex == 0 || comm->nranks == 1) return NGSB_OK;
-    double *send = nullptr, *recv = nullptr;
-    NGSB_CUDA(cudaMalloc(&send, P->nex * es * sizeof(double)));
-    NGSB_CUDA(cudaMalloc(&recv, P->nex * es * sizeof(double)));
-    pack_rt_kernel<<<(unsigned)((P->nex + 255) / 256), 256, 0, ctx->stream>>>(v, P->d_exdofs, send, P->nex, es);
-    ctx->launches += 3;
     int rc = NGSB_OK;
-    do {
+    {
+        SpanGuard g(ctx, KC_OTHER);
+        pack_kernel<<<(unsigned)((P->nex + 255) / 256), 256, 0, ctx->stream>>>(v, P->d_exdofs, send, P->nex, es);
+        if (cudaGetLastError() != cudaSuccess) rc = NGSB_ERR_CUDA;
+    }
+    ctx->launches += 3;
+    if (rc == NGSB_OK) {
         ncclResult_t r = g_nccl.GroupStart();
         for (size_t q = 0; q < P->peers.size() && r == ncclSuccess; q++) {
             const size_t off = P->peer_off[q] * es, cnt = (P->peer_off[q + 1] - P->peer_off[q]) * es;
@@ -241,16 +371,50 @@ static int cumulate_any(void *arg, double *v, int es)
         }
         ncclResult_t r2 = g_nccl.GroupEnd();
         if (r == ncclSuccess) r = r2;
-        if (r != ncclSuccess) { set_error("Cumulate(diagonal): %s", g_nccl.GetErrorString(r)); rc = NGSB_ERR_COMM; }
-    } while (0);
+        if (r != ncclSuccess) { set_error("Cumulate: %s", g_nccl.GetErrorString(r)); rc = NGSB_ERR_COMM; }
+    }
     if (rc == NGSB_OK) {
-        unpack_add_rt_kernel<<<(unsigned)((P->nif + 255) / 256), 256, 0, ctx->stream>>>(v, P->d_if_dof, P->d_if_first, P->d_if_pos, recv, P->nif, es);
+        SpanGuard g(ctx, KC_OTHER);
+        unpack_add_kernel<<<(unsigned)((P->nif + 255) / 256), 256, 0, ctx->stream>>>(v, P->d_if_dof, P->d_if_first, P->d_if_pos, recv, P->nif, es);
         if (cudaGetLastError() != cudaSuccess) rc = NGSB_ERR_CUDA;
     }
-    cudaStreamSynchronize(ctx->stream);
-    cudaFree(send);
-    cudaFree(recv);
+    if (own) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaFree(send);
+        cudaFree(recv);
+    }
     return rc;
+}
+
+static int cumulate_raw(const ngsb_parmat *P, double *v) { return cumulate_es(P, v, P->es); }
+
+__global__ void mask_zero_kernel(double *v, const uint8_t *master, size_t n, int es)
+{
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        if (!master[i])
+            for (int c = 0; c < es; c++) v[es * i + c] = 0.0;
+}
+
+// Cumulate of the diagonal (setup path of the Jacobi constructor), `es` = doubles per matrix value
+static int cumulate_any(void *arg, double *v, int es)
+{
+    const ngsb_parmat *P = (const ngsb_parmat *)arg;
+    NGSB_REQUIRE(es <= P->esmax, "Cumulate(diagonal): %d doubles per entry exceed the exchange buffers (%d)", es, P->esmax);
+    int rc = cumulate_es(P, v, es);
+    if (rc == NGSB_OK && cudaStreamSynchronize(P->comm->ctx->stream) != cudaSuccess) rc = NGSB_ERR_CUDA;
+    return rc;
+}
+
+// a wait in a peer-memory kernel timed out (a rank died or the ranks disagree on the sequence of collectives)
+static int check_peer_error(ngsb_comm *comm, const char *who)
+{
+    if (!comm->p2p) return NGSB_OK;
+    int err = 0;
+    NGSB_CUDA(cudaMemcpyAsync(&err, comm->d_err, sizeof(int), cudaMemcpyDeviceToHost, comm->ctx->stream));
+    NGSB_CUDA(cudaStreamSynchronize(comm->ctx->stream));
+    if (err) { set_error("%s: a peer-memory wait timed out (rank %d of %d)", who, comm->rank, comm->nranks); return NGSB_ERR_COMM; }
+    return NGSB_OK;
 }
 
 } // namespace ngsb
@@ -276,24 +440,97 @@ extern "C" int ngsb_comm_unique_id(void *uid128)
     return NGSB_OK;
 }
 
-extern "C" int ngsb_comm_create(ngsb_ctx *ctx, int nranks, int rank, const void *uid128, ngsb_comm **out)
+// set up the mailbox and map everybody else's; collective.  On return c->p2p tells whether ALL ranks succeeded.
+static int comm_setup_p2p(ngsb_comm *c)
+{
+    ngsb_ctx *ctx = c->ctx;
+    bool good = c->nranks <= NGSB_MAX_RANKS;
+    if (good && cudaMalloc(&c->mailbox, MB_BYTES) != cudaSuccess) { cudaGetLastError(); c->mailbox = nullptr; good = false; }
+    if (good) {
+        NGSB_CUDA(cudaMemset(c->mailbox, 0, MB_BYTES));
+        NGSB_TRY(write_magic(ctx, c->mailbox, MB_MAGIC, c->rank));
+    }
+    bool ok = false;
+    NGSB_TRY(ipc_exchange(c, good ? c->mailbox : nullptr, MB_MAGIC, nullptr, c->peer_mailbox, &ok));
+    if (!ok) {
+        if (c->mailbox) { cudaFree(c->mailbox); c->mailbox = nullptr; }
+        c->p2p = false;
+        return NGSB_OK;
+    }
+    PeerReduce R;
+    memset(&R, 0, sizeof(R));
+    R.nranks = c->nranks;
+    R.rank = c->rank;
+    R.seq = (unsigned long long *)(c->mailbox + MB_SEQ);
+    R.err = (int *)(c->mailbox + MB_ERR);
+    R.mine = (PeerSlot *)(c->mailbox + MB_SLOTS);
+    for (int p = 0; p < c->nranks; p++) R.theirs[p] = (PeerSlot *)(c->peer_mailbox[p] + MB_SLOTS);
+    c->d_err = R.err;
+    NGSB_CUDA(cudaMalloc(&c->d_R, sizeof(PeerReduce)));
+    NGSB_CUDA(cudaMemcpy(c->d_R, &R, sizeof(R), cudaMemcpyHostToDevice));
+    c->p2p = true;
+    return NGSB_OK;
+}
+
+// p2p_mode: -1 auto (peer memory if every rank can map every other rank, else NCCL), 0 NCCL only, 1 peer memory required.
+// uid128 may be NULL when a bootstrap all-gather callback is given: then there is no NCCL communicator at all.
+extern "C" int ngsb_comm_create_ex(ngsb_ctx *ctx, int nranks, int rank, const void *uid128,
+                                   int (*allgather)(void *user, const void *send, void *recv, size_t bytes_per_rank), void *user,
+                                   int p2p_mode, ngsb_comm **out)
 {
     NGSB_REQUIRE(ctx && out, "ngsb_comm_create: NULL argument");
     NGSB_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, "ngsb_comm_create: bad rank %d of %d", rank, nranks);
+    NGSB_REQUIRE(nranks == 1 || uid128 || allgather, "ngsb_comm_create: neither an ncclUniqueId nor a bootstrap all-gather given");
+    NGSB_REQUIRE(p2p_mode >= -1 && p2p_mode <= 1, "ngsb_comm_create: p2p_mode must be -1, 0 or 1");
+    NGSB_REQUIRE(p2p_mode != 0 || uid128 || nranks == 1, "ngsb_comm_create: NCCL-only mode needs an ncclUniqueId");
     NGSB_CUDA(cudaSetDevice(ctx->device));
+    const char *env = getenv("NGSB_COMM");
+    if (env && !strcmp(env, "nccl") && uid128) p2p_mode = 0;
+    if (env && !strcmp(env, "p2p")) p2p_mode = 1;
     ngsb_comm *c = new ngsb_comm();
     c->ctx = ctx;
     c->nranks = nranks;
     c->rank = rank;
-    if (nranks > 1) {
-        NGSB_REQUIRE(uid128, "ngsb_comm_create: uid is NULL");
-        NGSB_TRY(nccl_load());
-        ncclUniqueId id;
-        memcpy(&id, uid128, sizeof(id));
-        NGSB_NCCL(g_nccl.CommInitRank(&c->comm, nranks, id, rank));
+    c->boot_allgather = allgather;
+    c->boot_user = user;
+    int rc = NGSB_OK;
+    if (nranks > 1 && uid128) {
+        rc = nccl_load();
+        if (rc == NGSB_OK) {
+            ncclUniqueId id;
+            memcpy(&id, uid128, sizeof(id));
+            ncclResult_t r = g_nccl.CommInitRank(&c->comm, nranks, id, rank);
+            if (r != ncclSuccess) { set_error("ncclCommInitRank failed: %s", g_nccl.GetErrorString(r)); rc = NGSB_ERR_COMM; }
+        }
     }
-    NGSB_CUDA(cudaMalloc(&c->d_red, 4 * sizeof(double)));
+    if (rc == NGSB_OK && cudaMalloc(&c->d_red, 4 * sizeof(double)) != cudaSuccess) { set_error("ngsb_comm_create: out of memory"); rc = NGSB_ERR_NOMEM; }
+    if (rc == NGSB_OK && nranks > 1 && p2p_mode != 0) {
+        rc = comm_setup_p2p(c);
+        if (rc == NGSB_OK && !c->p2p && (p2p_mode == 1 || !c->comm)) {
+            set_error("ngsb_comm_create: peer memory (CUDA IPC between the ranks' GPUs) is not available%s", c->comm ? "" : " and there is no NCCL communicator");
+            rc = NGSB_ERR_COMM;
+        }
+    }
+    c->boot_allgather = nullptr;    // the callback is only valid during this call and ngsb_parmat_create_ex
+    c->boot_user = nullptr;
+    if (rc != NGSB_OK) { ngsb_comm_destroy(c); return rc; }
     *out = c;
+    return NGSB_OK;
+}
+
+extern "C" int ngsb_comm_create(ngsb_ctx *ctx, int nranks, int rank, const void *uid128, ngsb_comm **out)
+{
+    NGSB_REQUIRE(nranks == 1 || uid128, "ngsb_comm_create: uid is NULL");
+    return ngsb_comm_create_ex(ctx, nranks, rank, uid128, nullptr, nullptr, -1, out);
+}
+
+extern "C" int ngsb_comm_info(const ngsb_comm *c, int *nranks, int *rank, int *peer_memory, int *has_nccl)
+{
+    NGSB_REQUIRE(c, "ngsb_comm_info: comm is NULL");
+    if (nranks) *nranks = c->nranks;
+    if (rank) *rank = c->rank;
+    if (peer_memory) *peer_memory = c->p2p ? 1 : 0;
+    if (has_nccl) *has_nccl = c->comm ? 1 : 0;
     return NGSB_OK;
 }
 
@@ -302,18 +539,87 @@ extern "C" int ngsb_comm_destroy(ngsb_comm *c)
     if (!c) return NGSB_OK;
     cudaSetDevice(c->ctx->device);
     cudaStreamSynchronize(c->ctx->stream);
+    for (int p = 0; p < c->nranks && p < NGSB_MAX_RANKS; p++)
+        if (p != c->rank && c->peer_mailbox[p]) cudaIpcCloseMemHandle(c->peer_mailbox[p]);
     if (c->comm) g_nccl.CommDestroy(c->comm);
+    cudaFree(c->d_R);
+    cudaFree(c->mailbox);
     cudaFree(c->d_red);
     delete c;
     return NGSB_OK;
 }
 
-extern "C" int ngsb_parmat_create(ngsb_comm *comm, const ngsb_csr *local, const uint64_t *ex_first, const int32_t *ex_dofs,
-                                  ngsb_parmat **out)
+// receive areas + flags of the peer-memory Cumulate; collective.  P->p2p = all ranks succeeded.
+static int parmat_setup_p2p(ngsb_parmat *P, const uint64_t *ex_first)
+{
+    ngsb_comm *c = P->comm;
+    ngsb_ctx *ctx = c->ctx;
+    const int np = c->nranks;
+    const size_t stride = std::max<size_t>(2, P->nex * (size_t)P->esmax);           // doubles per parity
+    size_t bytes = HB_DATA + 2 * stride * sizeof(double);
+    bytes = (bytes + (2u << 20) - 1) & ~(size_t)((2u << 20) - 1);
+    bool good = (int)P->peers.size() < NGSB_MAX_RANKS;
+    if (good && cudaMalloc(&P->halo_mem, bytes) != cudaSuccess) { cudaGetLastError(); P->halo_mem = nullptr; good = false; }
+    if (good) {
+        NGSB_CUDA(cudaMemset(P->halo_mem, 0, HB_DATA));
+        NGSB_TRY(write_magic(ctx, P->halo_mem, HB_MAGIC, c->rank));
+    }
+    // everybody's exchange table offsets and strides: where my slice starts in each neighbour's packed list
+    std::vector<uint64_t> mine(np + 2), all((size_t)np * (np + 2));
+    for (int p = 0; p <= np; p++) mine[p] = ex_first[p];
+    mine[np + 1] = stride;
+    NGSB_TRY(boot_allgather(c, mine.data(), all.data(), mine.size() * sizeof(uint64_t)));
+    bool ok = false;
+    char *mapped[NGSB_MAX_RANKS] = {};
+    NGSB_TRY(ipc_exchange(c, good ? P->halo_mem : nullptr, HB_MAGIC, &P->peers, mapped, &ok));
+    if (!ok) {
+        if (P->halo_mem) { cudaFree(P->halo_mem); P->halo_mem = nullptr; }
+        P->p2p = false;
+        return NGSB_OK;
+    }
+    NGSB_CUDA(cudaMalloc(&P->d_local, 256));
+    NGSB_CUDA(cudaMemset(P->d_local, 0, 256));
+    PeerHalo H;
+    memset(&H, 0, sizeof(H));
+    H.npeers = (int)P->peers.size();
+    H.rank = c->rank;
+    H.seq = (unsigned long long *)P->d_local;
+    H.counter = (unsigned int *)(P->d_local + 64);
+    H.err = c->d_err;
+    H.recv = (double *)(P->halo_mem + HB_DATA);
+    H.stride = stride;
+    H.flags = (unsigned long long *)(P->halo_mem + HB_FLAGS);
+    for (size_t q = 0; q < P->peers.size(); q++) {
+        const int p = P->peers[q];
+        const uint64_t *theirs = &all[(size_t)p * (np + 2)];
+        P->peer_halo[q] = mapped[p];
+        H.peer_rank[q] = p;
+        H.peer_off[q] = (unsigned int)P->peer_off[q];
+        H.peer_recv[q] = (double *)(mapped[p] + HB_DATA);
+        H.peer_stride[q] = theirs[np + 1];
+        H.peer_my_off[q] = theirs[c->rank];
+        H.peer_flags[q] = (unsigned long long *)(mapped[p] + HB_FLAGS);
+        // both sides must list the same number of shared dofs
+        NGSB_REQUIRE(theirs[c->rank + 1] - theirs[c->rank] == P->peer_off[q + 1] - P->peer_off[q],
+                     "ngsb_parmat_create: rank %d shares %llu dofs with rank %d, which lists %llu", c->rank,
+                     (unsigned long long)(P->peer_off[q + 1] - P->peer_off[q]), p, (unsigned long long)(theirs[c->rank + 1] - theirs[c->rank]));
+    }
+    for (size_t q = P->peers.size(); q <= (size_t)NGSB_MAX_RANKS; q++) H.peer_off[q] = (unsigned int)P->nex;
+    H.peer_off[P->peers.size()] = (unsigned int)P->nex;
+    NGSB_CUDA(cudaMalloc(&P->d_H, sizeof(PeerHalo)));
+    NGSB_CUDA(cudaMemcpy(P->d_H, &H, sizeof(H), cudaMemcpyHostToDevice));
+    P->p2p = true;
+    return NGSB_OK;
+}
+
+extern "C" int ngsb_parmat_create_ex(ngsb_comm *comm, const ngsb_csr *local, const uint64_t *ex_first, const int32_t *ex_dofs,
+                                     int (*allgather)(void *user, const void *send, void *recv, size_t bytes_per_rank), void *user,
+                                     ngsb_parmat **out)
 {
     NGSB_REQUIRE(comm && local && ex_first && out, "ngsb_parmat_create: NULL argument");
     NGSB_REQUIRE(local->ctx == comm->ctx, "ngsb_parmat_create: matrix and communicator belong to different contexts");
     NGSB_REQUIRE(local->h == local->w, "ngsb_parmat_create: local matrix must be square");
+    NGSB_REQUIRE(comm->comm || allgather || comm->nranks == 1, "ngsb_parmat_create: this communicator has no NCCL; pass the bootstrap all-gather");
     ngsb_ctx *ctx = comm->ctx;
     NGSB_CUDA(cudaSetDevice(ctx->device));
     const int np = comm->nranks;
@@ -336,6 +642,7 @@ extern "C" int ngsb_parmat_create(ngsb_comm *comm, const ngsb_csr *local, const 
     P->local = local;
     P->n = n;
     P->es = (int)kind_scalars(local->kind);
+    P->esmax = (int)kind_matscalars(local->kind);
     P->nex = nex;
     P->peer_off.push_back(0);
     for (int p = 0; p < np; p++)
@@ -371,12 +678,29 @@ extern "C" int ngsb_parmat_create(ngsb_comm *comm, const ngsb_csr *local, const 
     if (rc == NGSB_OK) rc = up((void **)&P->d_if_first, if_first.data(), if_first.size() * sizeof(uint32_t));
     if (rc == NGSB_OK) rc = up((void **)&P->d_if_pos, if_pos.data(), if_pos.size() * sizeof(uint32_t));
     if (rc == NGSB_OK) rc = up((void **)&P->d_master, P->h_master.data(), n);
-    if (rc == NGSB_OK && cudaMalloc(&P->d_send, std::max<size_t>(16, nex * P->es * sizeof(double))) != cudaSuccess) rc = NGSB_ERR_NOMEM;
-    if (rc == NGSB_OK && cudaMalloc(&P->d_recv, std::max<size_t>(16, nex * P->es * sizeof(double))) != cudaSuccess) rc = NGSB_ERR_NOMEM;
     cudaStreamSynchronize(ctx->stream);
+    if (rc == NGSB_OK && comm->p2p) {
+        comm->boot_allgather = allgather;
+        comm->boot_user = user;
+        rc = parmat_setup_p2p(P, ex_first);
+        comm->boot_allgather = nullptr;
+        comm->boot_user = nullptr;
+        if (rc == NGSB_OK && !P->p2p && !comm->comm) { set_error("ngsb_parmat_create: could not map the neighbours' receive areas and there is no NCCL communicator"); rc = NGSB_ERR_COMM; }
+    }
+    if (rc == NGSB_OK && !P->p2p && np > 1) {
+        if (cudaMalloc(&P->d_send, std::max<size_t>(16, nex * P->es * sizeof(double))) != cudaSuccess) rc = NGSB_ERR_NOMEM;
+        if (rc == NGSB_OK && cudaMalloc(&P->d_recv, std::max<size_t>(16, nex * P->es * sizeof(double))) != cudaSuccess) rc = NGSB_ERR_NOMEM;
+        if (rc != NGSB_OK) set_error("ngsb_parmat_create: out of memory");
+    }
     if (rc != NGSB_OK) { ngsb_parmat_destroy(P); return rc; }
     *out = P;
     return NGSB_OK;
+}
+
+extern "C" int ngsb_parmat_create(ngsb_comm *comm, const ngsb_csr *local, const uint64_t *ex_first, const int32_t *ex_dofs,
+                                  ngsb_parmat **out)
+{
+    return ngsb_parmat_create_ex(comm, local, ex_first, ex_dofs, nullptr, nullptr, out);
 }
 
 extern "C" int ngsb_parmat_destroy(ngsb_parmat *P)
@@ -384,9 +708,23 @@ extern "C" int ngsb_parmat_destroy(ngsb_parmat *P)
     if (!P) return NGSB_OK;
     cudaSetDevice(P->comm->ctx->device);
     cudaStreamSynchronize(P->comm->ctx->stream);
+    if (P->graph_exec) cudaGraphExecDestroy(P->graph_exec);
+    for (size_t q = 0; q < P->peers.size() && q < (size_t)NGSB_MAX_RANKS; q++)
+        if (P->peer_halo[q]) cudaIpcCloseMemHandle(P->peer_halo[q]);
+    cudaFree(P->d_H); cudaFree(P->d_local); cudaFree(P->halo_mem);
     cudaFree(P->d_exdofs); cudaFree(P->d_send); cudaFree(P->d_recv);
     cudaFree(P->d_if_dof); cudaFree(P->d_if_first); cudaFree(P->d_if_pos); cudaFree(P->d_master);
     delete P;
+    return NGSB_OK;
+}
+
+extern "C" int ngsb_parmat_info(const ngsb_parmat *P, int *peer_memory, int *n_neighbours, size_t *n_exchange, size_t *n_interface)
+{
+    NGSB_REQUIRE(P, "ngsb_parmat_info: NULL argument");
+    if (peer_memory) *peer_memory = P->p2p ? 1 : 0;
+    if (n_neighbours) *n_neighbours = (int)P->peers.size();
+    if (n_exchange) *n_exchange = P->nex;
+    if (n_interface) *n_interface = P->nif;
     return NGSB_OK;
 }
 
@@ -409,7 +747,8 @@ extern "C" int ngsb_parmat_cumulate(const ngsb_parmat *P, ngsb_vec *v)
 {
     NGSB_TRY(check_pvec(P, v, "ParallelBaseVector::Cumulate"));
     NGSB_CUDA(cudaSetDevice(P->comm->ctx->device));
-    return cumulate_raw(P, v->d);
+    NGSB_TRY(cumulate_raw(P, v->d));
+    return check_peer_error(P->comm, "ParallelBaseVector::Cumulate");
 }
 
 extern "C" int ngsb_parmat_mult(const ngsb_parmat *P, const ngsb_vec *x, ngsb_vec *y)
@@ -419,36 +758,57 @@ extern "C" int ngsb_parmat_mult(const ngsb_parmat *P, const ngsb_vec *x, ngsb_ve
     return ngsb_csr_mult(P->local, x, y);
 }
 
-extern "C" int ngsb_parmat_dot(const ngsb_parmat *P, const ngsb_vec *x, const ngsb_vec *y, int both_cumulated, double *out)
+// out: (re, im); conjugate as in S_BaseVector<Complex>::InnerProduct (on the argument y)
+extern "C" int ngsb_parmat_dot(const ngsb_parmat *P, const ngsb_vec *x, const ngsb_vec *y, int both_cumulated, int conjugate, double out[2])
 {
     NGSB_TRY(check_pvec(P, x, "ParallelBaseVector::InnerProduct"));
     NGSB_TRY(check_pvec(P, y, "ParallelBaseVector::InnerProduct"));
     NGSB_REQUIRE(out, "ngsb_parmat_dot: out is NULL");
-    NGSB_REQUIRE(P->local->kind != NGSB_COMPLEX, "ngsb_parmat_dot: complex not supported here");
     ngsb_comm *comm = P->comm;
     ngsb_ctx *ctx = comm->ctx;
     NGSB_CUDA(cudaSetDevice(ctx->device));
-    double *tmp = nullptr;
-    if (both_cumulated) {
-        // both CUMULATED: the reference masks by master dofs (entry size 1) or Distribute()s one
-        // operand (parallelvvector.cpp:302-322); both equal "zero the non-master copies of x"
-        NGSB_TRY(ws_get_buf(ctx, x->nscal + 2, &tmp));
-        NGSB_CUDA(cudaMemcpyAsync(tmp, x->d, x->nscal * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-        int rc0 = launch_mask_zero(ctx, tmp, P->d_master, P->n, P->es);
-        if (rc0 != NGSB_OK) { ws_put_buf(ctx, x->nscal + 2, tmp); return rc0; }
-    }
-    int rc = launch_dot(ctx, both_cumulated ? tmp : x->d, y->d, x->nscal, 0, comm->d_red);
+    const bool cplx = P->local->kind == NGSB_COMPLEX;
+    // both CUMULATED: the reference masks by master dofs (entry size 1) or Distribute()s one operand
+    // (parallelvvector.cpp:302-322, 346-347); both equal "count every shared dof once, on its master"
+    int rc = launch_dot_masked(ctx, x->d, y->d, cplx ? x->n : x->nscal, cplx ? (conjugate ? 2 : 1) : 0, comm->d_red,
+                               both_cumulated ? P->d_master : nullptr, (unsigned)(cplx ? 1 : P->es));
     if (rc == NGSB_OK) rc = all_reduce2(comm, comm->d_red);
     if (rc == NGSB_OK) {
         cudaError_t e = cudaMemcpyAsync(ctx->h_pinned, comm->d_red, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) { set_error("ngsb_parmat_dot: %s", cudaGetErrorString(e)); rc = NGSB_ERR_CUDA; }
-        else *out = ctx->h_pinned[0];
+        else { out[0] = ctx->h_pinned[0]; out[1] = cplx ? ctx->h_pinned[1] : 0.0; }
     }
-    if (tmp) ws_put_buf(ctx, x->nscal + 2, tmp);
+    if (rc == NGSB_OK) rc = check_peer_error(comm, "ParallelBaseVector::InnerProduct");
     return rc;
 }
 
+// one distributed CG iteration; peer-memory mode: 6 kernels, no library call, capturable
+static int enqueue_par_iteration(const ngsb_parmat *P, const CgVecs &v, double *as)
+{
+    ngsb_comm *comm = P->comm;
+    ngsb_ctx *ctx = comm->ctx;
+    const ngsb_csr *A = P->local;
+    SpmvArgs a;
+    memset(&a, 0, sizeof(a));
+    a.A = A; a.x = v.s; a.y = as; a.sr = 1.0; a.accumulate = false;
+    a.epi = EPI_DOT_OUT; a.dotvec = v.s; a.dot_conj = v.ip_mode == NGSB_IP_COMPLEX_CONJ; a.dot_out = comm->d_red; a.state = v.state;
+    NGSB_TRY(spmv_launch(a));                                                   // as = A s (DISTRIBUTED), local <s,as>
+    if (P->p2p) {
+        NGSB_TRY(cumulate_es(P, as, P->es, v.state, comm->d_red, 1));           // as -> CUMULATED; kss all-reduced, al = wd/kss
+        NGSB_TRY(cg_launch_fused(ctx, A->kind, 1, v, 0));                       // u, d, w, masked <d,w> -> d_red
+        NGSB_TRY(cg_launch_finalize(ctx, 2, v.state, comm->d_red, v.hist, comm->d_R));   // all-reduce, be, loop condition
+    } else {
+        NGSB_TRY(all_reduce2(comm, comm->d_red));
+        NGSB_TRY(cg_launch_finalize(ctx, 1, v.state, comm->d_red, v.hist));
+        NGSB_TRY(cumulate_raw(P, as));
+        NGSB_TRY(cg_launch_fused(ctx, A->kind, 1, v, 0));
+        NGSB_TRY(all_reduce2(comm, comm->d_red));
+        NGSB_TRY(cg_launch_finalize(ctx, 2, v.state, comm->d_red, v.hist));
+    }
+    NGSB_TRY(cg_launch_dir(ctx, A->kind, v));                                   // s = be s + w
+    return NGSB_OK;
+}
 
 // Distributed Jacobi-PCG, the reference's sequence of statuses:
 //   d = f (DISTRIBUTED) -> Jacobi cumulates d; w, s CUMULATED; wdn = masked <w,d> + all-reduce
@@ -456,12 +816,13 @@ extern "C" int ngsb_parmat_dot(const ngsb_parmat *P, const ngsb_vec *x, const ng
 //         d -= al as cumulates as (the one neighbour exchange of the iteration);
 //         w = C d; wdn = masked <d,w> + all-reduce; s = be s + w.
 extern "C" int ngsb_parmat_cg_solve(const ngsb_parmat *P, const ngsb_jacobi *C, const ngsb_vec *f, ngsb_vec *u, double prec,
-                                    int maxsteps, int *steps, double *history, int hist_cap, int *nhist)
+                                    int maxsteps, int ip_mode, int *steps, double *history, int hist_cap, int *nhist)
 {
     NGSB_TRY(check_pvec(P, f, "CGSolver::Mult(parallel)"));
     NGSB_TRY(check_pvec(P, u, "CGSolver::Mult(parallel)"));
     const ngsb_csr *A = P->local;
-    NGSB_REQUIRE(A->kind != NGSB_COMPLEX, "ngsb_parmat_cg_solve: complex systems are not supported by the distributed CG");
+    NGSB_REQUIRE(ip_mode >= 0 && ip_mode <= 2 && (A->kind == NGSB_COMPLEX) == (ip_mode != NGSB_IP_REAL),
+                 "CGSolver::Mult(parallel): ip_mode %d does not fit matrix kind %d", ip_mode, A->kind);
     NGSB_REQUIRE(!C || (C->n == A->h && C->kind == A->kind && C->ctx == A->ctx), "ngsb_parmat_cg_solve: preconditioner does not match");
     NGSB_REQUIRE(maxsteps >= 0 && f->d != u->d, "ngsb_parmat_cg_solve: bad arguments");
     ngsb_comm *comm = P->comm;
@@ -482,7 +843,7 @@ extern "C" int ngsb_parmat_cg_solve(const ngsb_parmat *P, const ngsb_jacobi *C, 
     hs->prec2 = prec * prec;
     hs->maxsteps = maxsteps;
     hs->hist_cap = hist_cap;
-    hs->cplx = 0;
+    hs->cplx = ip_mode != NGSB_IP_REAL;
     int rc = NGSB_OK;
     auto cu = [&](cudaError_t e) { if (e != cudaSuccess && rc == NGSB_OK) { set_error("parallel CG: %s", cudaGetErrorString(e)); rc = NGSB_ERR_CUDA; } };
     cu(cudaMemcpyAsync(d_state, hs, sizeof(CgState), cudaMemcpyHostToDevice, ctx->stream));
@@ -499,7 +860,7 @@ extern "C" int ngsb_parmat_cg_solve(const ngsb_parmat *P, const ngsb_jacobi *C, 
     v.hist = d_hist;
     v.partials = ctx->d_partials;
     v.counter = ctx->d_counter;
-    v.ip_mode = NGSB_IP_REAL;
+    v.ip_mode = ip_mode;
 
     // u = 0; d = f, cumulated by the Jacobi application (linalg/jacobi.cpp:78)
     cu(cudaMemsetAsync(u->d, 0, nscal * sizeof(double), ctx->stream));
@@ -507,10 +868,32 @@ extern "C" int ngsb_parmat_cg_solve(const ngsb_parmat *P, const ngsb_jacobi *C, 
     if (rc == NGSB_OK) rc = cumulate_raw(P, d);
     v.f = d;                       // init kernel reads f, writes d: same values
     if (rc == NGSB_OK) rc = cg_launch_fused(ctx, A->kind, 0, v, 0);
-    if (rc == NGSB_OK) rc = all_reduce2(comm, comm->d_red);
-    if (rc == NGSB_OK) rc = cg_launch_finalize(ctx, 0, d_state, comm->d_red, d_hist);
+    if (rc == NGSB_OK && !P->p2p) rc = all_reduce2(comm, comm->d_red);
+    if (rc == NGSB_OK) rc = cg_launch_finalize(ctx, 0, d_state, comm->d_red, d_hist, P->p2p ? comm->d_R : nullptr);
 
     const long batch = ctx->cg_batch;
+    // peer-memory mode has no library call inside the iteration: one CUDA graph per batch
+    ngsb_parmat *Pm = const_cast<ngsb_parmat *>(P);
+    const bool use_graph = P->p2p && !ctx->timing && getenv("NGSB_NO_CUDA_GRAPH") == nullptr && batch > 1;
+    if (rc == NGSB_OK && use_graph) {
+        const void *key[8] = {u->d, d, w, s, as, C, (const void *)(intptr_t)ip_mode, d_hist};
+        const bool hit = Pm->graph_exec && Pm->g_batch == batch && memcmp(key, Pm->g_key, sizeof(key)) == 0;
+        if (!hit) {
+            if (Pm->graph_exec) { cudaGraphExecDestroy(Pm->graph_exec); Pm->graph_exec = nullptr; }
+            cudaGraph_t graph = nullptr;
+            const uint64_t launches_before = ctx->launches;
+            cu(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+            if (rc == NGSB_OK) {
+                for (long k = 0; k < batch && rc == NGSB_OK; k++) rc = enqueue_par_iteration(P, v, as);
+                cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
+                ctx->launches = launches_before;
+                if (rc == NGSB_OK) cu(ce);
+                if (rc == NGSB_OK) cu(cudaGraphInstantiate(&Pm->graph_exec, graph, 0));
+                if (graph) cudaGraphDestroy(graph);
+                if (rc == NGSB_OK) { memcpy(Pm->g_key, key, sizeof(key)); Pm->g_batch = batch; }
+            }
+        }
+    }
     cudaEvent_t ev[2] = {nullptr, nullptr};
     cu(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
     cu(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
@@ -519,19 +902,11 @@ extern "C" int ngsb_parmat_cg_solve(const ngsb_parmat *P, const ngsb_jacobi *C, 
     bool finished = false;
     while (rc == NGSB_OK && !finished) {
         if (enq < max_batches) {
-            for (long k = 0; k < batch && rc == NGSB_OK; k++) {
-                SpmvArgs a;
-                memset(&a, 0, sizeof(a));
-                a.A = A; a.x = s; a.y = as; a.sr = 1.0; a.accumulate = false;
-                a.epi = EPI_DOT_OUT; a.dotvec = s; a.dot_out = comm->d_red; a.state = d_state;
-                rc = spmv_launch(a);                                                   // as = A s, local <s,as>
-                if (rc == NGSB_OK) rc = all_reduce2(comm, comm->d_red);
-                if (rc == NGSB_OK) rc = cg_launch_finalize(ctx, 1, d_state, comm->d_red, d_hist);
-                if (rc == NGSB_OK) rc = cumulate_raw(P, as);                            // as -> CUMULATED
-                if (rc == NGSB_OK) rc = cg_launch_fused(ctx, A->kind, 1, v, 0);        // u, d, w, masked <d,w>
-                if (rc == NGSB_OK) rc = all_reduce2(comm, comm->d_red);
-                if (rc == NGSB_OK) rc = cg_launch_finalize(ctx, 2, d_state, comm->d_red, d_hist);
-                if (rc == NGSB_OK) rc = cg_launch_dir(ctx, A->kind, v);                // s = be s + w
+            if (use_graph) {
+                cu(cudaGraphLaunch(Pm->graph_exec, ctx->stream));
+                ctx->launches += 6 * batch;
+            } else {
+                for (long k = 0; k < batch && rc == NGSB_OK; k++) rc = enqueue_par_iteration(P, v, as);
             }
             if (rc != NGSB_OK) break;
         }
@@ -547,6 +922,7 @@ extern "C" int ngsb_parmat_cg_solve(const ngsb_parmat *P, const ngsb_jacobi *C, 
     cu(cudaStreamSynchronize(ctx->stream));
     if (ev[0]) cudaEventDestroy(ev[0]);
     if (ev[1]) cudaEventDestroy(ev[1]);
+    if (rc == NGSB_OK) rc = check_peer_error(comm, "CGSolver::Mult(parallel)");
     if (rc == NGSB_OK) {
         cu(cudaMemcpyAsync(&hs[3], d_state, sizeof(CgState), cudaMemcpyDeviceToHost, ctx->stream));
         cu(cudaStreamSynchronize(ctx->stream));
@@ -563,4 +939,25 @@ extern "C" int ngsb_parmat_cg_solve(const ngsb_parmat *P, const ngsb_jacobi *C, 
     ws_put_buf(ctx, nscal, as);
     if (w) ws_put_buf(ctx, nscal, w);
     return rc;
+}
+
+// GMRESSolver<IPTYPE>::Mult on parallel vectors (linalg/cg.cpp:854-1022 with parallel/parallelvvector.cpp semantics):
+// f DISTRIBUTED in, x CUMULATED out.
+static int gm_allreduce(void *arg, double *d_buf) { return all_reduce2(((const ngsb_parmat *)arg)->comm, d_buf); }
+static int gm_cumulate(void *arg, double *v) { return cumulate_raw((const ngsb_parmat *)arg, v); }
+
+extern "C" int ngsb_parmat_gmres_solve(const ngsb_parmat *P, const ngsb_jacobi *C, const ngsb_vec *f, ngsb_vec *x, double prec,
+                                       int maxsteps, int *steps, double *history, int hist_cap, int *nhist)
+{
+    NGSB_TRY(check_pvec(P, f, "GMRESSolver::Mult(parallel)"));
+    NGSB_TRY(check_pvec(P, x, "GMRESSolver::Mult(parallel)"));
+    ngsb_comm *comm = P->comm;
+    GmresDist dist;
+    dist.master = P->d_master;
+    dist.R = (comm->nranks > 1 && P->p2p) ? comm->d_R : nullptr;
+    dist.allreduce = (comm->nranks > 1 && !P->p2p) ? gm_allreduce : nullptr;
+    dist.cumulate = gm_cumulate;
+    dist.arg = (void *)P;
+    NGSB_TRY(gmres_solve_impl(P->local, C, f, x, prec, maxsteps, 1, steps, history, hist_cap, nhist, &dist));
+    return check_peer_error(comm, "GMRESSolver::Mult(parallel)");
 }

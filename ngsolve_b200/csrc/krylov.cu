@@ -14,6 +14,7 @@
 // Gram-Schmidt in the reference's order (each projection fused with the next inner product),
 // Givens rotations and the triangular solve in single-thread kernels on the device.
 #include "krylov.cuh"
+#include "peer.cuh"
 
 #include <map>
 
@@ -355,19 +356,20 @@ static int launch_cg_fused(ngsb_ctx *ctx, int kind, const CgVecs &v, int sub)
     return NGSB_OK;
 }
 
-__global__ void cg_finalize_kernel(int which, CgState *st, const double *dot, double *hist)
+__global__ void cg_finalize_kernel(int which, CgState *st, double *dot, double *hist, const PeerReduce *R)
 {
     if (which != 0 && st->done) return;
+    if (R) pr_allreduce_inplace(*R, dot);        // distributed, peer-memory mode: sum of the ranks' partials
     double2 t = make_double2(dot[0], dot[1]);
     if (which == 0) cg_finalize_init(st, t, hist);
     else if (which == 1) cg_finalize_kss(st, t);
     else cg_finalize_wdn(st, t, hist);
 }
 
-int cg_launch_finalize(ngsb_ctx *ctx, int which, CgState *st, const double *dot, double *hist)
+int cg_launch_finalize(ngsb_ctx *ctx, int which, CgState *st, double *dot, double *hist, const PeerReduce *R)
 {
     SpanGuard g(ctx, KC_OTHER);
-    cg_finalize_kernel<<<1, 1, 0, ctx->stream>>>(which, st, dot, hist);
+    cg_finalize_kernel<<<1, 1, 0, ctx->stream>>>(which, st, dot, hist, R);
     NGSB_CUDA(cudaGetLastError());
     return NGSB_OK;
 }
@@ -572,8 +574,9 @@ __device__ __forceinline__ double2 z_sqrt(double2 z, int cplx)
 }
 
 // after norm2 = sum |r|^2 (tmp) and rr = <r,r> (tmp2): cg.cpp:889-903
-__global__ void gmres_init_kernel(GmresState *st, double2 *gammai, double *hist)
+__global__ void gmres_init_kernel(GmresState *st, double2 *gammai, double *hist, const PeerReduce *R)
 {
+    if (R) { pr_allreduce_inplace(*R, st->tmp); pr_allreduce_inplace(*R, st->tmp2); }
     st->norm = sqrt(st->tmp[0]);
     double2 rr = make_double2(st->tmp2[0], st->cplx ? st->tmp2[1] : 0.0);
     double2 sq = z_sqrt(rr, st->cplx);
@@ -591,17 +594,20 @@ __global__ void gmres_init_kernel(GmresState *st, double2 *gammai, double *hist)
 }
 
 // h(i,j) = tmp; publish -h(i,j) as the next axpy scalar (kept in hcol[i])
-__global__ void gmres_store_h_kernel(GmresState *st, double2 *h, int ms, int i)
+__global__ void gmres_store_h_kernel(GmresState *st, double2 *h, int ms, int i, const PeerReduce *R)
 {
     if (st->done) return;
+    if (R) pr_allreduce_inplace(*R, st->tmp);
     int j = st->j;
     h[(size_t)i * ms + j] = make_double2(st->tmp[0], st->cplx ? st->tmp[1] : 0.0);
 }
 
 // after <w,w> (tmp): h(j+1,j), scale, Givens, norm, loop condition -- cg.cpp:934-962
-__global__ void gmres_givens_kernel(GmresState *st, double2 *h, double2 *gammai, double2 *ci, double2 *si, int ms, double *hist)
+__global__ void gmres_givens_kernel(GmresState *st, double2 *h, double2 *gammai, double2 *ci, double2 *si, int ms, double *hist,
+                                    const PeerReduce *R)
 {
     if (st->done) return;
+    if (R) pr_allreduce_inplace(*R, st->tmp);
     const int j = st->j;
     const int cplx = st->cplx;
 #define H(a, b) h[(size_t)(a) * ms + (b)]
@@ -653,7 +659,7 @@ template <bool CPLX>
 __global__ void __launch_bounds__(256) gmres_mgs_kernel(double *__restrict__ w, const double *__restrict__ vprev,
                                                        const double2 *__restrict__ hprev, const double *__restrict__ vnext,
                                                        int selfdot, uint64_t N, GmresState *st, double *partials,
-                                                       unsigned int *counter)
+                                                       unsigned int *counter, const uint8_t *__restrict__ master, unsigned mask_div)
 {
     if (st->done) return;
     double hr = 0.0, hi = 0.0;
@@ -671,12 +677,14 @@ __global__ void __launch_bounds__(256) gmres_mgs_kernel(double *__restrict__ w, 
                 wv.y -= hr * p.y + hi * p.x;
                 reinterpret_cast<double2 *>(w)[i] = wv;
             }
+            if (master && !master[i]) continue;      // masked inner product: master dofs only
             double2 q = selfdot ? wv : reinterpret_cast<const double2 *>(vnext)[i];
             ar += q.x * wv.x - q.y * wv.y;
             ai += q.x * wv.y + q.y * wv.x;
         } else {
             double wv = w[i];
             if (vprev) { wv -= hr * vprev[i]; w[i] = wv; }
+            if (master && !master[i / mask_div]) continue;
             double q = selfdot ? wv : vnext[i];
             ar = fma(q, wv, ar);
         }
@@ -758,10 +766,25 @@ extern "C" int ngsb_cg_solve_host(const ngsb_csr *A, const ngsb_jacobi *C, const
 extern "C" int ngsb_gmres_solve(const ngsb_csr *A, const ngsb_jacobi *C, const ngsb_vec *fvec, ngsb_vec *xvec, double prec,
                                 int maxsteps, int initialize, int *steps, double *history, int hist_cap, int *nhist)
 {
+    return ngsb::gmres_solve_impl(A, C, fvec, xvec, prec, maxsteps, initialize, steps, history, hist_cap, nhist, nullptr);
+}
+
+// dist == NULL: one GPU.  Otherwise the reference's parallel-vector choreography: A v is DISTRIBUTED and is
+// cumulated before the preconditioner, every Krylov vector is CUMULATED, inner products and the norm are
+// restricted to master dofs and summed over the ranks (parallelvvector.cpp:289-358).
+int ngsb::gmres_solve_impl(const ngsb_csr *A, const ngsb_jacobi *C, const ngsb_vec *fvec, ngsb_vec *xvec, double prec,
+                           int maxsteps, int initialize, int *steps, double *history, int hist_cap, int *nhist, const GmresDist *dist)
+{
     NGSB_TRY(check_solver_args(A, C, fvec, xvec, "GMRESSolver::Mult"));
     NGSB_REQUIRE(maxsteps >= 1, "GMRESSolver::Mult: maxsteps < 1");
     ngsb_ctx *ctx = A->ctx;
     NGSB_CUDA(cudaSetDevice(ctx->device));
+    const uint8_t *master = dist ? dist->master : nullptr;
+    const PeerReduce *R = dist ? dist->R : nullptr;
+    const unsigned mask_div = (unsigned)(A->kind == NGSB_BLOCK3 ? 3 : 1);
+    // host-enqueued all-reduce of a device (re,im) pair (NCCL mode); peer-memory mode reduces inside the scalar kernels
+    auto allred = [&](double *d_buf) -> int { return (dist && dist->allreduce) ? dist->allreduce(dist->arg, d_buf) : NGSB_OK; };
+    auto cumulate = [&](double *v) -> int { return (dist && dist->cumulate) ? dist->cumulate(dist->arg, v) : NGSB_OK; };
     const bool cplx = A->kind == NGSB_COMPLEX;
     const size_t nscal = A->h * kind_scalars(A->kind);
     const uint64_t N = cplx ? A->h : nscal;        // reduction / update length in scalars of the IP type
@@ -822,6 +845,8 @@ extern "C" int ngsb_gmres_solve(const ngsb_csr *A, const ngsb_jacobi *C, const n
 
     double *x = xvec->d;
     const double *f = fvec->d;
+    double *d_tmp = (double *)((char *)d_st + offsetof(GmresState, tmp));
+    double *d_tmp2 = (double *)((char *)d_st + offsetof(GmresState, tmp2));
     auto spmv = [&](const double *in, double *out) {
         SpmvArgs a;
         memset(&a, 0, sizeof(a));
@@ -831,9 +856,10 @@ extern "C" int ngsb_gmres_solve(const ngsb_csr *A, const ngsb_jacobi *C, const n
     const int rgrid = reduce_grid(ctx, N);
     auto mgs = [&](const double *vprev, const double2 *hprev, const double *vnext, int selfdot) {
         SpanGuard g(ctx, KC_VEC);
-        if (cplx) gmres_mgs_kernel<true><<<rgrid, 256, 0, ctx->stream>>>(w, vprev, hprev, vnext, selfdot, N, d_st, ctx->d_partials, ctx->d_counter);
-        else gmres_mgs_kernel<false><<<rgrid, 256, 0, ctx->stream>>>(w, vprev, hprev, vnext, selfdot, N, d_st, ctx->d_partials, ctx->d_counter);
-        return cudaGetLastError() == cudaSuccess ? NGSB_OK : NGSB_ERR_CUDA;
+        if (cplx) gmres_mgs_kernel<true><<<rgrid, 256, 0, ctx->stream>>>(w, vprev, hprev, vnext, selfdot, N, d_st, ctx->d_partials, ctx->d_counter, master, mask_div);
+        else gmres_mgs_kernel<false><<<rgrid, 256, 0, ctx->stream>>>(w, vprev, hprev, vnext, selfdot, N, d_st, ctx->d_partials, ctx->d_counter, master, mask_div);
+        if (cudaGetLastError() != cudaSuccess) return NGSB_ERR_CUDA;
+        return allred(d_tmp);
     };
 
     // r = f (or f - A x); r = C r
@@ -845,16 +871,19 @@ extern "C" int ngsb_gmres_solve(const ngsb_csr *A, const ngsb_jacobi *C, const n
         GM_CUDA(cudaMemcpyAsync(r, f, nscal * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
         GM_TRY(launch_axpby(ctx, r, av, N, -1.0, 0.0, cplx, true));
     }
+    GM_TRY(cumulate(r));
     if (C) {
         GM_TRY(jacobi_apply(C, 1.0, 0.0, r, hv, false));
         GM_CUDA(cudaMemcpyAsync(r, hv, nscal * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
     }
     // norm = r.L2Norm(); v = 1/sqrt(<r,r>) r
-    GM_TRY(launch_dot(ctx, r, r, nscal, 3, (double *)((char *)d_st + offsetof(GmresState, tmp))));
-    GM_TRY(launch_dot(ctx, r, r, N, cplx ? 1 : 0, (double *)((char *)d_st + offsetof(GmresState, tmp2))));
+    GM_TRY(launch_dot_masked(ctx, r, r, nscal, 3, d_tmp, master, cplx ? 2 : mask_div));
+    GM_TRY(allred(d_tmp));
+    GM_TRY(launch_dot_masked(ctx, r, r, N, cplx ? 1 : 0, d_tmp2, master, mask_div));
+    GM_TRY(allred(d_tmp2));
     {
         SpanGuard g(ctx, KC_OTHER);
-        gmres_init_kernel<<<1, 1, 0, ctx->stream>>>(d_st, d_gam, d_hist);
+        gmres_init_kernel<<<1, 1, 0, ctx->stream>>>(d_st, d_gam, d_hist, R);
     }
     double *d_st_scale = (double *)((char *)d_st + offsetof(GmresState, scale));
     // v_0
@@ -874,6 +903,7 @@ extern "C" int ngsb_gmres_solve(const ngsb_csr *A, const ngsb_jacobi *C, const n
         j = hst.j;   // current column
         double *v = vi[j];
         GM_TRY(spmv(v, av));
+        GM_TRY(cumulate(av));
         const double *avp = av;
         if (C) { GM_TRY(jacobi_apply(C, 1.0, 0.0, av, hv, false)); avp = hv; }
         GM_CUDA(cudaMemcpyAsync(w, avp, nscal * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
@@ -881,12 +911,12 @@ extern "C" int ngsb_gmres_solve(const ngsb_csr *A, const ngsb_jacobi *C, const n
         for (int i = 0; i <= j; i++) {
             GM_TRY(mgs(i > 0 ? vi[i - 1] : nullptr, i > 0 ? d_h + (size_t)(i - 1) * ms + j : nullptr, vi[i], 0));
             SpanGuard g(ctx, KC_OTHER);
-            gmres_store_h_kernel<<<1, 1, 0, ctx->stream>>>(d_st, d_h, ms, i);
+            gmres_store_h_kernel<<<1, 1, 0, ctx->stream>>>(d_st, d_h, ms, i, R);
         }
         GM_TRY(mgs(vi[j], d_h + (size_t)j * ms + j, nullptr, 1));       // last projection + <w,w>
         {
             SpanGuard g(ctx, KC_OTHER);
-            gmres_givens_kernel<<<1, 1, 0, ctx->stream>>>(d_st, d_h, d_gam, d_ci, d_si, ms, d_hist);
+            gmres_givens_kernel<<<1, 1, 0, ctx->stream>>>(d_st, d_h, d_gam, d_ci, d_si, ms, d_hist, R);
         }
         // v_{j+1} = 1/h(j+1,j) * w  (always formed, like the reference)
         double *vn = nullptr;

@@ -2,6 +2,8 @@
 #pragma once
 #include "jacobi.cuh"
 
+struct PeerReduce;
+
 namespace ngsb {
 
 struct CgVecs {
@@ -25,7 +27,19 @@ struct CgVecs {
 int cg_launch_fused(ngsb_ctx *ctx, int kind, int mode, const CgVecs &v, int sub);
 int cg_launch_dir(ngsb_ctx *ctx, int kind, const CgVecs &v);
 // scalar steps from a reduced dot (device, 2 doubles): which 0 init, 1 kss, 2 wdn
-int cg_launch_finalize(ngsb_ctx *ctx, int which, CgState *st, const double *dot, double *hist);
+// R != NULL (distributed, peer-memory mode): `dot` holds this rank's partial and is all-reduced in place first
+int cg_launch_finalize(ngsb_ctx *ctx, int which, CgState *st, double *dot, double *hist, const PeerReduce *R = nullptr);
+
+// hooks that turn the one-GPU GMRES into the parallel-vector version (dist.cu)
+struct GmresDist {
+    const uint8_t *master;                        // device, 1 byte per dof
+    const PeerReduce *R;                          // device; NULL: reduce with `allreduce`
+    int (*allreduce)(void *arg, double *d_buf);   // enqueue an all-reduce (sum) of 2 doubles; NULL in peer-memory mode
+    int (*cumulate)(void *arg, double *v);        // ParallelBaseVector::Cumulate of a raw local vector
+    void *arg;
+};
+int gmres_solve_impl(const ngsb_csr *A, const ngsb_jacobi *C, const ngsb_vec *f, ngsb_vec *x, double prec, int maxsteps,
+                     int initialize, int *steps, double *history, int hist_cap, int *nhist, const GmresDist *dist);
 
 // solver workspace (cached on the context)
 int ws_get_buf(ngsb_ctx *ctx, size_t nscal, double **out);

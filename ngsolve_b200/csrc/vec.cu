@@ -338,6 +338,59 @@ int launch_dot(ngsb_ctx *ctx, const double *x, const double *y, size_t N, int mo
     return NGSB_OK;
 }
 
+// the same reduction restricted to entries whose owner byte is set (masked inner product of two
+// CUMULATED parallel vectors, parallel/parallelvvector.cpp:305-314); mask index = i / mask_div
+template <int MODE>
+__global__ void __launch_bounds__(256) dot_masked_kernel(const double *__restrict__ x, const double *__restrict__ y, size_t N,
+                                                         const uint8_t *__restrict__ mask, unsigned mask_div,
+                                                         double *__restrict__ partials, unsigned int *counter, double *__restrict__ out)
+{
+    size_t per = (N + gridDim.x - 1) / gridDim.x;
+    size_t lo = (size_t)blockIdx.x * per;
+    size_t hi = lo + per < N ? lo + per : N;
+    double a = 0.0, b = 0.0;
+    for (size_t k = lo + threadIdx.x; k < hi; k += blockDim.x) {
+        if (!mask[k / mask_div]) continue;
+        if (MODE == 0 || MODE == 3) {
+            a = fma(x[k], (MODE == 3 ? x[k] : y[k]), a);
+        } else {
+            double2 u = reinterpret_cast<const double2 *>(x)[k], v = reinterpret_cast<const double2 *>(y)[k];
+            if (MODE == 2) v.y = -v.y;
+            a += u.x * v.x - u.y * v.y;
+            b += u.x * v.y + u.y * v.x;
+        }
+    }
+    double2 mine = block_sum2(a, b);
+    double2 total;
+    if (finish_partials(mine, partials, counter, &total)) {
+        out[0] = total.x;
+        out[1] = total.y;
+    }
+}
+
+int launch_dot_masked(ngsb_ctx *ctx, const double *x, const double *y, size_t N, int mode, double *d_out, const uint8_t *mask,
+                      unsigned mask_div)
+{
+    if (!mask) return launch_dot(ctx, x, y, N, mode, d_out);
+    SpanGuard g(ctx, KC_VEC);
+    size_t blocks = (N + 4095) / 4096;
+    size_t cap = (size_t)ctx->sm_count * 4;
+    if (cap > (size_t)MAX_PARTIALS) cap = MAX_PARTIALS;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    int grid = (int)blocks;
+    if (mask_div < 1) mask_div = 1;
+    switch (mode) {
+    case 0: dot_masked_kernel<0><<<grid, 256, 0, ctx->stream>>>(x, y, N, mask, mask_div, ctx->d_partials, ctx->d_counter, d_out); break;
+    case 1: dot_masked_kernel<1><<<grid, 256, 0, ctx->stream>>>(x, y, N, mask, mask_div, ctx->d_partials, ctx->d_counter, d_out); break;
+    case 2: dot_masked_kernel<2><<<grid, 256, 0, ctx->stream>>>(x, y, N, mask, mask_div, ctx->d_partials, ctx->d_counter, d_out); break;
+    default: dot_masked_kernel<3><<<grid, 256, 0, ctx->stream>>>(x, x, N, mask, mask_div, ctx->d_partials, ctx->d_counter, d_out); break;
+    }
+    NGSB_CUDA(cudaGetLastError());
+    return NGSB_OK;
+}
+
+
 // in-place inclusive scan of rowlen[0..n] (three-phase, chunk per CTA)
 __global__ void __launch_bounds__(256) scan_chunks_kernel(uint64_t *a, uint64_t n, uint64_t chunk, uint64_t *sums)
 {

@@ -1,6 +1,7 @@
-"""One GPU per process: ParallelDofs / ParallelMatrix / Cumulate and the distributed Jacobi-PCG
+"""One GPU per process: ParallelDofs / ParallelMatrix / Cumulate and the distributed Krylov solvers
 (linalg/paralleldofs.cpp, parallel/parallel_matrices.cpp, parallel/parallelvvector.cpp), bound to
-the C ABI.  torch.distributed is only the plumbing that hands the ncclUniqueId to the ranks."""
+the C ABI.  torch.distributed is only the bootstrap plumbing: it hands the ncclUniqueId to the ranks,
+or (bootstrap="allgather") carries the CUDA IPC handles of the peer-memory data path itself."""
 import ctypes as C
 import weakref
 
@@ -10,14 +11,40 @@ from . import _capi, la
 from ._capi import check
 
 
-class Communicator:
-    """NgMPI_Comm stand-in: an NCCL communicator on the context's stream."""
+def _make_allgather(dist, nranks):
+    """ngsb_allgather_fn on top of torch.distributed (any backend)."""
+    import torch
 
-    def __init__(self, ctx, nranks, rank, dist=None):
-        self.ctx, self.nranks, self.rank = ctx, nranks, rank
-        uid = (C.c_ubyte * 128)()
-        if nranks > 1:
+    def fn(_user, send, recv, nbytes):
+        try:
+            src = torch.frombuffer((C.c_ubyte * nbytes).from_address(send), dtype=torch.uint8).clone()
+            cuda = dist.get_backend() == "nccl"
+            if cuda:
+                src = src.cuda()
+            outs = [torch.empty_like(src) for _ in range(nranks)]
+            dist.all_gather(outs, src)
+            flat = torch.cat(outs).cpu().numpy().tobytes()
+            C.memmove(recv, flat, nbytes * nranks)
+            return 0
+        except Exception:      # never raise through the C frame
+            import traceback
+            traceback.print_exc()
+            return 1
+    return _capi.ALLGATHER_FN(fn)
+
+
+class Communicator:
+    """NgMPI_Comm stand-in.  bootstrap="nccl": an NCCL communicator on the context's stream (also the
+    fall-back data path); bootstrap="allgather": no NCCL at all, peer memory only.
+    p2p: -1 auto, 0 NCCL data path, 1 peer memory required."""
+
+    def __init__(self, ctx, nranks, rank, dist=None, bootstrap="nccl", p2p=-1):
+        self.ctx, self.nranks, self.rank, self.dist = ctx, nranks, rank, dist
+        self._cb = _make_allgather(dist, nranks) if (nranks > 1 and bootstrap == "allgather") else None
+        uid = None
+        if nranks > 1 and bootstrap == "nccl":
             import torch
+            uid = (C.c_ubyte * 128)()
             if rank == 0:
                 check(_capi.lib().ngsb_comm_unique_id(uid))
             t = torch.tensor(list(uid), dtype=torch.uint8)
@@ -26,9 +53,16 @@ class Communicator:
             dist.broadcast(t, 0)
             uid = (C.c_ubyte * 128)(*t.cpu().tolist())
         h = C.c_void_p()
-        check(_capi.lib().ngsb_comm_create(ctx.handle, nranks, rank, uid, C.byref(h)))
+        check(_capi.lib().ngsb_comm_create_ex(ctx.handle, nranks, rank, uid, C.cast(self._cb, C.c_void_p) if self._cb else None,
+                                              None, p2p, C.byref(h)))
         self.handle = h
         self._fin = weakref.finalize(self, _capi.lib().ngsb_comm_destroy, h)
+
+    @property
+    def peer_memory(self):
+        pm = C.c_int()
+        check(_capi.lib().ngsb_comm_info(self.handle, None, None, C.byref(pm), None))
+        return bool(pm.value)
 
 
 class ParallelDofs:
@@ -62,10 +96,17 @@ class ParallelMatrix(la.BaseMatrix):
         self.height = self.width = local.height
         self.is_complex, self.entrysize = local.is_complex, local.entrysize
         h = C.c_void_p()
-        check(_capi.lib().ngsb_parmat_create(comm.handle, local.handle, la._np_ptr(pardofs.ex_first),
-                                             la._np_ptr(pardofs.ex_dofs) if len(pardofs.ex_dofs) else None, C.byref(h)))
+        check(_capi.lib().ngsb_parmat_create_ex(comm.handle, local.handle, la._np_ptr(pardofs.ex_first),
+                                                la._np_ptr(pardofs.ex_dofs) if len(pardofs.ex_dofs) else None,
+                                                C.cast(comm._cb, C.c_void_p) if comm._cb else None, None, C.byref(h)))
         self.handle = h
         self._fin = weakref.finalize(self, _capi.lib().ngsb_parmat_destroy, h)
+
+    @property
+    def peer_memory(self):
+        pm = C.c_int()
+        check(_capi.lib().ngsb_parmat_info(self.handle, C.byref(pm), None, None, None))
+        return bool(pm.value)
 
     def MasterDofs(self):
         out = np.empty(self.height, dtype=np.uint8)
@@ -81,12 +122,12 @@ class ParallelMatrix(la.BaseMatrix):
         v._dev_write()
         check(_capi.lib().ngsb_parmat_cumulate(self.handle, v.handle))
 
-    def InnerProduct(self, x, y, both_cumulated):
+    def InnerProduct(self, x, y, both_cumulated, conjugate=True):
         x._dev_read()
         y._dev_read()
-        out = C.c_double()
-        check(_capi.lib().ngsb_parmat_dot(self.handle, x.handle, y.handle, 1 if both_cumulated else 0, C.byref(out)))
-        return out.value
+        out = (C.c_double * 2)()
+        check(_capi.lib().ngsb_parmat_dot(self.handle, x.handle, y.handle, 1 if both_cumulated else 0, 1 if conjugate else 0, out))
+        return complex(out[0], out[1]) if self.is_complex else out[0]
 
     def CreateSmoother(self, freedofs=None):
         bits = la._freebits(freedofs)
@@ -94,15 +135,27 @@ class ParallelMatrix(la.BaseMatrix):
         check(_capi.lib().ngsb_parmat_jacobi_create(self.handle, la._np_ptr(bits) if bits is not None else None, C.byref(h)))
         return _ParJacobi(self, h)
 
-    def cg_solve(self, jac, f, u, precision=1e-8, maxsteps=200):
+    def cg_solve(self, jac, f, u, precision=1e-8, maxsteps=200, conjugate=False):
         """CGSolver::Mult on parallel vectors: f DISTRIBUTED in, u CUMULATED out"""
         f._dev_read()
         u._dev_write()
         cap = min(maxsteps, 1 << 20) + 2
         hist = np.zeros(cap)
         steps, nh = C.c_int(), C.c_int()
+        ip = _capi.IP_REAL if not self.is_complex else (_capi.IP_COMPLEX_CONJ if conjugate else _capi.IP_COMPLEX)
         check(_capi.lib().ngsb_parmat_cg_solve(self.handle, jac.handle if jac is not None else None, f.handle, u.handle, precision,
-                                               maxsteps, C.byref(steps), la._np_ptr(hist), cap, C.byref(nh)))
+                                               maxsteps, ip, C.byref(steps), la._np_ptr(hist), cap, C.byref(nh)))
+        return _Result(steps.value, hist[:min(nh.value, cap)].copy())
+
+    def gmres_solve(self, jac, f, x, precision=1e-8, maxsteps=200):
+        """GMRESSolver::Mult on parallel vectors: f DISTRIBUTED in, x CUMULATED out"""
+        f._dev_read()
+        x._dev_write()
+        cap = maxsteps + 2
+        hist = np.zeros(cap)
+        steps, nh = C.c_int(), C.c_int()
+        check(_capi.lib().ngsb_parmat_gmres_solve(self.handle, jac.handle if jac is not None else None, f.handle, x.handle, precision,
+                                                  maxsteps, C.byref(steps), la._np_ptr(hist), cap, C.byref(nh)))
         return _Result(steps.value, hist[:min(nh.value, cap)].copy())
 
 
