@@ -76,13 +76,13 @@ def _worker(rank, world, port, cfg, out):
     dist.destroy_process_group()
 
 
-def _run(cfg):
+def _run(cfg, world=2):
     import torch.multiprocessing as mp
     import ngsolve_b200.la as la
     from ngsolve_b200 import workloads as W
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(_worker, args=(2, _free_port(), cfg, out), nprocs=2, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), cfg, out), nprocs=world, join=True)
     glob = W.FemBox(tuple(cfg.get("G", G_DEFAULT)), **_box_kw(cfg))
     A, f = glob.device_system()
     jac = A.CreateSmoother(glob.freedofs())
@@ -93,7 +93,7 @@ def _run(cfg):
     u = (inv * f).Evaluate().NumPy().reshape(-1)
     es = glob.entrysize
     cplx = cfg["kind"] == COMPLEX
-    for r in range(2):
+    for r in range(world):
         steps, gi, ur, hist, cnt, n_cum, n_mix, n_glob = out[r]
         assert abs(steps - inv.GetSteps()) <= 2, (steps, inv.GetSteps())
         k = min(len(hist), len(inv.history), 25)
@@ -129,6 +129,19 @@ def test_two_ranks_on_one_gpu_peer_memory(case):
     context switch -> keep the GMRES systems small: step j has j+2 reductions)"""
     extra = dict(G=(6, 5, 8)) if case["solver"] == "gmres" else {}
     _run(dict(case, devices="same", p2p=1, **extra))
+
+
+def test_four_ranks_on_one_gpu_peer_memory():
+    """4 slabs: the middle ranks have two neighbours each, the scalar all-reduce has 4 contributions (the layout of the
+    4- and 8-GPU bench runs), still without NCCL"""
+    _run(dict(order=2, kind=REAL, solver="cg", devices="same", p2p=1, G=(4, 4, 8)), world=4)
+
+
+@pytest.mark.parametrize("world", [4, 8])
+def test_many_gpu_solve_equals_one_gpu_solve(world):
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    _run(dict(order=3, kind=REAL, solver="cg", devices="two", p2p=1, G=(8, 8, 16)), world=world)
 
 
 @pytest.mark.parametrize("p2p", [1, 0], ids=["peer-memory", "nccl"])
