@@ -56,6 +56,7 @@ typedef struct ngsb_vec ngsb_vec;
 typedef struct ngsb_scalar ngsb_scalar;
 typedef struct ngsb_csr ngsb_csr;
 typedef struct ngsb_jacobi ngsb_jacobi;
+typedef struct ngsb_blockjacobi ngsb_blockjacobi;
 typedef struct ngsb_comm ngsb_comm;
 typedef struct ngsb_parmat ngsb_parmat;
 
@@ -170,6 +171,43 @@ int ngsb_jacobi_destroy(ngsb_jacobi *J);
 int ngsb_jacobi_download(const ngsb_jacobi *J, void *invdiag);
 int ngsb_jacobi_multadd(const ngsb_jacobi *J, const double s[2], const ngsb_vec *x, ngsb_vec *y);
 int ngsb_jacobi_mult(const ngsb_jacobi *J, const ngsb_vec *x, ngsb_vec *y);
+
+/* ---- transposes, symmetric storage, several right-hand sides ----
+ * ngsb_csr_transpose: SparseMatrixTM::CreateTranspose(sorted=true) (linalg/sparsematrix.cpp; Python
+ * `mat.CreateTranspose()`, linalg/python_linalg.cpp:172): a new device matrix, rows ascending.
+ * ngsb_csr_multtransadd: SparseMatrix::MultTransAdd, y += s * A^T x (linalg/sparsematrix_impl.hpp:
+ * 344-352; the reference scatters serially).  A^T is built on first use and cached in the handle;
+ * x has Height() entries, y Width().
+ * ngsb_csr_create_symmetric: a SparseMatrixSymmetric<TM> handed over as its stored lower triangle
+ * (columns <= row, ascending; linalg/sparsematrix.hpp:760-835).  The full matrix is formed on the
+ * device; Mult/MultAdd then equal SparseMatrixSymmetric::MultAdd (sparsematrix_impl.hpp:967-983).
+ * ngsb_csr_multadd_multi: SparseMatrix<double>::MultAdd(FlatVector alpha, MultiVector x, MultiVector y)
+ * (linalg/sparsematrix.cpp:2274-2351): y[k] += alpha[k] * A * x[k]; real matrices sweep four vectors
+ * per pass over the matrix. */
+int ngsb_csr_transpose(const ngsb_csr *A, ngsb_csr **out);
+int ngsb_csr_multtransadd(const ngsb_csr *A, const double s[2], const ngsb_vec *x, ngsb_vec *y);
+int ngsb_csr_create_symmetric(ngsb_ctx *ctx, size_t n, size_t nnz, const uint64_t *rowptr, const int32_t *col,
+                              const void *val, int kind, ngsb_csr **out);
+int ngsb_csr_multadd_multi(const ngsb_csr *A, size_t nvec, const double *alpha, const ngsb_vec *const *x,
+                           ngsb_vec *const *y);
+
+/* ---- block-Jacobi: replaces DevBlockJacobiMatrix (ngscuda/dev_blockjacobi.cpp:21-140) and the
+ * BlockJacobiPrecond<double> constructor (linalg/blockjacobi.cpp:380-500; reached from Python by
+ * mat.CreateBlockSmoother(blocks), linalg/python_linalg.cpp).  Block b owns the dofs
+ * dofs[first[b] .. first[b+1]) (the reference's Table<int>, blocks may overlap); its matrix
+ * A(block, block) is inverted on the device with the reference's T_CalcInverse
+ * (basiclinalg/calcinverse.cpp:26-107).  TM = double only, like the reference device class.
+ * MultAdd: y(block) += s * inv_b * x(block) summed over the blocks in ascending block order
+ * (linalg/blockjacobi.cpp:594-634); transpose != 0: MultTransAdd (:637-681). */
+int ngsb_blockjacobi_create(const ngsb_csr *A, size_t nblocks, const uint64_t *first, const int32_t *dofs,
+                            ngsb_blockjacobi **out);
+int ngsb_blockjacobi_destroy(ngsb_blockjacobi *J);
+int ngsb_blockjacobi_info(const ngsb_blockjacobi *J, size_t *n, size_t *nblocks, size_t *maxbs, size_t *total,
+                          size_t *matrix_entries);
+/* the inverse blocks back to back, each row-major (BlockJacobiPrecond::GetInverses) */
+int ngsb_blockjacobi_download(const ngsb_blockjacobi *J, double *inverses);
+int ngsb_blockjacobi_multadd(const ngsb_blockjacobi *J, double s, const ngsb_vec *x, ngsb_vec *y, int transpose);
+int ngsb_blockjacobi_mult(const ngsb_blockjacobi *J, const ngsb_vec *x, ngsb_vec *y, int transpose);
 
 /* ---- Krylov solvers ----------------------------------------------------------------------
  * ngsb_cg_solve: CGSolver<IPTYPE>::Mult, linalg/cg.cpp:503-633 (same recurrences, same

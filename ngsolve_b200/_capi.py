@@ -72,6 +72,16 @@ PROTOTYPES = {
     "ngsb_jacobi_download": [_vp, _vp],
     "ngsb_jacobi_multadd": [_vp, C.POINTER(_d), _vp, _vp],
     "ngsb_jacobi_mult": [_vp, _vp, _vp],
+    "ngsb_csr_transpose": [_vp, _pvp],
+    "ngsb_csr_multtransadd": [_vp, C.POINTER(_d), _vp, _vp],
+    "ngsb_csr_create_symmetric": [_vp, _sz, _sz, _vp, _vp, _vp, _i, _pvp],
+    "ngsb_csr_multadd_multi": [_vp, _sz, _vp, _vp, _vp],
+    "ngsb_blockjacobi_create": [_vp, _sz, _vp, _vp, _pvp],
+    "ngsb_blockjacobi_destroy": [_vp],
+    "ngsb_blockjacobi_info": [_vp, C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_sz)],
+    "ngsb_blockjacobi_download": [_vp, _vp],
+    "ngsb_blockjacobi_multadd": [_vp, _d, _vp, _vp, _i],
+    "ngsb_blockjacobi_mult": [_vp, _vp, _vp, _i],
     "ngsb_cg_solve": [_vp, _vp, _vp, _vp, _d, _i, _i, _i, C.POINTER(_i), _vp, _i, C.POINTER(_i)],
     "ngsb_cg_solve_host": [_vp, _vp, _vp, _vp, _d, _i, _i, C.POINTER(_i), _vp, _i, C.POINTER(_i)],
     "ngsb_gmres_solve": [_vp, _vp, _vp, _vp, _d, _i, _i, C.POINTER(_i), _vp, _i, C.POINTER(_i)],

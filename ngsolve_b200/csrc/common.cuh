@@ -9,6 +9,7 @@
 #include <string>
 #include <vector>
 #include <memory>
+#include <algorithm>
 
 #include "../../include/ngsb200.h"
 

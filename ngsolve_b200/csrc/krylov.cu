@@ -668,26 +668,53 @@ __global__ void __launch_bounds__(256) gmres_mgs_kernel(double *__restrict__ w, 
     uint64_t lo = (uint64_t)blockIdx.x * per;
     uint64_t hi_ = lo + per < N ? lo + per : N;
     double ar = 0.0, ai = 0.0;
-    for (uint64_t i = lo + threadIdx.x; i < hi_; i += blockDim.x) {
-        if (CPLX) {
-            double2 wv = reinterpret_cast<double2 *>(w)[i];
+    if (CPLX) {
+        // two entries per thread and step: six independent 16-byte loads in flight (the loop is pure streaming)
+        double2 *w2 = reinterpret_cast<double2 *>(w);
+        const double2 *p2 = reinterpret_cast<const double2 *>(vprev);
+        const double2 *q2 = reinterpret_cast<const double2 *>(vnext);
+        double br = 0.0, bi = 0.0;
+        for (uint64_t i = lo + threadIdx.x; i < hi_; i += 2 * (uint64_t)blockDim.x) {
+            const uint64_t k = i + blockDim.x;
+            const bool two = k < hi_;
+            double2 wa = w2[i], wb = two ? w2[k] : make_double2(0.0, 0.0);
             if (vprev) {
-                double2 p = reinterpret_cast<const double2 *>(vprev)[i];
-                wv.x -= hr * p.x - hi * p.y;
-                wv.y -= hr * p.y + hi * p.x;
-                reinterpret_cast<double2 *>(w)[i] = wv;
+                const double2 pa = p2[i], pb = two ? p2[k] : make_double2(0.0, 0.0);
+                wa.x -= hr * pa.x - hi * pa.y;
+                wa.y -= hr * pa.y + hi * pa.x;
+                wb.x -= hr * pb.x - hi * pb.y;
+                wb.y -= hr * pb.y + hi * pb.x;
+                w2[i] = wa;
+                if (two) w2[k] = wb;
             }
-            if (master && !master[i]) continue;      // masked inner product: master dofs only
-            double2 q = selfdot ? wv : reinterpret_cast<const double2 *>(vnext)[i];
-            ar += q.x * wv.x - q.y * wv.y;
-            ai += q.x * wv.y + q.y * wv.x;
-        } else {
-            double wv = w[i];
-            if (vprev) { wv -= hr * vprev[i]; w[i] = wv; }
-            if (master && !master[i / mask_div]) continue;
-            double q = selfdot ? wv : vnext[i];
-            ar = fma(q, wv, ar);
+            if (!master || master[i]) {      // masked inner product: master dofs only
+                const double2 q = selfdot ? wa : q2[i];
+                ar += q.x * wa.x - q.y * wa.y;
+                ai += q.x * wa.y + q.y * wa.x;
+            }
+            if (two && (!master || master[k])) {
+                const double2 q = selfdot ? wb : q2[k];
+                br += q.x * wb.x - q.y * wb.y;
+                bi += q.x * wb.y + q.y * wb.x;
+            }
         }
+        ar += br;
+        ai += bi;
+    } else {
+        double br = 0.0;
+        for (uint64_t i = lo + threadIdx.x; i < hi_; i += 2 * (uint64_t)blockDim.x) {
+            const uint64_t k = i + blockDim.x;
+            const bool two = k < hi_;
+            double wa = w[i], wb = two ? w[k] : 0.0;
+            if (vprev) {
+                wa -= hr * vprev[i];
+                w[i] = wa;
+                if (two) { wb -= hr * vprev[k]; w[k] = wb; }
+            }
+            if (!master || master[i / mask_div]) ar = fma(selfdot ? wa : vnext[i], wa, ar);
+            if (two && (!master || master[k / mask_div])) br = fma(selfdot ? wb : vnext[k], wb, br);
+        }
+        ar += br;
     }
     double2 total;
     if (grid_finish(ar, ai, partials, counter, &total)) {
@@ -795,15 +822,15 @@ int ngsb::gmres_solve_impl(const ngsb_csr *A, const ngsb_jacobi *C, const ngsb_v
     GmresState *d_st = nullptr;
     double2 *d_h = nullptr, *d_gam = nullptr, *d_ci = nullptr, *d_si = nullptr, *d_y = nullptr;
     double *d_hist = nullptr, *d_scale = nullptr;
-    std::vector<double *> vi;
-    double *av = nullptr, *hv = nullptr, *w = nullptr, *r = nullptr;
+    std::vector<double *> vi, chunks;     // basis vectors live in chunks of up to 8 (one cudaMalloc = one device sync)
+    double *av = nullptr, *w = nullptr, *r = nullptr;
     int rc = NGSB_OK;
     GmresState hst;
     auto cleanup = [&]() {
         cudaStreamSynchronize(ctx->stream);
         cudaFree(d_st); cudaFree(d_h); cudaFree(d_gam); cudaFree(d_ci); cudaFree(d_si); cudaFree(d_y); cudaFree(d_hist); cudaFree(d_scale);
-        for (auto p : vi) cudaFree(p);
-        cudaFree(av); cudaFree(hv); cudaFree(w); cudaFree(r);
+        for (auto p : chunks) cudaFree(p);
+        cudaFree(av); cudaFree(w); cudaFree(r);
     };
 #define GM_CUDA(call)                                                                                      \
     do {                                                                                                   \
@@ -831,9 +858,23 @@ int ngsb::gmres_solve_impl(const ngsb_csr *A, const ngsb_jacobi *C, const ngsb_v
     GM_CUDA(cudaMalloc(&d_scale, sizeof(double) * 2));
     const size_t vbytes = (nscal ? nscal : 2) * sizeof(double);
     GM_CUDA(cudaMalloc(&av, vbytes));
-    GM_CUDA(cudaMalloc(&hv, vbytes));
     GM_CUDA(cudaMalloc(&w, vbytes));
     GM_CUDA(cudaMalloc(&r, vbytes));
+    const size_t vstride = (vbytes + 255) & ~(size_t)255;
+    const size_t per_chunk = std::max<size_t>(1, std::min<size_t>(8, ((size_t)4 << 30) / vstride));
+    size_t chunk_used = per_chunk;
+    auto new_basis_vector = [&](double **out) -> cudaError_t {
+        if (chunk_used == per_chunk) {
+            double *c = nullptr;
+            const size_t want = std::min<size_t>(per_chunk, (size_t)ms + 1 > vi.size() ? (size_t)ms + 1 - vi.size() : 1);
+            cudaError_t e = cudaMalloc(&c, vstride * std::max<size_t>(1, want));
+            if (e != cudaSuccess) return e;
+            chunks.push_back(c);
+            chunk_used = 0;
+        }
+        *out = (double *)((char *)chunks.back() + vstride * chunk_used++);
+        return cudaSuccess;
+    };
 
     memset(&hst, 0, sizeof(hst));
     hst.prec = prec;
@@ -873,8 +914,8 @@ int ngsb::gmres_solve_impl(const ngsb_csr *A, const ngsb_jacobi *C, const ngsb_v
     }
     GM_TRY(cumulate(r));
     if (C) {
-        GM_TRY(jacobi_apply(C, 1.0, 0.0, r, hv, false));
-        GM_CUDA(cudaMemcpyAsync(r, hv, nscal * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+        GM_TRY(jacobi_apply(C, 1.0, 0.0, r, w, false));
+        GM_CUDA(cudaMemcpyAsync(r, w, nscal * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
     }
     // norm = r.L2Norm(); v = 1/sqrt(<r,r>) r
     GM_TRY(launch_dot_masked(ctx, r, r, nscal, 3, d_tmp, master, cplx ? 2 : mask_div));
@@ -889,7 +930,7 @@ int ngsb::gmres_solve_impl(const ngsb_csr *A, const ngsb_jacobi *C, const ngsb_v
     // v_0
     {
         double *v0 = nullptr;
-        GM_CUDA(cudaMalloc(&v0, vbytes));
+        GM_CUDA(new_basis_vector(&v0));
         vi.push_back(v0);
         GM_TRY(launch_axpby_dev(ctx, v0, r, N, d_st_scale, cplx, false, false));
     }
@@ -902,11 +943,10 @@ int ngsb::gmres_solve_impl(const ngsb_csr *A, const ngsb_jacobi *C, const ngsb_v
     while (!done) {
         j = hst.j;   // current column
         double *v = vi[j];
-        GM_TRY(spmv(v, av));
-        GM_TRY(cumulate(av));
-        const double *avp = av;
-        if (C) { GM_TRY(jacobi_apply(C, 1.0, 0.0, av, hv, false)); avp = hv; }
-        GM_CUDA(cudaMemcpyAsync(w, avp, nscal * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+        // w = C A v: the product lands in `av` and the preconditioner writes w (no preconditioner: straight into w)
+        GM_TRY(spmv(v, C ? av : w));
+        GM_TRY(cumulate(C ? av : w));
+        if (C) GM_TRY(jacobi_apply(C, 1.0, 0.0, av, w, false));
         // MGS: h(i,j) = <v_i, w>; w -= h(i,j) v_i  (projection i fused with inner product i+1)
         for (int i = 0; i <= j; i++) {
             GM_TRY(mgs(i > 0 ? vi[i - 1] : nullptr, i > 0 ? d_h + (size_t)(i - 1) * ms + j : nullptr, vi[i], 0));
@@ -920,7 +960,7 @@ int ngsb::gmres_solve_impl(const ngsb_csr *A, const ngsb_jacobi *C, const ngsb_v
         }
         // v_{j+1} = 1/h(j+1,j) * w  (always formed, like the reference)
         double *vn = nullptr;
-        GM_CUDA(cudaMalloc(&vn, vbytes));
+        GM_CUDA(new_basis_vector(&vn));
         vi.push_back(vn);
         GM_TRY(launch_axpby_dev(ctx, vn, w, N, d_st_scale, cplx, false, false));
         GM_CUDA(cudaMemcpyAsync(&hst, d_st, sizeof(hst), cudaMemcpyDeviceToHost, ctx->stream));

@@ -285,6 +285,63 @@ __global__ void __launch_bounds__(256, MINB) sell_spmv_kernel(const SellParams p
     }
 }
 
+// SparseMatrix<double>::MultAdd(FlatVector alpha, MultiVector x, MultiVector y) (linalg/sparsematrix.cpp:2274-2351): four
+// right-hand sides per sweep over the matrix; values and columns are read once, every row keeps four accumulators that
+// are summed in storage order exactly like the single-vector kernel (bit-identical results per vector).
+struct SellMultiParams {
+    const uint64_t *slice_off;
+    const uint32_t *slice_src;
+    const uint32_t *row_of;
+    const int32_t *scol;
+    const double *sval;
+    uint32_t nslices;
+    const double *x[4];
+    double *y[4];
+    double alpha[4];
+};
+
+__global__ void __launch_bounds__(256, 4) sell_spmm4_kernel(const SellMultiParams p)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const double *__restrict__ xa = p.x[0], *__restrict__ xb = p.x[1], *__restrict__ xc = p.x[2], *__restrict__ xd = p.x[3];
+    for (uint64_t s = (uint64_t)blockIdx.x * 8 + wid; s < p.nslices; s += (uint64_t)gridDim.x * 8) {
+        const uint64_t off = p.slice_off[s];
+        const uint32_t width = (uint32_t)((p.slice_off[s + 1] - off) >> 5);
+        const uint32_t row = p.row_of[(uint32_t)((uint64_t)p.slice_src[s] * 32 + lane)];
+        const double2 *v2 = reinterpret_cast<const double2 *>(p.sval + off) + lane;
+        const int2 *c2 = reinterpret_cast<const int2 *>(p.scol + off) + lane;
+        const uint32_t np = width >> 1;
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        uint32_t q = 0;
+        for (; q + 2 <= np; q += 2) {
+            const double2 va = ldg_stream_d2(v2 + (q + 0) * 32), vb = ldg_stream_d2(v2 + (q + 1) * 32);
+            const int2 ca = ldg_stream_i2(c2 + (q + 0) * 32), cb = ldg_stream_i2(c2 + (q + 1) * 32);
+            const double a0 = __ldg(xa + ca.x), a1 = __ldg(xa + ca.y), a2 = __ldg(xa + cb.x), a3 = __ldg(xa + cb.y);
+            const double b0 = __ldg(xb + ca.x), b1 = __ldg(xb + ca.y), b2 = __ldg(xb + cb.x), b3 = __ldg(xb + cb.y);
+            const double c0 = __ldg(xc + ca.x), c1 = __ldg(xc + ca.y), c2_ = __ldg(xc + cb.x), c3 = __ldg(xc + cb.y);
+            const double d0 = __ldg(xd + ca.x), d1 = __ldg(xd + ca.y), d2 = __ldg(xd + cb.x), d3 = __ldg(xd + cb.y);
+            s0 = fma(va.x, a0, s0); s0 = fma(va.y, a1, s0); s0 = fma(vb.x, a2, s0); s0 = fma(vb.y, a3, s0);
+            s1 = fma(va.x, b0, s1); s1 = fma(va.y, b1, s1); s1 = fma(vb.x, b2, s1); s1 = fma(vb.y, b3, s1);
+            s2 = fma(va.x, c0, s2); s2 = fma(va.y, c1, s2); s2 = fma(vb.x, c2_, s2); s2 = fma(vb.y, c3, s2);
+            s3 = fma(va.x, d0, s3); s3 = fma(va.y, d1, s3); s3 = fma(vb.x, d2, s3); s3 = fma(vb.y, d3, s3);
+        }
+        for (; q < np; q++) {
+            const double2 va = ldg_stream_d2(v2 + q * 32);
+            const int2 ca = ldg_stream_i2(c2 + q * 32);
+            s0 = fma(va.x, __ldg(xa + ca.x), s0); s0 = fma(va.y, __ldg(xa + ca.y), s0);
+            s1 = fma(va.x, __ldg(xb + ca.x), s1); s1 = fma(va.y, __ldg(xb + ca.y), s1);
+            s2 = fma(va.x, __ldg(xc + ca.x), s2); s2 = fma(va.y, __ldg(xc + ca.y), s2);
+            s3 = fma(va.x, __ldg(xd + ca.x), s3); s3 = fma(va.y, __ldg(xd + ca.y), s3);
+        }
+        if (row != 0xffffffffu) {
+            p.y[0][row] = p.alpha[0] * s0 + p.y[0][row];
+            p.y[1][row] = p.alpha[1] * s1 + p.y[1][row];
+            p.y[2][row] = p.alpha[2] * s2 + p.y[2][row];
+            p.y[3][row] = p.alpha[3] * s3 + p.y[3][row];
+        }
+    }
+}
+
 // overflow part of long rows: one CTA per row, raw sum of val*x over the entries behind `cap`
 template <int KIND>
 __global__ void __launch_bounds__(256) sell_overflow_kernel(const uint64_t *__restrict__ optr, const int32_t *__restrict__ ocol,
@@ -658,6 +715,25 @@ int sell_launch(const SpmvArgs &a)
     if (grid > (uint64_t)MAX_PARTIALS - 8) grid = MAX_PARTIALS - 8;
     SpanGuard g(ctx, KC_SPMV);
     kern<<<(unsigned)grid, 256, 0, ctx->stream>>>(p);
+    NGSB_CUDA(cudaGetLastError());
+    return NGSB_OK;
+}
+
+// four real right-hand sides in one sweep; the caller guarantees kind == REAL and no overflow rows
+int sell_launch_multi4(const ngsb_csr *A, const double *const x[4], double *const y[4], const double alpha[4])
+{
+    ngsb_ctx *ctx = A->ctx;
+    SellMultiParams p;
+    memset(&p, 0, sizeof(p));
+    p.slice_off = A->d_slice_off; p.slice_src = A->d_slice_src; p.row_of = A->d_row_of; p.scol = A->d_scol; p.sval = A->d_sval;
+    p.nslices = A->nslices;
+    for (int k = 0; k < 4; k++) { p.x[k] = x[k]; p.y[k] = y[k]; p.alpha[k] = alpha[k]; }
+    uint64_t grid = (uint64_t)ctx->sm_count * 4;
+    const uint64_t need = ((uint64_t)A->nslices + 7) / 8;
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    SpanGuard g(ctx, KC_SPMV);
+    sell_spmm4_kernel<<<(unsigned)grid, 256, 0, ctx->stream>>>(p);
     NGSB_CUDA(cudaGetLastError());
     return NGSB_OK;
 }

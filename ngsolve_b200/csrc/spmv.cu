@@ -805,6 +805,7 @@ extern "C" int ngsb_csr_destroy(ngsb_csr *A)
     cudaFree(A->d_rowoff);
     cudaFree(A->d_longrows);
     sell_free(A);
+    if (A->transposed) ngsb_csr_destroy(A->transposed);
     delete A;
     return NGSB_OK;
 }
@@ -852,6 +853,40 @@ extern "C" int ngsb_csr_mult(const ngsb_csr *A, const ngsb_vec *x, ngsb_vec *y)
     memset(&a, 0, sizeof(a));
     a.A = A; a.x = x->d; a.y = y->d; a.sr = 1.0; a.si = 0.0; a.accumulate = false; a.epi = EPI_NONE;
     return spmv_launch(a);
+}
+
+// SparseMatrix<double>::MultAdd(alpha, MultiVector x, MultiVector y), linalg/sparsematrix.cpp:2274-2351: groups of four
+// vectors share one sweep over the matrix, the remainder goes vector by vector (the reference's own grouping)
+extern "C" int ngsb_csr_multadd_multi(const ngsb_csr *A, size_t nvec, const double *alpha, const ngsb_vec *const *x, ngsb_vec *const *y)
+{
+    NGSB_REQUIRE(A && (nvec == 0 || (alpha && x && y)), "SparseMatrix::MultAdd(MultiVector): NULL argument");
+    for (size_t k = 0; k < nvec; k++) {
+        NGSB_TRY(check_mult_args(A, x[k], y[k], "SparseMatrix::MultAdd(MultiVector)"));
+        for (size_t l = 0; l < nvec; l++) {
+            const double *xb = x[l]->d, *xe = x[l]->d + x[l]->nscal, *yb = y[k]->d, *ye = y[k]->d + y[k]->nscal;
+            NGSB_REQUIRE(xe <= yb || ye <= xb || x[l]->nscal == 0, "SparseMatrix::MultAdd(MultiVector): y[%zu] overlaps x[%zu]", k, l);
+            if (l != k) {
+                const double *zb = y[l]->d, *ze = y[l]->d + y[l]->nscal;
+                NGSB_REQUIRE(ze <= yb || ye <= zb || y[l]->nscal == 0, "SparseMatrix::MultAdd(MultiVector): y[%zu] overlaps y[%zu]", k, l);
+            }
+        }
+    }
+    NGSB_CUDA(cudaSetDevice(A->ctx->device));
+    size_t k = 0;
+    const bool grouped = A->kind == NGSB_REAL && A->novf == 0 && A->ctx->spmv_algo == 0;
+    if (grouped)
+        for (; k + 4 <= nvec; k += 4) {
+            const double *xs[4] = {x[k]->d, x[k + 1]->d, x[k + 2]->d, x[k + 3]->d};
+            double *ys[4] = {y[k]->d, y[k + 1]->d, y[k + 2]->d, y[k + 3]->d};
+            NGSB_TRY(sell_launch_multi4(A, xs, ys, alpha + k));
+        }
+    for (; k < nvec; k++) {
+        SpmvArgs a;
+        memset(&a, 0, sizeof(a));
+        a.A = A; a.x = x[k]->d; a.y = y[k]->d; a.sr = alpha[k]; a.si = 0.0; a.accumulate = true; a.epi = EPI_NONE;
+        NGSB_TRY(spmv_launch(a));
+    }
+    return NGSB_OK;
 }
 
 extern "C" int ngsb_csr_download(const ngsb_csr *A, uint64_t *rowptr, int32_t *col, void *val)

@@ -52,6 +52,7 @@ struct ngsb_csr {
     double *d_ovf_sum = nullptr;
     double mean_row = 0.0;
     size_t max_row = 0;
+    ngsb_csr *transposed = nullptr;    // A^T, built by the first MultTransAdd (transpose.cu), owned
 };
 
 namespace ngsb {
@@ -79,5 +80,7 @@ int spmv_launch(const SpmvArgs &a);
 int sell_build(ngsb_csr *A, const uint64_t *h_rowptr);
 void sell_free(ngsb_csr *A);
 int sell_launch(const SpmvArgs &a);
+// y_k += alpha_k * A * x_k for four real vectors in one sweep over the matrix (MultiVector MultAdd)
+int sell_launch_multi4(const ngsb_csr *A, const double *const x[4], double *const y[4], const double alpha[4]);
 
 } // namespace ngsb

@@ -572,6 +572,7 @@ extern "C" int ngsb_ctx_kernel_time(ngsb_ctx *ctx, const char *klass, double *ms
     if (!strcmp(klass, "spmv")) want = KC_SPMV;
     else if (!strcmp(klass, "cgupdate")) want = KC_CGUPDATE;
     else if (!strcmp(klass, "vec")) want = KC_VEC;
+    else if (!strcmp(klass, "other")) want = KC_OTHER;
     else if (!strcmp(klass, "all")) want = -1;
     else { set_error("ngsb_ctx_kernel_time: unknown class '%s'", klass); return NGSB_ERR_INVALID; }
     NGSB_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -542,6 +542,8 @@ class BaseMatrix:
         return self
 
     def __mul__(self, x):
+        if isinstance(x, MultiVector):
+            return _MultiVectorExpr(self, x)
         if isinstance(x, BaseVector):
             return _Expr([(1.0, self, x)])
         if isinstance(x, _Expr):
@@ -553,6 +555,37 @@ class BaseMatrix:
 
     def __rmul__(self, s):
         return _ScaledMatrix(s, self)       # VScaleMatrix, linalg/basematrix.hpp
+
+    # composite operators (SumMatrix / ProductMatrix / Transpose, linalg/basematrix.hpp:560-860); like the reference they
+    # hold their operands and recurse in CreateDeviceMatrix()
+    def __add__(self, o):
+        return SumMatrix(self, o, 1.0, 1.0) if isinstance(o, BaseMatrix) else NotImplemented
+
+    def __sub__(self, o):
+        return SumMatrix(self, o, 1.0, -1.0) if isinstance(o, BaseMatrix) else NotImplemented
+
+    def __neg__(self):
+        return _ScaledMatrix(-1.0, self)
+
+    def __matmul__(self, o):
+        return ProductMatrix(self, o) if isinstance(o, BaseMatrix) else NotImplemented
+
+    @property
+    def T(self):
+        return TransposeMatrix(self)
+
+    def MultTrans(self, s, x, y):
+        # Python binding: y = 0; MultTransAdd(1.0, x, y) -- `s` is ignored (linalg/python_linalg.cpp:1074)
+        y.SetScalar(0.0)
+        self.MultTransAdd(1.0, x, y)
+
+    def MultTransAdd(self, s, x, y):
+        raise NgsbError("%s: MultTransAdd is not implemented" % type(self).__name__)
+
+    def MultScale(self, s, x, y):
+        self.Mult(x, y)
+        if s != 1.0:
+            y.Scale(s)
 
     def _check(self, x, y, who):
         if x.size != self.Width():
@@ -578,6 +611,140 @@ class _ScaledMatrix(BaseMatrix):
 
     def MultAdd(self, s, x, y):
         self.m.MultAdd(s * self.s, x, y)
+
+    def MultTransAdd(self, s, x, y):
+        self.m.MultTransAdd(s * self.s, x, y)
+
+    def CreateDeviceMatrix(self):
+        return _ScaledMatrix(self.s, self.m.CreateDeviceMatrix())
+
+
+class SumMatrix(BaseMatrix):
+    """a*A + b*B (SumMatrix, linalg/basematrix.hpp:560-600)"""
+
+    def __init__(self, A, B, a=1.0, b=1.0):
+        if A.Height() != B.Height() or A.Width() != B.Width():
+            raise NgsbError("SumMatrix: sizes don't match: %d x %d and %d x %d" % (A.Height(), A.Width(), B.Height(), B.Width()))
+        self.A, self.B, self.a, self.b = A, B, a, b
+        self.is_complex, self.entrysize, self.ctx = A.is_complex or B.is_complex, A.entrysize, A.ctx or B.ctx
+
+    def Height(self):
+        return self.A.Height()
+
+    def Width(self):
+        return self.A.Width()
+
+    def Mult(self, x, y):
+        # SumMatrix::Mult: a == 1 ? A.Mult : (y = 0; A.MultAdd(a)); then B.MultAdd(b)
+        if self.a == 1:
+            self.A.Mult(x, y)
+        else:
+            y.SetScalar(0.0)
+            self.A.MultAdd(self.a, x, y)
+        self.B.MultAdd(self.b, x, y)
+
+    def MultAdd(self, s, x, y):
+        self.A.MultAdd(s * self.a, x, y)
+        self.B.MultAdd(s * self.b, x, y)
+
+    def MultTransAdd(self, s, x, y):
+        self.A.MultTransAdd(s * self.a, x, y)
+        self.B.MultTransAdd(s * self.b, x, y)
+
+    def CreateDeviceMatrix(self):
+        return SumMatrix(self.A.CreateDeviceMatrix(), self.B.CreateDeviceMatrix(), self.a, self.b)
+
+
+class ProductMatrix(BaseMatrix):
+    """A @ B (ProductMatrix, linalg/basematrix.hpp:720-760): y = A (B x) through a temporary of B's column type"""
+
+    def __init__(self, A, B):
+        if A.Width() != B.Height():
+            raise NgsbError("ProductMatrix: width of A = %d != height of B = %d" % (A.Width(), B.Height()))
+        self.A, self.B = A, B
+        self.is_complex, self.entrysize, self.ctx = A.is_complex or B.is_complex, A.entrysize, A.ctx or B.ctx
+        self._tmp = None
+
+    def Height(self):
+        return self.A.Height()
+
+    def Width(self):
+        return self.B.Width()
+
+    def CreateRowVector(self):
+        return self.B.CreateRowVector()
+
+    def CreateColVector(self):
+        return self.A.CreateColVector()
+
+    def _t(self):
+        if self._tmp is None:
+            self._tmp = self.B.CreateColVector()
+        return self._tmp
+
+    def Mult(self, x, y):
+        self.B.Mult(x, self._t())
+        self.A.Mult(self._t(), y)
+
+    def MultAdd(self, s, x, y):
+        self.B.Mult(x, self._t())
+        self.A.MultAdd(s, self._t(), y)
+
+    def MultTransAdd(self, s, x, y):
+        t = self.A.CreateRowVector()
+        self.A.MultTrans(1.0, x, t)
+        self.B.MultTransAdd(s, t, y)
+
+    def CreateDeviceMatrix(self):
+        return ProductMatrix(self.A.CreateDeviceMatrix(), self.B.CreateDeviceMatrix())
+
+
+class TransposeMatrix(BaseMatrix):
+    """A.T (Transpose, linalg/basematrix.hpp:800-860): Mult = MultTrans of the operand"""
+
+    def __init__(self, A):
+        self.A = A
+        self.is_complex, self.entrysize, self.ctx = A.is_complex, A.entrysize, A.ctx
+
+    def Height(self):
+        return self.A.Width()
+
+    def Width(self):
+        return self.A.Height()
+
+    def CreateRowVector(self):
+        return self.A.CreateColVector()
+
+    def CreateColVector(self):
+        return self.A.CreateRowVector()
+
+    def Mult(self, x, y):
+        self.A.MultTrans(1.0, x, y)
+
+    def MultAdd(self, s, x, y):
+        self.A.MultTransAdd(s, x, y)
+
+    def MultTransAdd(self, s, x, y):
+        self.A.MultAdd(s, x, y)
+
+    def CreateDeviceMatrix(self):
+        return TransposeMatrix(self.A.CreateDeviceMatrix())
+
+
+class IdentityMatrix(BaseMatrix):
+    """IdentityMatrix(n) (linalg/special_matrix.hpp): y = x"""
+
+    def __init__(self, size, complex=False, ctx=None):
+        self.height = self.width = int(size)
+        self.is_complex, self.ctx = complex, ctx or default_context()
+
+    def Mult(self, x, y):
+        y.Set(1.0, x)
+
+    def MultAdd(self, s, x, y):
+        y.Add(s, x)
+
+    MultTransAdd = MultAdd
 
 
 class SparseMatrix(BaseMatrix):
@@ -626,6 +793,10 @@ class SparseMatrix(BaseMatrix):
     def CreateSmoother(self, freedofs=None):
         return JacobiPrecond(self, freedofs)
 
+    def CreateBlockSmoother(self, blocks):
+        """mat.CreateBlockSmoother(blocks) (linalg/python_linalg.cpp): blocks = list of dof lists (may overlap)"""
+        return BlockJacobiPrecond(self, blocks)
+
     def Mult(self, x, y):
         raise NgsbError("SparseMatrix on the host: this package has no CPU path, use CreateDeviceMatrix()")
 
@@ -668,6 +839,35 @@ class DevSparseMatrix(BaseMatrix):
     def CreateSmoother(self, freedofs=None):
         return DevJacobiMatrix(self, freedofs)
 
+    def CreateBlockSmoother(self, blocks):
+        return DevBlockJacobiMatrix(self, blocks)
+
+    def MultTransAdd(self, s, x, y):
+        """SparseMatrix::MultTransAdd, linalg/sparsematrix_impl.hpp:344-352 (A^T is built on the device at first use)"""
+        x._dev_read()
+        y._dev_write()
+        check(_capi.lib().ngsb_csr_multtransadd(self.handle, scal2(s), x.handle, y.handle))
+
+    def CreateTranspose(self, sorted=True):
+        """mat.CreateTranspose() (linalg/python_linalg.cpp:172)"""
+        h = C.c_void_p()
+        check(_capi.lib().ngsb_csr_transpose(self.handle, C.byref(h)))
+        return DevSparseMatrix(None, ctx=self.ctx, _handle=h)
+
+    def MultAddMulti(self, alpha, xs, ys):
+        """SparseMatrix<double>::MultAdd(alpha, MultiVector x, MultiVector y), linalg/sparsematrix.cpp:2274-2351"""
+        k = len(xs)
+        if len(ys) != k or len(alpha) != k:
+            raise NgsbError("MultAdd(MultiVector): %d x vectors, %d y vectors, %d scalars" % (k, len(ys), len(alpha)))
+        for v in xs:
+            v._dev_read()
+        for v in ys:
+            v._dev_write()
+        al = np.ascontiguousarray(alpha, dtype=np.float64)
+        xa = (C.c_void_p * max(1, k))(*[v.handle for v in xs])
+        ya = (C.c_void_p * max(1, k))(*[v.handle for v in ys])
+        check(_capi.lib().ngsb_csr_multadd_multi(self.handle, k, _np_ptr(al), xa, ya))
+
     def Reorder(self, perm):
         """SparseMatrix::Reorder, linalg/sparsematrix_impl.hpp:762-783"""
         p = np.ascontiguousarray(perm, dtype=np.uint64)
@@ -695,10 +895,77 @@ class DevSparseMatrix(BaseMatrix):
         return b.value
 
 
+class SparseMatrixSymmetric(SparseMatrix):
+    """SparseMatrixSymmetric<TM> as its CSR() hands it out: the lower triangle (columns <= row), what
+    BilinearForm(symmetric_storage=True) assembles (linalg/sparsematrix.hpp:760-835).  CreateDeviceMatrix() expands it
+    to the full matrix on the device; Mult/MultAdd then equal SparseMatrixSymmetric::MultAdd."""
+
+    def CreateDeviceMatrix(self):
+        h = C.c_void_p()
+        check(_capi.lib().ngsb_csr_create_symmetric(self.ctx.handle, self.height, self.nze, _np_ptr(self.rowptr), _np_ptr(self.col),
+                                                    _np_ptr(self.val), _mat_kind(self.is_complex, self.entrysize), C.byref(h)))
+        return DevSparseMatrix(None, ctx=self.ctx, _handle=h)
+
+
+class _MultiVectorExpr:
+    def __init__(self, mat, mv):
+        self.mat, self.mv = mat, mv
+
+
+class MultiVector:
+    """MultiVector(vec, k) (linalg/multivector.hpp, linalg/python_linalg.cpp:716-880): k vectors of vec's kind.
+    `my[:] = mat * mx` runs the multi-right-hand-side product of the device matrix."""
+
+    def __init__(self, arg, k=None):
+        if isinstance(arg, BaseVector):
+            self.vecs = [arg.CreateVector() for _ in range(int(k))]
+        else:
+            self.vecs = list(arg)
+
+    def __len__(self):
+        return len(self.vecs)
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return MultiVector(self.vecs[i])
+        return self.vecs[i]
+
+    def __setitem__(self, key, value):
+        tgt = self.vecs[key] if isinstance(key, slice) else [self.vecs[key]]
+        if isinstance(value, _MultiVectorExpr):
+            if len(value.mv) != len(tgt):
+                raise NgsbError("MultiVector: %d vectors assigned to %d" % (len(value.mv), len(tgt)))
+            for v in tgt:
+                v.SetScalar(0.0)
+            m = value.mat
+            if isinstance(m, DevSparseMatrix):
+                m.MultAddMulti(np.ones(len(tgt)), value.mv.vecs, tgt)
+            else:
+                for x, y in zip(value.mv.vecs, tgt):
+                    m.MultAdd(1.0, x, y)
+        elif isinstance(value, MultiVector):
+            for x, y in zip(value.vecs, tgt):
+                y.Set(1.0, x)
+        else:
+            for y in tgt:
+                y.SetScalar(value)
+
+    def __rmul__(self, m):
+        return _MultiVectorExpr(m, self) if isinstance(m, BaseMatrix) else NotImplemented
+
+    def InnerProduct(self, other, conjugate=True):
+        """matrix of inner products (MultiVector::InnerProduct): out[i, j] = <other[j], self[i]> as `other.InnerProduct`"""
+        out = np.zeros((len(self), len(other)), dtype=np.complex128 if self.vecs and self.vecs[0].is_complex else np.float64)
+        for i, a in enumerate(self.vecs):
+            for j, b in enumerate(other.vecs):
+                out[i, j] = a.InnerProduct(b, conjugate=conjugate)
+        return out
+
+
 def CreateDevMatrix(mat):
     """ngscuda.CreateDevMatrix: throws if no device version exists (ngscuda/cuda_linalg.cpp:176-182)"""
     dev = mat.CreateDeviceMatrix()
-    if dev is mat and not isinstance(mat, (DevSparseMatrix, DevJacobiMatrix)):
+    if dev is mat and not isinstance(mat, (DevSparseMatrix, DevJacobiMatrix, DevBlockJacobiMatrix)):
         raise NgsbError("CreateDevMatrix: no device matrix for %s" % type(mat).__name__)
     return dev
 
@@ -760,10 +1027,99 @@ class DevJacobiMatrix(BaseMatrix):
         y._dev_write()
         check(_capi.lib().ngsb_jacobi_multadd(self.handle, scal2(s), x.handle, y.handle))
 
+    def MultTransAdd(self, s, x, y):
+        if self.entrysize != 1:
+            raise NgsbError("DiagonalMatrix::MultTransAdd: only scalar entries")
+        self.MultAdd(s, x, y)
+
     def InvDiag(self):
         ms = 9 if self.entrysize == 3 else 1
         out = np.empty(self.height * ms, dtype=np.complex128 if self.is_complex else np.float64)
         check(_capi.lib().ngsb_jacobi_download(self.handle, _np_ptr(out)))
+        return out
+
+
+def _block_table(blocks):
+    """list of dof lists (or (first, dofs) arrays) -> the reference's Table<int> as (first uint64[nb+1], dofs int32)"""
+    if isinstance(blocks, tuple) and len(blocks) == 2 and isinstance(blocks[0], np.ndarray):
+        return np.ascontiguousarray(blocks[0], dtype=np.uint64), np.ascontiguousarray(blocks[1], dtype=np.int32)
+    first = np.zeros(len(blocks) + 1, dtype=np.uint64)
+    first[1:] = np.cumsum([len(b) for b in blocks], dtype=np.uint64)
+    dofs = np.fromiter((d for b in blocks for d in b), dtype=np.int32, count=int(first[-1]))
+    return first, dofs
+
+
+class BlockJacobiPrecond(BaseMatrix):
+    """mat.CreateBlockSmoother(blocks) on a host matrix (BlockJacobiPrecond<double>, linalg/blockjacobi.cpp:380-500);
+    the block inverses are built on the device by CreateDeviceMatrix()."""
+
+    def __init__(self, mat, blocks):
+        self.mat, self.blocks = mat, blocks
+        self.height = self.width = mat.height
+        self.is_complex, self.entrysize, self.ctx = mat.is_complex, mat.entrysize, mat.ctx
+        self._dev = None
+
+    def CreateDeviceMatrix(self, devmat=None):
+        if self._dev is None:
+            self._dev = DevBlockJacobiMatrix(devmat or self.mat.CreateDeviceMatrix(), self.blocks)
+        return self._dev
+
+    def Mult(self, x, y):
+        raise NgsbError("BlockJacobiPrecond on the host: this package has no CPU path, use CreateDeviceMatrix()")
+
+    MultAdd = Mult
+
+
+class DevBlockJacobiMatrix(BaseMatrix):
+    """DevBlockJacobiMatrix (ngscuda/dev_blockjacobi.cpp:21-140): y(block) += s * inv(A(block,block)) * x(block)."""
+
+    def __init__(self, devmat, blocks):
+        self.ctx = devmat.ctx
+        first, dofs = _block_table(blocks)
+        h = C.c_void_p()
+        check(_capi.lib().ngsb_blockjacobi_create(devmat.handle, len(first) - 1, _np_ptr(first), _np_ptr(dofs) if len(dofs) else None, C.byref(h)))
+        self.handle = h
+        self.height = self.width = devmat.height
+        self.is_complex, self.entrysize = False, 1
+        self.first, self.dofs = first, dofs
+        self._fin = weakref.finalize(self, _capi.lib().ngsb_blockjacobi_destroy, h)
+
+    def Mult(self, x, y):
+        self._check(x, y, "BlockJacobiPrecond::Mult")
+        x._dev_read()
+        y._dev_write()
+        check(_capi.lib().ngsb_blockjacobi_mult(self.handle, x.handle, y.handle, 0))
+
+    def MultAdd(self, s, x, y):
+        self._check(x, y, "BlockJacobiPrecond::MultAdd")
+        x._dev_read()
+        y._dev_write()
+        check(_capi.lib().ngsb_blockjacobi_multadd(self.handle, float(s), x.handle, y.handle, 0))
+
+    def MultTrans(self, s, x, y):
+        # the Python binding takes a `value` and ignores it: y = 0; MultTransAdd(1.0, x, y)  (linalg/python_linalg.cpp:1074)
+        self._check(x, y, "BlockJacobiPrecond::MultTrans")
+        x._dev_read()
+        y._dev_write()
+        check(_capi.lib().ngsb_blockjacobi_mult(self.handle, x.handle, y.handle, 1))
+
+    def MultTransAdd(self, s, x, y):
+        self._check(x, y, "BlockJacobiPrecond::MultTransAdd")
+        x._dev_read()
+        y._dev_write()
+        check(_capi.lib().ngsb_blockjacobi_multadd(self.handle, float(s), x.handle, y.handle, 1))
+
+    def GetInverses(self):
+        """the inverse blocks (row-major numpy matrices), BlockJacobiPrecond::GetInverses"""
+        tot = C.c_size_t()
+        check(_capi.lib().ngsb_blockjacobi_info(self.handle, None, None, None, None, C.byref(tot)))
+        flat = np.empty(max(1, tot.value))
+        check(_capi.lib().ngsb_blockjacobi_download(self.handle, _np_ptr(flat)))
+        out, off = [], 0
+        for b in range(len(self.first) - 1):
+            bs = int(self.first[b + 1] - self.first[b])
+            out.append(flat[off:off + bs * bs].reshape(bs, bs).copy())
+            off += bs * bs
         return out
 
 
@@ -790,7 +1146,7 @@ def Projector(mask, range=True, ctx=None):
 class _KrylovSolver(BaseMatrix):
     def __init__(self, mat, pre=None, printrates=False, precision=1e-8, maxsteps=200, conjugate=False):
         self.mat = mat.CreateDeviceMatrix() if isinstance(mat, SparseMatrix) else mat
-        if isinstance(pre, JacobiPrecond):
+        if isinstance(pre, (JacobiPrecond, BlockJacobiPrecond)):
             pre = pre.CreateDeviceMatrix(self.mat if isinstance(self.mat, DevSparseMatrix) else None)
         self.pre = pre
         self.precision, self.maxsteps, self.conjugate, self.printrates = precision, maxsteps, conjugate, printrates

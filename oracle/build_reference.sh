@@ -30,6 +30,8 @@ farm() {  # farm <src> <dst>: dst is a real directory whose entries are symlinks
 mkdir -p "$BUILD" "$PFX"
 NGSRC=$BUILD/src/ngsolve_v6.2.2506-0-g0000000
 farm "$REF" "$NGSRC"
+# cmake/generate_version_file.cmake reads <source>/version.txt when the tree is not a git checkout
+echo "v6.2.2506-0-g0000000" > "$NGSRC/version.txt"
 # netgen lives below external_dependencies/ (a symlink into the read-only tree) -- build it from there
 NETGEN=$REF/external_dependencies/netgen
 

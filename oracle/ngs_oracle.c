@@ -287,10 +287,20 @@ static int64_t diag_pos(const uint64_t *firsti, const int32_t *colnr, size_t i)
 
 /* T_CalcInverse, basiclinalg/calcinverse.cpp:26-107 (Gauss-Jordan with column pivoting),
  * reached from CalcInverse(Mat<3,3>&) via FlatMatrix (basiclinalg/calcinverse.hpp:63-68). */
+static int calc_inverse_core(int n, double *inv, int *p, double *hv);
 static int calc_inverse_n(int n, double *inv)
 {
-    int p[8];
-    double hv[8];
+    int p8[8];
+    double hv8[8];
+    int *p = n <= 8 ? p8 : (int *)malloc((size_t)n * sizeof(int));
+    double *hv = n <= 8 ? hv8 : (double *)malloc((size_t)n * sizeof(double));
+    int rc = calc_inverse_core(n, inv, p, hv);
+    if (n > 8) { free(p); free(hv); }
+    return rc;
+}
+
+static int calc_inverse_core(int n, double *inv, int *p, double *hv)
+{
     for (int j = 0; j < n; j++) p[j] = j;
     for (int j = 0; j < n; j++) {
         double maxval = fabs(inv[j * n + j]);
@@ -633,4 +643,106 @@ void orc_pardofs_build(int ntasks, int id, size_t ndof, const uint64_t *dp_first
     for (int p = 0; p < id; p++)                /* shared with any lower rank -> not master */
         for (uint64_t k = ex_first[p]; k < ex_first[p + 1]; k++) ismaster[ex_data[k]] = 0;
     free(cnt);
+}
+
+
+/* ---- BlockJacobiPrecond<double> ---------------------------------------------------------------------------------- */
+/* ctor, linalg/blockjacobi.cpp:380-500: block b = dofs[bfirst[b] .. bfirst[b+1]); blockmat(j,k) = A(block[j], block[k])
+ * (absent positions read as zero), then CalcInverse(blockmat).  The reference switches to LAPACK for blocks of 100 and
+ * more dofs (basiclinalg/calcinverse.cpp:188-190); this restatement uses T_CalcInverse (:26-107) for every size.
+ * inverses: blocks back to back, row-major.  Returns 0, or -1 - b if block b is singular. */
+int orc_blockjacobi_setup(size_t n, const uint64_t *firsti, const int32_t *colnr, const double *data, size_t nblocks,
+                          const uint64_t *bfirst, const int32_t *bdofs, double *inverses)
+{
+    (void)n;
+    size_t off = 0;
+    for (size_t b = 0; b < nblocks; b++) {
+        const int bs = (int)(bfirst[b + 1] - bfirst[b]);
+        const int32_t *blk = bdofs + bfirst[b];
+        double *m = inverses + off;
+        for (int j = 0; j < bs; j++)
+            for (int k = 0; k < bs; k++) {
+                double v = 0.0;
+                for (uint64_t e = firsti[blk[j]]; e < firsti[blk[j] + 1]; e++)
+                    if (colnr[e] == blk[k]) { v = data[e]; break; }
+                m[(size_t)j * bs + k] = v;
+            }
+        if (bs > 0 && calc_inverse_n(bs, m) != 0) return -1 - (int)b;
+        off += (size_t)bs * bs;
+    }
+    return 0;
+}
+
+/* MultAdd / MultTransAdd, linalg/blockjacobi.cpp:594-681: y(block) += s * (inv_b | inv_b^T) * x(block).  The reference
+ * walks the blocks colour by colour; blocks are visited here in ascending order (the order only matters for the
+ * rounding of dofs that sit in several blocks). */
+void orc_blockjacobi_multadd(size_t nblocks, const uint64_t *bfirst, const int32_t *bdofs, const double *inverses, double s,
+                             const double *x, double *y, int transpose)
+{
+    size_t off = 0;
+    for (size_t b = 0; b < nblocks; b++) {
+        const int bs = (int)(bfirst[b + 1] - bfirst[b]);
+        const int32_t *blk = bdofs + bfirst[b];
+        const double *m = inverses + off;
+        double *hy = (double *)malloc((size_t)(bs > 0 ? bs : 1) * sizeof(double));
+        for (int r = 0; r < bs; r++) {
+            double sum = 0.0;
+            for (int c = 0; c < bs; c++) sum += (transpose ? m[(size_t)c * bs + r] : m[(size_t)r * bs + c]) * x[blk[c]];
+            hy[r] = sum;
+        }
+        for (int r = 0; r < bs; r++) y[blk[r]] += s * hy[r];
+        free(hy);
+        off += (size_t)bs * bs;
+    }
+}
+
+/* ---- SparseMatrix::MultTransAdd, linalg/sparsematrix_impl.hpp:344-352 + AddRowTransToVector (linalg/sparsematrix.hpp):
+ * serial scatter, row by row: y(col[j]) += Trans(data[j]) * (s * x(i)).  kind 0 / 1 (plain transpose, no conjugation) / 3 */
+void orc_csr_multtransadd(int kind, size_t h, const uint64_t *firsti, const int32_t *colnr, const void *data, double s,
+                          const void *xv, void *yv)
+{
+    if (kind == 0) {
+        const double *d = (const double *)data, *x = (const double *)xv;
+        double *y = (double *)yv;
+        for (size_t i = 0; i < h; i++) {
+            const double el = s * x[i];
+            for (uint64_t j = firsti[i]; j < firsti[i + 1]; j++) y[colnr[j]] += d[j] * el;
+        }
+    } else if (kind == 1) {
+        const orc_cplx *d = (const orc_cplx *)data, *x = (const orc_cplx *)xv;
+        orc_cplx *y = (orc_cplx *)yv;
+        for (size_t i = 0; i < h; i++) {
+            const orc_cplx el = s * x[i];
+            for (uint64_t j = firsti[i]; j < firsti[i + 1]; j++) y[colnr[j]] += d[j] * el;
+        }
+    } else {
+        const double *d = (const double *)data, *x = (const double *)xv;
+        double *y = (double *)yv;
+        for (size_t i = 0; i < h; i++) {
+            const double e0 = s * x[3 * i], e1 = s * x[3 * i + 1], e2 = s * x[3 * i + 2];
+            for (uint64_t j = firsti[i]; j < firsti[i + 1]; j++) {
+                const double *m = d + 9 * j;
+                double *yy = y + 3 * (size_t)colnr[j];
+                yy[0] += m[0] * e0 + m[3] * e1 + m[6] * e2;
+                yy[1] += m[1] * e0 + m[4] * e1 + m[7] * e2;
+                yy[2] += m[2] * e0 + m[5] * e1 + m[8] * e2;
+            }
+        }
+    }
+}
+
+/* ---- SparseMatrixSymmetric<double>::MultAdd, linalg/sparsematrix_impl.hpp:967-983: lower triangle stored (columns
+ * <= row, diagonal last); y(i) += s * row(i).x ; then the strict lower part of row i is scattered transposed. */
+void orc_csrsym_multadd_d(size_t n, const uint64_t *firsti, const int32_t *colnr, const double *data, double s,
+                          const double *x, double *y)
+{
+    for (size_t i = 0; i < n; i++) {
+        double sum = 0.0;
+        for (uint64_t j = firsti[i]; j < firsti[i + 1]; j++) sum += data[j] * x[colnr[j]];
+        y[i] += s * sum;
+        const double el = s * x[i];
+        uint64_t last = firsti[i + 1];
+        if (last > firsti[i] && (size_t)colnr[last - 1] == i) last--;       /* AddRowTransToVectorNoDiag */
+        for (uint64_t j = firsti[i]; j < last; j++) y[colnr[j]] += data[j] * el;
+    }
 }

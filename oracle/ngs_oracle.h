@@ -103,6 +103,18 @@ void orc_csr_reorder(int kind, size_t n, const uint64_t *firsti, const int32_t *
 void orc_pardofs_build(int ntasks, int id, size_t ndof, const uint64_t *dp_first, const int32_t *dp_data,
                        uint64_t *ex_first, int32_t *ex_data, uint8_t *ismaster);
 
+/* ---- BlockJacobiPrecond<double> (linalg/blockjacobi.cpp:380-500, 594-681) ---------------- */
+int orc_blockjacobi_setup(size_t n, const uint64_t *firsti, const int32_t *colnr, const double *data, size_t nblocks,
+                          const uint64_t *bfirst, const int32_t *bdofs, double *inverses);
+void orc_blockjacobi_multadd(size_t nblocks, const uint64_t *bfirst, const int32_t *bdofs, const double *inverses, double s,
+                             const double *x, double *y, int transpose);
+
+/* ---- MultTransAdd (linalg/sparsematrix_impl.hpp:344-352) and symmetric storage (:967-983) ---- */
+void orc_csr_multtransadd(int kind, size_t h, const uint64_t *firsti, const int32_t *colnr, const void *data, double s,
+                          const void *x, void *y);
+void orc_csrsym_multadd_d(size_t n, const uint64_t *firsti, const int32_t *colnr, const double *data, double s,
+                          const double *x, double *y);
+
 #ifdef __cplusplus
 }
 #endif

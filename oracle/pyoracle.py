@@ -148,6 +148,62 @@ class Jacobi:
         return self.multadd(1.0, x, y)
 
 
+class BlockJacobi:
+    """BlockJacobiPrecond<double>: blocks = list of dof lists"""
+
+    def __init__(self, A, blocks):
+        assert A.kind == KIND_REAL
+        self.n = A.n
+        self.first = np.zeros(len(blocks) + 1, dtype=np.uint64)
+        self.first[1:] = np.cumsum([len(b) for b in blocks], dtype=np.uint64)
+        self.dofs = np.array([d for b in blocks for d in b] or [0], dtype=np.int32)
+        self.nblocks = len(blocks)
+        tot = int(sum(len(b) ** 2 for b in blocks))
+        self.inv = np.zeros(max(1, tot))
+        L = lib()
+        L.orc_blockjacobi_setup.restype = C.c_int
+        rc = L.orc_blockjacobi_setup(C.c_size_t(A.n), _p(A.rowptr), _p(A.col), _p(A.val), C.c_size_t(self.nblocks), _p(self.first),
+                                     _p(self.dofs), _p(self.inv))
+        if rc != 0:
+            raise RuntimeError("Inverse matrix: Matrix singular (block %d)" % (-1 - rc))
+
+    def inverses(self):
+        out, off = [], 0
+        for b in range(self.nblocks):
+            bs = int(self.first[b + 1] - self.first[b])
+            out.append(self.inv[off:off + bs * bs].reshape(bs, bs).copy())
+            off += bs * bs
+        return out
+
+    def multadd(self, s, x, y, transpose=False):
+        x = _prep(KIND_REAL, x)
+        assert y.flags.c_contiguous and y.dtype == np.float64
+        lib().orc_blockjacobi_multadd(C.c_size_t(self.nblocks), _p(self.first), _p(self.dofs), _p(self.inv), C.c_double(s), _p(x), _p(y),
+                                      C.c_int(1 if transpose else 0))
+        return y
+
+    def mult(self, x, transpose=False):
+        return self.multadd(1.0, x, np.zeros(self.n), transpose)
+
+
+def multtransadd(A, s, x, y):
+    """SparseMatrix::MultTransAdd (serial scatter), y modified in place"""
+    x = _prep(A.kind, x)
+    assert y.flags.c_contiguous and y.dtype == _dtype(A.kind)
+    lib().orc_csr_multtransadd(C.c_int(A.kind), C.c_size_t(A.n), _p(A.rowptr), _p(A.col), _p(A.val), C.c_double(s), _p(x), _p(y))
+    return y
+
+
+def sym_multadd(rowptr, col, val, s, x, y):
+    """SparseMatrixSymmetric<double>::MultAdd on lower-triangular storage"""
+    rowptr = np.ascontiguousarray(rowptr, dtype=np.uint64)
+    col = np.ascontiguousarray(col, dtype=np.int32)
+    val = _prep(KIND_REAL, val)
+    x = _prep(KIND_REAL, x)
+    lib().orc_csrsym_multadd_d(C.c_size_t(len(rowptr) - 1), _p(rowptr), _p(col), _p(val), C.c_double(s), _p(x), _p(y))
+    return y
+
+
 def cg_solve(A, jac, f, prec=1e-8, maxsteps=200, ip_mode=None, initialize=True, u0=None):
     """CGSolver<IPTYPE>::Mult.  Returns (u, steps, history of Abs(wdn))."""
     kind = A.kind

@@ -118,8 +118,22 @@ def run(cfg, scale):
         S = 16 if cplx else 8
         # step j moves B_spmv + 3 N S + (2 (j+1) + 4) N S
         bytes_tot = sum(b + (2 * (j + 1) + 7) * A.height * es * S for j in range(its))
+        # modified Gram-Schmidt as the reference does it (cg.cpp:927-932) cannot do better than 4 passes per projection
+        # (read w, v_i, v_i+1; write w): the traffic this implementation really needs
+        mgs_bytes = sum(b + (4 * (j + 1) + 3 + 3 + 2) * A.height * es * S for j in range(its))
         out.update(solver="GMRES+Jacobi (no restart)", iterations=its, it_per_s=its / s, gmres_gbs=bytes_tot / s / 1e9,
-                   gmres_frac_of_measured_peak=bytes_tot / s / 1e9 / peak())
+                   gmres_frac_of_measured_peak=bytes_tot / s / 1e9 / peak(), gmres_mgs_gbs=mgs_bytes / s / 1e9,
+                   gmres_mgs_frac_of_measured_peak=mgs_bytes / s / 1e9 / peak(), solve_s=s)
+    ctx.set_option("timing", 1)
+    ctx.kernel_time_reset()
+    t0 = time.perf_counter()
+    inv.Mult(f, u)
+    ctx.sync()
+    wall = time.perf_counter() - t0
+    out["kernel_ms_by_class"] = {k: ctx.kernel_time(k) for k in ("spmv", "cgupdate", "vec", "other", "all")}
+    out["timed_solve_wall_ms"] = wall * 1e3
+    ctx.kernel_time_reset()
+    ctx.set_option("timing", 0)
     return out
 
 
