@@ -30,7 +30,7 @@ import numpy as np  # noqa: E402
 
 METRIC = "cg_iterations_per_s"
 UNIT = "iterations/s"
-SAMPLE_M = 33            # CPU sample: (3*33+1)^3 = 1.0 M dofs (BASELINE.json configs[0] size)
+SAMPLE_M = 50            # CPU sample: (3*50+1)^3 = 3.4 M dofs, 163 M non-zeros (2 GB of matrix: far out of the host caches)
 
 
 def parse():
@@ -54,9 +54,51 @@ def workload_name(m):
 # ---------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference path
 # ---------------------------------------------------------------------------------------------
-def cpu_cg(iters, full_nnz, full_ndof):
-    """Jacobi-PCG of the oracle (reference recurrences, 16-chunk dots, OpenMP rows) on the sample
-    system; returns dict(value scaled to the full size, raw numbers)."""
+def _reference_env():
+    """environment of the reference build (oracle/build_reference.sh -> oracle/_ref/ngs), or None when it is absent"""
+    pfx = os.path.join(ROOT, "oracle", "_ref", "ngs")
+    site = os.path.join(pfx, "lib", "python3.12", "site-packages")
+    if not os.path.isdir(os.path.join(site, "ngsolve")):
+        return None
+    import importlib.util
+    spec = importlib.util.find_spec("cv2")
+    libs = os.path.join(os.path.dirname(os.path.dirname(spec.origin)), "opencv_python_headless.libs") if spec and spec.origin else ""
+    env = dict(os.environ)
+    env["PYTHONPATH"] = site + os.pathsep + env.get("PYTHONPATH", "")
+    env["LD_LIBRARY_PATH"] = os.pathsep.join([os.path.join(pfx, "lib"), os.path.join(site, "netgen"), libs, env.get("LD_LIBRARY_PATH", "")])
+    return env
+
+
+def cpu_cg_reference(iters, warmup, full_nnz):
+    """the reference itself (NGSolve's C++ CGSolver under its TaskManager) on the sample system, in a subprocess
+    (`import ngsolve` has to precede numpy/torch).  None when the build is not on this box or does not run."""
+    env = _reference_env()
+    if env is None:
+        return None
+    try:
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "ref_cpu_cg.py"), "--m", str(SAMPLE_M), "--iters", str(iters),
+                            "--warmup", str(warmup)], env=env, capture_output=True, text=True, timeout=900)
+        d = json.loads(r.stdout.strip().splitlines()[-1])
+    except Exception as e:                    # noqa: BLE001  (report and fall back to the port)
+        sys.stderr.write("reference CPU arm unavailable: %r\n" % (e,))
+        return None
+    raw, nnz, n = d["it_per_s"], d["nnz"], d["ndof"]
+    b_iter = nnz * 12 + n * (4 + 8 + 8) + 21 * n * 8
+    return dict(value=raw * nnz / full_nnz, unit=UNIT, cores=d["threads"], kind="reference",
+                sample="NGSolve %s C++ CGSolver + JacobiPrecond under TaskManager(%d threads), %d iterations on the %.2fM-dof system of the same "
+                       "family (%d^3 cubes, injected by CreateFromCOO): %.1f it/s = %.1f GB/s of the reference's per-iteration traffic, SpMV alone "
+                       "%.2f ms = %.1f GB/s; scaled by nnz ratio %.4g to the full size"
+                       % (d["ngsolve_version"], d["threads"], d["iterations"], n / 1e6, SAMPLE_M, raw, raw * b_iter / 1e9, d["spmv_ms"], d["spmv_gbs"],
+                          nnz / full_nnz),
+                raw_iterations_per_s=raw, sample_ndof=n, sample_nnz=nnz, reference_setup_s=d["setup_s"])
+
+
+def cpu_cg(iters, full_nnz, full_ndof, warmup=3):
+    """CPU baseline on the sample system: the reference itself when its build travelled with the repo, else the
+    oracle port (reference recurrences, 16-chunk dots, OpenMP rows).  dict(value scaled to the full size, raw numbers)."""
+    ref = cpu_cg_reference(iters, warmup, full_nnz)
+    if ref is not None:
+        return ref
     from oracle import pyoracle as orc
     from ngsolve_b200 import workloads as W
     box = W.FemBox(SAMPLE_M, order=3)
@@ -65,7 +107,7 @@ def cpu_cg(iters, full_nnz, full_ndof):
     A = orc.Csr(rp, col, val, 0)
     J = orc.Jacobi(A, free.bytes)
     cores = orc.max_threads()
-    orc.cg_solve(A, J, rhs, prec=0.0, maxsteps=3)                     # warm-up
+    orc.cg_solve(A, J, rhs, prec=0.0, maxsteps=warmup)                     # warm-up
     t0 = time.perf_counter()
     _, steps, _ = orc.cg_solve(A, J, rhs, prec=0.0, maxsteps=iters)
     dt = time.perf_counter() - t0
@@ -113,15 +155,16 @@ def run_reference(args):
         nnz = int(int(rp[-1]) / box.ndof * ndof)
     iters = max(1, args.steps)
     t0 = time.perf_counter()
-    base = cpu_cg(iters + args.warmup, nnz, ndof)
+    base = cpu_cg(iters, nnz, ndof, warmup=max(1, args.warmup))
     dt = time.perf_counter() - t0
     line = {
         "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 / base["value"], "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(m), "global_dofs": ndof, "nnz": nnz, "precond": "Jacobi (freedofs-masked)",
-                   "note": "CPU arm = oracle port of the reference path (NGSolve needs cmake+netgen: unbuildable on the box), "
-                           "timed on a bounded sample and scaled by nnz"},
+                   "note": "CPU arm = the reference (NGSolve CGSolver under TaskManager) when its build (oracle/build_reference.sh) travelled "
+                           "with the repo, else the oracle port of the same path; timed on a bounded sample and scaled by nnz: kind = "
+                           + base["kind"]},
         "cpu_baseline": base,
         "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": dt,

@@ -201,6 +201,11 @@ int ngsb_csr_multadd_multi(const ngsb_csr *A, size_t nvec, const double *alpha, 
  * (linalg/blockjacobi.cpp:594-634); transpose != 0: MultTransAdd (:637-681). */
 int ngsb_blockjacobi_create(const ngsb_csr *A, size_t nblocks, const uint64_t *first, const int32_t *dofs,
                             ngsb_blockjacobi **out);
+/* the same object from inverses computed elsewhere (the adapter hands over BlockJacobiPrecond::GetInverses(), which the
+ * reference's constructor already built on the host -- what DevBlockJacobiMatrix's constructor copies,
+ * ngscuda/dev_blockjacobi.cpp:95-113): blocks back to back, each row-major; n = vector length */
+int ngsb_blockjacobi_create_from_inverses(ngsb_ctx *ctx, size_t n, size_t nblocks, const uint64_t *first, const int32_t *dofs,
+                                          const double *inverses, ngsb_blockjacobi **out);
 int ngsb_blockjacobi_destroy(ngsb_blockjacobi *J);
 int ngsb_blockjacobi_info(const ngsb_blockjacobi *J, size_t *n, size_t *nblocks, size_t *maxbs, size_t *total,
                           size_t *matrix_entries);

@@ -147,6 +147,8 @@ namespace ngla
     { double z[2] = {s,0}; Check (ngsb_csr_multadd (A, z, B200Vector<SCAL>::Cast(x).Dev(), const_cast<B200Vector<SCAL>&>(B200Vector<SCAL>::Cast(y)).DevW())); }
     void MultAdd (Complex s, const BaseVector & x, BaseVector & y) const override
     { double z[2] = {s.real(),s.imag()}; Check (ngsb_csr_multadd (A, z, B200Vector<SCAL>::Cast(x).Dev(), const_cast<B200Vector<SCAL>&>(B200Vector<SCAL>::Cast(y)).DevW())); }
+    void MultTransAdd (double s, const BaseVector & x, BaseVector & y) const override
+    { double z[2] = {s,0}; Check (ngsb_csr_multtransadd (A, z, B200Vector<SCAL>::Cast(x).Dev(), const_cast<B200Vector<SCAL>&>(B200Vector<SCAL>::Cast(y)).DevW())); }
   };
 
   // ---- Jacobi: replaces DevDiagonalMatrix built from JacobiPrecond<TM> (keeps the freedofs mask) ------
@@ -162,7 +164,10 @@ namespace ngla
     B200Jacobi (const JacobiPrecond<TM> & jac) : n(jac.Height())
     {
       auto inv = jac.GetInverse();                              // Array<TM> invdiag (linalg/jacobi.hpp)
-      auto inner = jac.GetInner();                              // shared_ptr<BitArray> or nullptr
+      // `inner` (the freedofs BitArray) is a protected member without getter: reach it through a derived-class
+      // member pointer, so that the masked apply is exactly JacobiPrecond::MultAdd (linalg/jacobi.cpp:71-109)
+      struct Access : JacobiPrecond<TM> { static auto Ptr () { return &Access::inner; } };
+      shared_ptr<BitArray> inner = jac.*(Access::Ptr());
       Check (ngsb_jacobi_create (TheCtx(), n, inv.Data(), cplx ? NGSB_COMPLEX : (es == 3 ? NGSB_BLOCK3 : NGSB_REAL),
                                  inner ? (const uint8_t*)inner->Data() : nullptr, &J));
     }
@@ -177,6 +182,47 @@ namespace ngla
     { Check (ngsb_jacobi_mult (J, B200Vector<SCAL>::Cast(x).Dev(), const_cast<B200Vector<SCAL>&>(B200Vector<SCAL>::Cast(y)).DevW())); }
     void MultAdd (double s, const BaseVector & x, BaseVector & y) const override
     { double z[2] = {s,0}; Check (ngsb_jacobi_multadd (J, z, B200Vector<SCAL>::Cast(x).Dev(), const_cast<B200Vector<SCAL>&>(B200Vector<SCAL>::Cast(y)).DevW())); }
+  };
+
+  // ---- block Jacobi: replaces DevBlockJacobiMatrix (ngscuda/dev_blockjacobi.cpp:21-140) --------------------
+  class B200BlockJacobi : public BaseMatrix
+  {
+    ngsb_blockjacobi * J = nullptr;
+    size_t n;
+  public:
+    B200BlockJacobi (const BlockJacobiPrecond<double> & bj) : n(bj.Height())
+    {
+      auto table = bj.GetBlockTable();                               // shared_ptr<Table<int>>
+      const Array<FlatMatrix<double>> & inverses = bj.GetInverses();  // row-major blocks, already inverted on the host
+      Array<uint64_t> first(table->Size()+1);
+      first[0] = 0;
+      size_t entries = 0;
+      for (size_t b = 0; b < table->Size(); b++)
+        { first[b+1] = first[b] + (*table)[b].Size(); entries += sqr (size_t((*table)[b].Size())); }
+      Array<double> flat(entries);
+      size_t off = 0;
+      for (size_t b = 0; b < table->Size(); b++)
+        {
+          size_t bs = (*table)[b].Size();
+          for (size_t r = 0; r < bs; r++)
+            for (size_t c = 0; c < bs; c++)
+              flat[off + r*bs + c] = inverses[b](r,c);
+          off += bs*bs;
+        }
+      Check (ngsb_blockjacobi_create_from_inverses (TheCtx(), n, table->Size(), first.Data(), table->AsArray().Data(),
+                                                    flat.Data(), &J));
+    }
+    ~B200BlockJacobi () { ngsb_blockjacobi_destroy (J); }
+    int VHeight () const override { return n; }
+    int VWidth () const override { return n; }
+    AutoVector CreateRowVector () const override { return make_unique<B200Vector<double>> (n, 1); }
+    AutoVector CreateColVector () const override { return make_unique<B200Vector<double>> (n, 1); }
+    void MultAdd (double s, const BaseVector & x, BaseVector & y) const override
+    { Check (ngsb_blockjacobi_multadd (J, s, B200Vector<double>::Cast(x).Dev(), const_cast<B200Vector<double>&>(B200Vector<double>::Cast(y)).DevW(), 0)); }
+    void MultTransAdd (double s, const BaseVector & x, BaseVector & y) const override
+    { Check (ngsb_blockjacobi_multadd (J, s, B200Vector<double>::Cast(x).Dev(), const_cast<B200Vector<double>&>(B200Vector<double>::Cast(y)).DevW(), 1)); }
+    void Mult (const BaseVector & x, BaseVector & y) const override
+    { Check (ngsb_blockjacobi_mult (J, B200Vector<double>::Cast(x).Dev(), const_cast<B200Vector<double>&>(B200Vector<double>::Cast(y)).DevW(), 0)); }
   };
 
   // ---- fused device CG: same interface as DevCGSolver (ngscuda/cuda_linalg.hpp:289-310) ----------------
@@ -225,6 +271,8 @@ namespace ngla
     BaseVector::RegisterDeviceVectorCreator (typeid(VVector<Vec<3,double>>), dvec);
     BaseVector::RegisterDeviceVectorCreator (typeid(S_BaseVectorPtr<double>), dvec);
     BaseVector::RegisterDeviceVectorCreator (typeid(S_BaseVectorPtr<Complex>), dvec);
+    BaseMatrix::RegisterDeviceMatrixCreator (typeid(BlockJacobiPrecond<double>), [] (const BaseMatrix & m) -> shared_ptr<BaseMatrix>
+      { return make_shared<B200BlockJacobi> (dynamic_cast<const BlockJacobiPrecond<double>&> (m)); });
     RegisterFor<double> ();
     RegisterFor<Complex> ();
     RegisterFor<Mat<3,3,double>> ();

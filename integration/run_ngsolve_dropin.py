@@ -1,0 +1,95 @@
+#!/usr/bin/env python
+"""The drop-in, end to end: an UNCHANGED NGSolve solve script (netgen mesh, BilinearForm.Assemble, CreateSmoother,
+CGSolver(mat, pre)) run once on NGSolve's own CPU path and once behind CreateDeviceMatrix()/CreateDeviceVector() with
+the adapter module `_ngsb200` imported -- the same lines as docs/i-tutorials/unit-5.5-cuda/poisson_cuda.ipynb cells 5-6
+with `import ngsolve.ngscuda` replaced by `import _ngsb200`.
+
+Needs NGSolve (oracle/build_reference.sh), the adapter (integration/build_adapter.sh) and a GPU:
+    source oracle/_ref/ngs/env.sh && python integration/run_ngsolve_dropin.py [--maxh 0.05] [--order 3]
+Prints one JSON line (steps, timings, difference of the two solutions).
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import ngsolve
+from ngsolve import *          # noqa: F401,F403
+from netgen.csg import unit_cube
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "_build"))
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--maxh", type=float, default=0.05)
+ap.add_argument("--order", type=int, default=3)
+ap.add_argument("--threads", type=int, default=0)
+args = ap.parse_args()
+ngsolve.ngsglobals.msg_level = 0
+SetNumThreads(args.threads or os.cpu_count())
+
+import _ngsb200               # registers the device creators (BaseMatrix::RegisterDeviceMatrixCreator, ...)
+
+out = {"ngsolve": ngsolve.__version__, "maxh": args.maxh, "order": args.order, "threads": args.threads or os.cpu_count()}
+with TaskManager():
+    t0 = time.perf_counter()
+    mesh = Mesh(unit_cube.GenerateMesh(maxh=args.maxh))
+    fes = H1(mesh, order=args.order, dirichlet=".*")
+    u, v = fes.TnT()
+    a = BilinearForm(grad(u) * grad(v) * dx).Assemble()
+    f = LinearForm(1 * v * dx).Assemble()
+    jac = a.mat.CreateSmoother(fes.FreeDofs())
+    out.update(ndof=fes.ndof, nze=a.mat.nze, ne=mesh.ne, setup_s=time.perf_counter() - t0)
+
+    # ---- NGSolve's own CPU path
+    gfu = GridFunction(fes)
+    inv = CGSolver(a.mat, jac, precision=1e-8, maxsteps=20000)
+    t0 = time.perf_counter()
+    gfu.vec.data = inv * f.vec
+    out.update(cpu_steps=inv.GetSteps(), cpu_solve_s=time.perf_counter() - t0)
+
+    # ---- the same script lines behind the device creators
+    t0 = time.perf_counter()
+    adev = a.mat.CreateDeviceMatrix()
+    jdev = jac.CreateDeviceMatrix()
+    fdev = f.vec.CreateDeviceVector()
+    out.update(upload_s=time.perf_counter() - t0, types=[type(adev).__name__, type(jdev).__name__, type(fdev).__name__],
+               is_host_object=[adev is a.mat, jdev is jac])
+    invdev = CGSolver(adev, jdev, precision=1e-8, maxsteps=20000)        # NGSolve's C++ CG loop, every op a virtual call into libngsb200
+    res = (invdev * fdev).Evaluate()
+    t0 = time.perf_counter()
+    res = (invdev * fdev).Evaluate()
+    out.update(dev_steps=invdev.GetSteps(), dev_solve_s=time.perf_counter() - t0)
+    gfu2 = GridFunction(fes)
+    gfu2.vec.data = res
+    diff = gfu.vec.CreateVector()
+    diff.data = gfu.vec - gfu2.vec
+    out.update(rel_diff=Norm(diff) / Norm(gfu.vec))
+
+    # ---- fused device solver (same interface as ngscuda.DevCGSolver)
+    fused = _ngsb200.DevCGSolver(adev, jdev, maxsteps=20000, precision=1e-8)
+    res3 = (fused * fdev).Evaluate()
+    t0 = time.perf_counter()
+    res3 = (fused * fdev).Evaluate()
+    out.update(fused_steps=fused.GetSteps(), fused_solve_s=time.perf_counter() - t0)
+    gfu2.vec.data = res3
+    diff.data = gfu.vec - gfu2.vec
+    out.update(fused_rel_diff=Norm(diff) / Norm(gfu.vec))
+    # ---- block Jacobi (the tutorial's second device example): BlockJacobiPrecond -> DevBlockJacobiMatrix
+    blocks = fes.CreateSmoothingBlocks()
+    bj = a.mat.CreateBlockSmoother(blocks)
+    invb = CGSolver(a.mat, bj, precision=1e-8, maxsteps=20000)
+    t0 = time.perf_counter()
+    gfu.vec.data = invb * f.vec
+    out.update(bj_cpu_steps=invb.GetSteps(), bj_cpu_solve_s=time.perf_counter() - t0)
+    bjdev = bj.CreateDeviceMatrix()
+    invbd = CGSolver(adev, bjdev, precision=1e-8, maxsteps=20000)
+    res4 = (invbd * fdev).Evaluate()
+    t0 = time.perf_counter()
+    res4 = (invbd * fdev).Evaluate()
+    out.update(bj_dev_steps=invbd.GetSteps(), bj_dev_solve_s=time.perf_counter() - t0, bj_type=type(bjdev).__name__)
+    gfu2.vec.data = res4
+    diff.data = gfu.vec - gfu2.vec
+    out.update(bj_rel_diff=Norm(diff) / Norm(gfu.vec))
+print(json.dumps(out))

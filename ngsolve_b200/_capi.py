@@ -77,6 +77,7 @@ PROTOTYPES = {
     "ngsb_csr_create_symmetric": [_vp, _sz, _sz, _vp, _vp, _vp, _i, _pvp],
     "ngsb_csr_multadd_multi": [_vp, _sz, _vp, _vp, _vp],
     "ngsb_blockjacobi_create": [_vp, _sz, _vp, _vp, _pvp],
+    "ngsb_blockjacobi_create_from_inverses": [_vp, _sz, _sz, _vp, _vp, _vp, _pvp],
     "ngsb_blockjacobi_destroy": [_vp],
     "ngsb_blockjacobi_info": [_vp, C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_sz)],
     "ngsb_blockjacobi_download": [_vp, _vp],

@@ -219,17 +219,15 @@ static void bj_free(ngsb_blockjacobi *J)
     delete J;
 }
 
-extern "C" int ngsb_blockjacobi_create(const ngsb_csr *A, size_t nblocks, const uint64_t *first, const int32_t *dofs,
-                                       ngsb_blockjacobi **out)
+// A != NULL: build the block matrices from the device matrix and invert them here; A == NULL: `inverses` (host, blocks back
+// to back, row-major) were computed by the caller (the reference's BlockJacobiPrecond::GetInverses) and are uploaded.
+static int bj_build(ngsb_ctx *ctx, size_t ndof, const ngsb_csr *A, const double *inverses, size_t nblocks, const uint64_t *first,
+                    const int32_t *dofs, ngsb_blockjacobi **out)
 {
-    NGSB_REQUIRE(A && out && (nblocks == 0 || (first && dofs)), "ngsb_blockjacobi_create: NULL argument");
-    NGSB_REQUIRE(A->kind == NGSB_REAL, "BlockJacobiPrecond: only TM = double is supported on the device (as in ngscuda/dev_blockjacobi.cpp:38)");
-    NGSB_REQUIRE(A->h == A->w, "BlockJacobiPrecond: matrix must be square (%zu x %zu)", A->h, A->w);
-    ngsb_ctx *ctx = A->ctx;
     NGSB_CUDA(cudaSetDevice(ctx->device));
     const size_t total = nblocks ? (size_t)first[nblocks] : 0;
     NGSB_REQUIRE(nblocks == 0 || first[0] == 0, "BlockJacobiPrecond: block table must start at 0");
-    std::vector<uint64_t> moff(nblocks + 1, 0), dfirst(A->h + 1, 0), dslot(total);
+    std::vector<uint64_t> moff(nblocks + 1, 0), dfirst(ndof + 1, 0), dslot(total);
     std::vector<uint32_t> slot_block(total);
     uint32_t maxbs = 0;
     for (size_t b = 0; b < nblocks; b++) {
@@ -239,18 +237,18 @@ extern "C" int ngsb_blockjacobi_create(const ngsb_csr *A, size_t nblocks, const 
         moff[b + 1] = moff[b] + bs * bs;
         if (bs > maxbs) maxbs = (uint32_t)bs;
         for (uint64_t k = first[b]; k < first[b + 1]; k++) {
-            NGSB_REQUIRE(dofs[k] >= 0 && (size_t)dofs[k] < A->h, "BlockJacobiPrecond: dof %d of block %zu out of range [0,%zu)", dofs[k], b, A->h);
+            NGSB_REQUIRE(dofs[k] >= 0 && (size_t)dofs[k] < ndof, "BlockJacobiPrecond: dof %d of block %zu out of range [0,%zu)", dofs[k], b, ndof);
             dfirst[(size_t)dofs[k] + 1]++;
             slot_block[k] = (uint32_t)b;
         }
     }
-    for (size_t d = 0; d < A->h; d++) dfirst[d + 1] += dfirst[d];
+    for (size_t d = 0; d < ndof; d++) dfirst[d + 1] += dfirst[d];
     {
         std::vector<uint64_t> fill(dfirst.begin(), dfirst.end() - 1);
         for (size_t k = 0; k < total; k++) dslot[fill[(size_t)dofs[k]]++] = k;      // ascending slot = ascending block per dof
     }
     ngsb_blockjacobi *J = new ngsb_blockjacobi();
-    J->ctx = ctx; J->n = A->h; J->nblocks = nblocks; J->total = total; J->mtotal = (size_t)moff[nblocks]; J->maxbs = maxbs;
+    J->ctx = ctx; J->n = ndof; J->nblocks = nblocks; J->total = total; J->mtotal = (size_t)moff[nblocks]; J->maxbs = maxbs;
     uint32_t *d_slot_block = nullptr;
     int *d_status = nullptr, *d_perm = nullptr;
     double *d_colws = nullptr;
@@ -262,7 +260,7 @@ extern "C" int ngsb_blockjacobi_create(const ngsb_csr *A, size_t nblocks, const 
     cu(cudaMalloc(&J->d_dofs, std::max<size_t>(1, total) * sizeof(int32_t)));
     cu(cudaMalloc(&J->d_inv, std::max<size_t>(1, J->mtotal) * sizeof(double)));
     cu(cudaMalloc(&J->d_tmp, std::max<size_t>(1, total) * sizeof(double)));
-    cu(cudaMalloc(&J->d_dfirst, (A->h + 1) * sizeof(uint64_t)));
+    cu(cudaMalloc(&J->d_dfirst, (ndof + 1) * sizeof(uint64_t)));
     cu(cudaMalloc(&J->d_dslot, std::max<size_t>(1, total) * sizeof(uint64_t)));
     cu(cudaMalloc(&d_slot_block, std::max<size_t>(1, total) * sizeof(uint32_t)));
     cu(cudaMalloc(&d_status, std::max<size_t>(1, nblocks) * sizeof(int)));
@@ -272,7 +270,7 @@ extern "C" int ngsb_blockjacobi_create(const ngsb_csr *A, size_t nblocks, const 
         uint64_t zero = 0;
         cu(cudaMemcpyAsync(J->d_first, nblocks ? first : &zero, (nblocks + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
         cu(cudaMemcpyAsync(J->d_moff, moff.data(), (nblocks + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
-        cu(cudaMemcpyAsync(J->d_dfirst, dfirst.data(), (A->h + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+        cu(cudaMemcpyAsync(J->d_dfirst, dfirst.data(), (ndof + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
         if (total) {
             cu(cudaMemcpyAsync(J->d_dofs, dofs, total * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
             cu(cudaMemcpyAsync(J->d_dslot, dslot.data(), total * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
@@ -281,7 +279,17 @@ extern "C" int ngsb_blockjacobi_create(const ngsb_csr *A, size_t nblocks, const 
         cu(cudaMemsetAsync(J->d_inv, 0, std::max<size_t>(1, J->mtotal) * sizeof(double), ctx->stream));
         cu(cudaMemsetAsync(d_status, 0, std::max<size_t>(1, nblocks) * sizeof(int), ctx->stream));
     }
-    if (rc == NGSB_OK && total) {
+    if (rc == NGSB_OK && total && !A) {
+        // inverses from the host: row-major -> the column-major device layout
+        std::vector<double> cm((size_t)moff[nblocks]);
+        for (size_t b = 0; b < nblocks; b++) {
+            const size_t bs = (size_t)(first[b + 1] - first[b]), off = (size_t)moff[b];
+            for (size_t r = 0; r < bs; r++)
+                for (size_t c = 0; c < bs; c++) cm[off + c * bs + r] = inverses[off + r * bs + c];
+        }
+        cu(cudaMemcpyAsync(J->d_inv, cm.data(), cm.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        cu(cudaStreamSynchronize(ctx->stream));
+    } else if (rc == NGSB_OK && total) {
         const size_t threads = total * 32;
         bj_extract_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, ctx->stream>>>(A->d_rowptr, A->d_col, A->d_val, J->d_first, J->d_moff,
                                                                                       J->d_dofs, d_slot_block, total, J->d_inv);
@@ -302,6 +310,23 @@ extern "C" int ngsb_blockjacobi_create(const ngsb_csr *A, size_t nblocks, const 
     if (rc != NGSB_OK) { bj_free(J); return rc; }
     *out = J;
     return NGSB_OK;
+}
+
+extern "C" int ngsb_blockjacobi_create(const ngsb_csr *A, size_t nblocks, const uint64_t *first, const int32_t *dofs,
+                                       ngsb_blockjacobi **out)
+{
+    NGSB_REQUIRE(A && out && (nblocks == 0 || (first && dofs)), "ngsb_blockjacobi_create: NULL argument");
+    NGSB_REQUIRE(A->kind == NGSB_REAL, "BlockJacobiPrecond: only TM = double is supported on the device (as in ngscuda/dev_blockjacobi.cpp:38)");
+    NGSB_REQUIRE(A->h == A->w, "BlockJacobiPrecond: matrix must be square (%zu x %zu)", A->h, A->w);
+    return bj_build(A->ctx, A->h, A, nullptr, nblocks, first, dofs, out);
+}
+
+extern "C" int ngsb_blockjacobi_create_from_inverses(ngsb_ctx *ctx, size_t n, size_t nblocks, const uint64_t *first, const int32_t *dofs,
+                                                     const double *inverses, ngsb_blockjacobi **out)
+{
+    NGSB_REQUIRE(ctx && out && (nblocks == 0 || (first && dofs)), "ngsb_blockjacobi_create_from_inverses: NULL argument");
+    NGSB_REQUIRE(inverses || nblocks == 0 || first[nblocks] == 0, "ngsb_blockjacobi_create_from_inverses: inverses is NULL");
+    return bj_build(ctx, n, nullptr, inverses, nblocks, first, dofs, out);
 }
 
 extern "C" int ngsb_blockjacobi_destroy(ngsb_blockjacobi *J)

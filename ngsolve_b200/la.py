@@ -1073,13 +1073,21 @@ class BlockJacobiPrecond(BaseMatrix):
 class DevBlockJacobiMatrix(BaseMatrix):
     """DevBlockJacobiMatrix (ngscuda/dev_blockjacobi.cpp:21-140): y(block) += s * inv(A(block,block)) * x(block)."""
 
-    def __init__(self, devmat, blocks):
-        self.ctx = devmat.ctx
+    def __init__(self, devmat, blocks, inverses=None, n=None, ctx=None):
         first, dofs = _block_table(blocks)
         h = C.c_void_p()
-        check(_capi.lib().ngsb_blockjacobi_create(devmat.handle, len(first) - 1, _np_ptr(first), _np_ptr(dofs) if len(dofs) else None, C.byref(h)))
+        if inverses is None:
+            self.ctx = devmat.ctx
+            check(_capi.lib().ngsb_blockjacobi_create(devmat.handle, len(first) - 1, _np_ptr(first), _np_ptr(dofs) if len(dofs) else None, C.byref(h)))
+            self.height = self.width = devmat.height
+        else:
+            # inverse blocks computed elsewhere (list of row-major matrices), e.g. the reference's GetInverses()
+            self.ctx = ctx or (devmat.ctx if devmat is not None else default_context())
+            flat = np.ascontiguousarray(np.concatenate([np.asarray(m, dtype=np.float64).reshape(-1) for m in inverses] or [np.zeros(1)]))
+            self.height = self.width = int(n if n is not None else devmat.height)
+            check(_capi.lib().ngsb_blockjacobi_create_from_inverses(self.ctx.handle, self.height, len(first) - 1, _np_ptr(first),
+                                                                    _np_ptr(dofs) if len(dofs) else None, _np_ptr(flat), C.byref(h)))
         self.handle = h
-        self.height = self.width = devmat.height
         self.is_complex, self.entrysize = False, 1
         self.first, self.dofs = first, dofs
         self._fin = weakref.finalize(self, _capi.lib().ngsb_blockjacobi_destroy, h)

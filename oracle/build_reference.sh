@@ -13,6 +13,8 @@ REF=${REF:-/root/reference}
 PFX=${PFX:-$HERE/_ref/ngs}
 BUILD=${BUILD:-/tmp/ngsbuild}
 JOBS=${JOBS:-6}
+# portable instruction set (the GPU box's host CPU is not this container's): x86-64-v3 = AVX2+FMA, no -march=native
+ARCH=${ARCH:--march=x86-64-v3}
 LIBS=$(python -c "import os,cv2;print(os.path.join(os.path.dirname(os.path.dirname(cv2.__file__)),'opencv_python_headless.libs'))" 2>/dev/null \
        || echo /opt/prime-rl/.venv/lib/python3.12/site-packages/opencv_python_headless.libs)
 OPENBLAS=$(ls $LIBS/libopenblasp-*.so | head -1)
@@ -38,13 +40,13 @@ NETGEN=$REF/external_dependencies/netgen
 if [ ! -f "$PFX/lib/cmake/netgen/NetgenConfig.cmake" ]; then
     cmake -S "$NETGEN" -B "$BUILD/netgen" -G Ninja -DUSE_SUPERBUILD=OFF -DUSE_GUI=OFF -DUSE_OCC=OFF -DUSE_PYTHON=ON \
           -DUSE_MPI=OFF -DBUILD_STUB_FILES=OFF -DCMAKE_BUILD_TYPE=Release -DCMAKE_INSTALL_PREFIX="$PFX" \
-          -DNETGEN_VERSION_GIT=v6.2.2506-0-g0000000
+          -DUSE_NATIVE_ARCH=OFF "-DCMAKE_CXX_FLAGS=$ARCH" -DNETGEN_VERSION_GIT=v6.2.2506-0-g0000000
     ninja -C "$BUILD/netgen" -j"$JOBS" install
 fi
 PYBIND_INC=$NETGEN/external_dependencies/pybind11/include
 cmake -S "$NGSRC" -B "$BUILD/ngsolve" -G Ninja -DUSE_SUPERBUILD=OFF -DNetgen_DIR="$PFX/lib/cmake/netgen" -DUSE_UMFPACK=OFF \
       -DUSE_MKL=OFF -DUSE_CUDA=OFF -DBUILD_STUB_FILES=OFF -DCMAKE_BUILD_TYPE=Release -DCMAKE_INSTALL_PREFIX="$PFX" \
-      -DCMAKE_CXX_FLAGS=-I$PYBIND_INC -DUSE_LAPACK=ON "-DLAPACK_LIBRARIES=$OPENBLAS;$GFORTRAN;$QUADMATH"
+      "-DCMAKE_CXX_FLAGS=-I$PYBIND_INC $ARCH" -DUSE_NATIVE_ARCH=OFF -DUSE_LAPACK=ON "-DLAPACK_LIBRARIES=$OPENBLAS;$GFORTRAN;$QUADMATH"
 ninja -C "$BUILD/ngsolve" -j"$JOBS" install
 cat > "$PFX/env.sh" <<EOF
 # source this: the reference build of oracle/build_reference.sh

@@ -55,6 +55,10 @@ def test_inverses_and_products_match_the_oracle():
     y = la.BaseVector(y0)
     bj.MultTransAdd(2.5, xv, y)
     assert _rel(y.NumPy(), obj.multadd(2.5, x, y0.copy(), transpose=True)) <= 1e-12
+    # the same preconditioner from inverses computed elsewhere (the adapter's path: BlockJacobiPrecond::GetInverses)
+    bj2 = la.DevBlockJacobiMatrix(None, blocks, inverses=obj.inverses(), n=n)
+    bj2.Mult(xv, y)
+    assert _rel(y.NumPy(), obj.mult(x)) <= 1e-13
     # deterministic: no atomics on the path
     y1, y2 = bj.CreateColVector(), bj.CreateColVector()
     bj.Mult(xv, y1)

@@ -14,7 +14,7 @@ timeout 300 python bench.py --impl reference > $O/${TAG}_bench_reference_arm.jso
 timeout 900 python tools/bench_configs.py c1 c2 c4 c5 --out $O/${TAG}_configs.jsonl > $O/${TAG}_configs.log 2>&1; tail -5 $O/${TAG}_configs.log
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${TAG}_ncu_launches_bench_n1.csv \
     python bench.py --steps 10 --warmup 3 --no-full-solve --no-cpu-baseline > $O/${TAG}_ncu_launches.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:sell_spmv -s 20 -c 2 -f -o $O/${TAG}_prof_sell_bench \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:sell_spmv -s 1 -c 2 -f -o $O/${TAG}_prof_sell_bench \
     python bench.py --steps 10 --warmup 3 --no-full-solve --no-cpu-baseline > $O/${TAG}_ncu_full.log 2>&1
 ncu -i $O/${TAG}_prof_sell_bench.ncu-rep --page raw --csv > $O/${TAG}_prof_sell_bench_raw.csv 2>/dev/null
 ls -la $O
