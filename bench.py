@@ -319,6 +319,7 @@ def run_b200(args):
     ctx.set_option("timing", 0)
     b_spmv = A.MultBytes()                                  # nnz*12 + 4h + 8h + 8h
     sell_entries, sell_ovf, sell_cap = A.Layout()
+    stream_bytes, c16_entries = A.StreamBytes()          # what the kernel streams as stored (16-bit column offsets where possible)
     # exactly K launches do work; the rest of the last batch returns at once on the device-side `done` flag
     # (a few microseconds each), so the class total divided by K is the per-launch duration
     t_spmv = spmv_ms / K * 1e-3
@@ -406,7 +407,11 @@ def run_b200(args):
                        "sell_padding": sell_entries / max(1, nnz_local) - 1.0, "sell_overflow_rows": sell_ovf},
             "roofline": {"bound": "hbm", "kernel": "sell_spmv_kernel (SELL-32 SpMV + fused <s,As> + CG alpha step)", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": b_spmv, "avg_launch_ms": t_spmv * 1e3, "launches_timed": K, "launches_enqueued": spmv_n,
+                         "algorithmic_bytes_per_launch": b_spmv, "stored_bytes_per_launch": stream_bytes,
+                         "achieved_on_stored_bytes": stream_bytes / t_spmv / 1e9,
+                         "c16_share_of_entries": c16_entries / max(1, sell_entries),
+                         "note": "achieved/frac use the ALGORITHMIC bytes of SURVEY 8d (12 B per entry); the kernel stores 16-bit column "
+                                 "offsets for most slices and streams stored_bytes_per_launch, which is why frac can exceed the copy peak", "avg_launch_ms": t_spmv * 1e3, "launches_timed": K, "launches_enqueued": spmv_n,
                          "kernel_share_of_step": spmv_ms / all_ms if all_ms else None,
                          "cg_update_kernels_ms_per_iteration": upd_ms / K},
             "cpu_baseline": cpu,

@@ -155,6 +155,10 @@ int ngsb_csr_download(const ngsb_csr *A, uint64_t *rowptr, int32_t *col, void *v
 /* device layout diagnostics: padded entries of the SELL-32 copy the default SpMV kernel streams,
  * rows with an overflow part, and the per-row cap of the slices.  Any pointer may be NULL. */
 int ngsb_csr_layout(const ngsb_csr *A, uint64_t *sell_entries, uint32_t *overflow_rows, uint32_t *cap);
+/* bytes the default kernel streams per Mult with the layout as stored (padding included; real matrices
+ * store 16-bit column offsets per slice where the columns of one entry step lie within 65535 of each
+ * other: 10.125 instead of 12 bytes per entry); *c16_entries = padded entries in such slices */
+int ngsb_csr_stream_bytes(const ngsb_csr *A, double *bytes, uint64_t *c16_entries);
 /* algorithmic bytes of one Mult: nnz*(b*b*S+4) + 4*h + 2*N*S */
 int ngsb_csr_mult_bytes(const ngsb_csr *A, double *bytes);
 

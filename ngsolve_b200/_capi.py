@@ -65,6 +65,7 @@ PROTOTYPES = {
     "ngsb_csr_reorder": [_vp, _vp, _pvp],
     "ngsb_csr_download": [_vp, _vp, _vp, _vp],
     "ngsb_csr_mult_bytes": [_vp, C.POINTER(_d)],
+    "ngsb_csr_stream_bytes": [_vp, C.POINTER(_d), C.POINTER(C.c_uint64)],
     "ngsb_csr_layout": [_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)],
     "ngsb_jacobi_create": [_vp, _sz, _vp, _i, _vp, _pvp],
     "ngsb_jacobi_create_from_csr": [_vp, _vp, _pvp],

@@ -911,6 +911,20 @@ extern "C" int ngsb_csr_layout(const ngsb_csr *A, uint64_t *sell_entries, uint32
     return NGSB_OK;
 }
 
+// bytes the default (SELL) kernel streams per Mult with the layout as stored: padded entries, 16-bit column offsets
+// where a slice allows them (8 + 2 + 4/32 bytes per entry instead of 12), slot -> row table, x once, y once
+extern "C" int ngsb_csr_stream_bytes(const ngsb_csr *A, double *bytes, uint64_t *c16_entries)
+{
+    NGSB_REQUIRE(A && bytes, "ngsb_csr_stream_bytes: NULL argument");
+    const double S = A->kind == NGSB_COMPLEX ? 16.0 : 8.0;
+    const double b = A->kind == NGSB_BLOCK3 ? 3.0 : 1.0;
+    const double per_entry = b * b * S + 4.0;
+    const double c16 = (double)A->sell_c16_entries, rest = (double)A->sell_entries - c16;
+    *bytes = c16 * (8.0 + 2.0 + 4.0 / 32.0) + rest * per_entry + 4.0 * (double)A->h + (double)(A->w + A->h) * b * S;
+    if (c16_entries) *c16_entries = A->sell_c16_entries;
+    return NGSB_OK;
+}
+
 extern "C" int ngsb_csr_mult_bytes(const ngsb_csr *A, double *bytes)
 {
     NGSB_REQUIRE(A && bytes, "ngsb_csr_mult_bytes: NULL argument");

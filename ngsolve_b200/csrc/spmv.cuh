@@ -43,6 +43,10 @@ struct ngsb_csr {
     uint32_t *d_ovf_slot = nullptr;
     int32_t *d_scol = nullptr;
     double *d_sval = nullptr;
+    uint16_t *d_scol16 = nullptr;      // 16-bit column offsets of the compressed slices (real matrices)
+    int32_t *d_sbase = nullptr;        // per (slice, entry step) base column
+    uint8_t *d_slice_c16 = nullptr;    // per scheduled slice: compressed?
+    uint64_t sell_c16_entries = 0;     // padded entries living in compressed slices
     uint32_t novf = 0;
     uint32_t *d_ovf_rows = nullptr;
     uint64_t *d_ovf_ptr = nullptr;

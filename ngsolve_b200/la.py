@@ -889,6 +889,12 @@ class DevSparseMatrix(BaseMatrix):
         check(_capi.lib().ngsb_csr_layout(self.handle, C.byref(e), C.byref(o), C.byref(c)))
         return e.value, o.value, c.value
 
+    def StreamBytes(self):
+        """(bytes the SELL kernel streams per Mult as stored, padded entries held with 16-bit column offsets)"""
+        b, c = C.c_double(), C.c_uint64()
+        check(_capi.lib().ngsb_csr_stream_bytes(self.handle, C.byref(b), C.byref(c)))
+        return b.value, c.value
+
     def MultBytes(self):
         b = C.c_double()
         check(_capi.lib().ngsb_csr_mult_bytes(self.handle, C.byref(b)))

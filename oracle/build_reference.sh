@@ -48,9 +48,11 @@ cmake -S "$NGSRC" -B "$BUILD/ngsolve" -G Ninja -DUSE_SUPERBUILD=OFF -DNetgen_DIR
       -DUSE_MKL=OFF -DUSE_CUDA=OFF -DBUILD_STUB_FILES=OFF -DCMAKE_BUILD_TYPE=Release -DCMAKE_INSTALL_PREFIX="$PFX" \
       "-DCMAKE_CXX_FLAGS=-I$PYBIND_INC $ARCH" -DUSE_NATIVE_ARCH=OFF -DUSE_LAPACK=ON "-DLAPACK_LIBRARIES=$OPENBLAS;$GFORTRAN;$QUADMATH"
 ninja -C "$BUILD/ngsolve" -j"$JOBS" install
-cat > "$PFX/env.sh" <<EOF
-# source this: the reference build of oracle/build_reference.sh
-export PYTHONPATH=$PFX/lib/python3.12/site-packages\${PYTHONPATH:+:\$PYTHONPATH}
-export LD_LIBRARY_PATH=$PFX/lib:$LIBS\${LD_LIBRARY_PATH:+:\$LD_LIBRARY_PATH}
-EOF
+cat > "$PFX/env.sh" <<'ENVEOF'
+# source this: the reference build of oracle/build_reference.sh (paths relative to this file, so that it works on the GPU box)
+_NGS_PFX="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
+_NGS_LIBS=$(python -c "import os,importlib.util as u;s=u.find_spec('cv2');print(os.path.join(os.path.dirname(os.path.dirname(s.origin)),'opencv_python_headless.libs'))")
+export PYTHONPATH=$_NGS_PFX/lib/python3.12/site-packages${PYTHONPATH:+:$PYTHONPATH}
+export LD_LIBRARY_PATH=$_NGS_PFX/lib:$_NGS_PFX/lib/python3.12/site-packages/netgen:$_NGS_LIBS${LD_LIBRARY_PATH:+:$LD_LIBRARY_PATH}
+ENVEOF
 echo "reference installed under $PFX"

@@ -122,3 +122,37 @@ def test_elasticity_cg_and_helmholtz_gmres_match_oracle_on_generated_systems(mod
     ox, osteps, _ = orc.gmres_solve(oAc, orc.Jacobi(oAc, freec.bytes), rhs, prec=1e-8, maxsteps=150)
     assert abs(g.GetSteps() - osteps) <= 2, (g.GetSteps(), osteps)
     assert np.max(np.abs(x - ox)) <= 1e-6 * np.max(np.abs(ox))
+
+
+def test_c16_column_compression_is_bit_exact_and_partial():
+    """16-bit column offsets (SELL slices whose entry steps span < 65536 columns) change the bytes streamed, not the
+    arithmetic: products with and without are bit-identical; on a grid whose plane stride exceeds 65535 dofs some slices
+    must keep their 32-bit columns"""
+    import ngsolve_b200.la as la
+    from ngsolve_b200 import workloads as W
+    ctx = la.default_context()
+    box = W.FemBox((88, 88, 3), order=3)            # plane stride (3*88+1)^2 = 70 225 > 65 535
+    rng = np.random.default_rng(5)
+    ys = []
+    for c16 in (1, 0):
+        ctx.set_option("sell_c16", c16)
+        A, f = box.device_system(ctx)
+        x = la.BaseVector(rng.random(A.height) if not ys else xs, ctx=ctx)
+        xs = x.NumPy().copy()
+        y = A.CreateColVector()
+        A.Mult(x, y)
+        sb, n16 = A.StreamBytes()
+        ent = A.Layout()[0]
+        if c16:
+            assert 0 < n16 < ent and n16 > 0.5 * ent
+            assert sb < A.MultBytes() * 1.02
+        else:
+            assert n16 == 0
+        ys.append(y.NumPy().copy())
+        inv = la.CGSolver(A, A.CreateSmoother(box.freedofs()), precision=1e-8, maxsteps=500)
+        u = f.CreateVector()
+        inv.Mult(f, u)
+        ys.append(u.NumPy().copy())
+        ys.append(inv.GetSteps())
+    ctx.set_option("sell_c16", 1)
+    assert np.array_equal(ys[0], ys[3]) and np.array_equal(ys[1], ys[4]) and ys[2] == ys[5]

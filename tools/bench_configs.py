@@ -96,9 +96,11 @@ def run(cfg, scale):
     b = A.MultBytes()
     gbs = b / ms / 1e6
     ent, ovf, cap = A.Layout()
+    sb, c16 = A.StreamBytes()
     out = dict(config=name, rows=A.height, scalars=A.height * es * (2 if cplx else 1), nnz=A.nze, entry="complex" if cplx else ("3x3" if es == 3 else "real"),
                spmv_ms=ms, spmv_bytes=b, spmv_gbs=gbs, spmv_frac_of_measured_peak=gbs / peak(), spmv_pct_of_8TBs=gbs / 80.0,
-               sell_padding=ent / max(1, A.nze) - 1.0, sell_overflow_rows=ovf, setup_s=setup)
+               sell_padding=ent / max(1, A.nze) - 1.0, sell_overflow_rows=ovf, setup_s=setup,
+               stored_bytes=sb, spmv_gbs_on_stored_bytes=sb / ms / 1e6, c16_share_of_entries=c16 / max(1, ent))
     u = f.CreateVector()
     K = cfg["steps"]
     if cfg["solver"] == "cg":
