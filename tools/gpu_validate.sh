@@ -13,7 +13,7 @@ timeout 600 python bench.py > $O/${TAG}_bench_n1.json 2> $O/${TAG}_bench_n1.err;
 timeout 300 python bench.py --impl reference > $O/${TAG}_bench_reference_arm.json 2> $O/${TAG}_bench_ref.err; cat $O/${TAG}_bench_reference_arm.json
 timeout 900 python tools/bench_configs.py c1 c2 c4 c5 --out $O/${TAG}_configs.jsonl > $O/${TAG}_configs.log 2>&1; tail -5 $O/${TAG}_configs.log
 if [ -f oracle/_ref/ngs/env.sh ] && ls integration/_build/_ngsb200*.so >/dev/null 2>&1; then
-    ( source oracle/_ref/ngs/env.sh; timeout 900 python integration/run_ngsolve_dropin.py --maxh 0.04 > $O/${TAG}_dropin.json 2> $O/${TAG}_dropin.err ); cat $O/${TAG}_dropin.json; tail -3 $O/${TAG}_dropin.err
+    ( source oracle/_ref/ngs/env.sh; timeout 900 python integration/run_ngsolve_dropin.py --maxh 0.03 > $O/${TAG}_dropin.json 2> $O/${TAG}_dropin.err ); cat $O/${TAG}_dropin.json; tail -3 $O/${TAG}_dropin.err
 fi
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${TAG}_ncu_launches_bench_n1.csv \
     python bench.py --steps 10 --warmup 3 --no-full-solve --no-cpu-baseline > $O/${TAG}_ncu_launches.log 2>&1
