@@ -39,6 +39,8 @@ struct SellParams {
     const uint16_t *scol16;       // 16-bit column offsets (same indexing as scol) of the compressed slices, or NULL
     const int32_t *sbase;         // per (slice, entry step j): smallest column of the 32 lanes, index slice_off/32 + j
     const uint8_t *slice_c16;     // per scheduled slice: 1 = columns are sbase + scol16
+    int pf_steps;                 // compressed slices: L2 prefetch distance inside a slice in steps of 4 packets (0 = off)
+    int pf_next;                  // compressed slices: packets of the warp's NEXT slice prefetched into L2 at slice start (0 = off)
     const int32_t *slice_ovf;     // per slice: first overflow entry of this slice or -1 (NULL: none)
     const uint32_t *ovf_slot;     // slots of the rows with an overflow part, ascending
     const double *ovf_sum;        // raw overflow sums, es doubles per overflow row
@@ -88,6 +90,8 @@ __device__ __forceinline__ unsigned int ldg_stream_u32(const unsigned int *p)
     return v;
 }
 
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 __device__ __forceinline__ double warp_sum_s(double v)
 {
 #pragma unroll
@@ -120,6 +124,21 @@ __global__ void __launch_bounds__(256, MINB) sell_spmv_kernel(const SellParams p
             const int2 *b2 = reinterpret_cast<const int2 *>(p.sbase + (off >> 5));
             const uint32_t np = width >> 1;
             uint32_t q = 0;
+            if (p.pf_next > 0) {
+                // the compressed stream carries fewer bytes per dependent step, so the loads of one step no longer cover the DRAM
+                // latency: pull the head of this warp's next slice into L2 now (lane l fetches its own 128-byte line)
+                const uint64_t sn = s + (uint64_t)gridDim.x * 8;
+                if (sn < p.nslices) {
+                    const uint64_t offn = p.slice_off[sn];
+                    const uint32_t npn = min((uint32_t)((p.slice_off[sn + 1] - offn) >> 6), (uint32_t)p.pf_next);
+                    const char *vn = reinterpret_cast<const char *>(p.sval + offn);
+                    const char *hn = reinterpret_cast<const char *>(p.scol16 + offn);
+                    for (uint32_t l = lane; l < npn * 4; l += 32) prefetch_l2(vn + (size_t)l * 128);      // 512 B of values per packet
+                    if ((uint32_t)lane < npn) prefetch_l2(hn + (size_t)lane * 128);                        // 128 B of offsets per packet
+                    if (lane == 0) prefetch_l2(p.sbase + (offn >> 5));
+                }
+            }
+            const uint32_t pfd = (uint32_t)p.pf_steps * 4;
 #define NGSB_C16(h, b, c0, c1) { c0 = (b).x + (int)((h) & 0xffffu); c1 = (b).y + (int)((h) >> 16); }
             if (np >= 4) {
                 double2 va = ldg_stream_d2(v2), vb = ldg_stream_d2(v2 + 32), vc = ldg_stream_d2(v2 + 64), vd = ldg_stream_d2(v2 + 96);
@@ -132,6 +151,11 @@ __global__ void __launch_bounds__(256, MINB) sell_spmv_kernel(const SellParams p
                 for (q = 4; q + 4 <= np; q += 4) {
                     double x0 = __ldg(p.x + ca0), x1 = __ldg(p.x + ca1), x2 = __ldg(p.x + cb0), x3 = __ldg(p.x + cb1);
                     double x4 = __ldg(p.x + cc0), x5 = __ldg(p.x + cc1), x6 = __ldg(p.x + cd0), x7 = __ldg(p.x + cd1);
+                    if (pfd && q + pfd + 4 <= np) {
+                        // 2 KB of values = 16 lines (lanes 0-15), 512 B of offsets = 4 lines (lanes 16-19) of the step `pf_steps` ahead
+                        if (lane < 16) prefetch_l2(reinterpret_cast<const char *>(p.sval + off) + (size_t)(q + pfd) * 512 + lane * 128);
+                        else if (lane < 20) prefetch_l2(reinterpret_cast<const char *>(p.scol16 + off) + (size_t)(q + pfd) * 128 + (lane - 16) * 128);
+                    }
                     double2 na = ldg_stream_d2(v2 + (q + 0) * 32), nb = ldg_stream_d2(v2 + (q + 1) * 32);
                     double2 nc = ldg_stream_d2(v2 + (q + 2) * 32), nd = ldg_stream_d2(v2 + (q + 3) * 32);
                     const unsigned int ha = ldg_stream_u32(h2 + (q + 0) * 32), hb = ldg_stream_u32(h2 + (q + 1) * 32);
@@ -800,6 +824,8 @@ int sell_launch(const SpmvArgs &a)
     p.ovf_slot = A->d_ovf_slot; p.ovf_sum = A->d_ovf_sum; p.novf = A->novf;
     p.nslices = A->nslices; p.nrows = A->h;
     if (A->sell_c16_entries > 0 && ctx->sell_c16 != 0) { p.scol16 = A->d_scol16; p.sbase = A->d_sbase; p.slice_c16 = A->d_slice_c16; }
+    p.pf_steps = (int)ctx->sell_pf_steps;
+    p.pf_next = (int)ctx->sell_pf_next;
     p.x = a.x; p.y = a.y; p.sr = a.sr; p.si = A->kind == NGSB_COMPLEX ? a.si : 0.0;
     p.accumulate = a.accumulate ? 1 : 0; p.epi = a.epi; p.dot_conj = a.dot_conj;
     p.dotvec = a.dotvec; p.dot_out = a.dot_out; p.state = a.state;
