@@ -82,10 +82,30 @@ namespace ngla
       UpdateHost(); dev_uptodate = false; return FlatVector<Complex> (this->size * EntryScalars(), (Complex*)host.Data());
     }
 
-    static const B200Vector & Cast (const BaseVector & v)
+    // a read-only operand: a device vector as it is, a host vector through a temporary upload (what
+    // UnifiedVectorWrapper does, ngscuda/unifiedvector.hpp:100-136; `*dev = hostvec` in CreateDeviceVector(copy=True),
+    // linalg/python_linalg.cpp:656-662, arrives here as Set(1.0, hostvec))
+    struct Operand
     {
-      auto p = dynamic_cast<const B200Vector*> (&v);
-      if (!p) throw Exception ("B200Vector: operand is not a device vector (use CreateDeviceVector)");
+      const B200Vector * p;
+      std::unique_ptr<B200Vector> tmp;
+      ngsb_vec * Dev () const { return p->Dev(); }
+    };
+    static Operand Cast (const BaseVector & v)
+    {
+      if (auto p = dynamic_cast<const B200Vector*> (&v)) return Operand { p, nullptr };
+      if (v.IsComplex() != std::is_same_v<SCAL,Complex>) throw Exception ("B200Vector: real/complex mismatch of operands");
+      auto t = std::make_unique<B200Vector> (v.Size(), v.EntrySize() / (v.IsComplex() ? 2 : 1));
+      Check (ngsb_vec_h2d (t->dev, v.Memory(), 0, v.Size()));
+      t->host_uptodate = false; t->dev_uptodate = true;
+      const B200Vector * q = t.get();
+      return Operand { q, std::move(t) };
+    }
+    // a written operand must live on the device
+    static B200Vector & CastW (BaseVector & v)
+    {
+      auto p = dynamic_cast<B200Vector*> (&v);
+      if (!p) throw Exception ("B200Vector: result vector is not a device vector (use CreateDeviceVector / CreateColVector of the device matrix)");
       return *p;
     }
 
@@ -142,13 +162,13 @@ namespace ngla
     AutoVector CreateRowVector () const override { return make_unique<B200Vector<SCAL>> (w, es); }
     AutoVector CreateColVector () const override { return make_unique<B200Vector<SCAL>> (h, es); }
     void Mult (const BaseVector & x, BaseVector & y) const override
-    { Check (ngsb_csr_mult (A, B200Vector<SCAL>::Cast(x).Dev(), const_cast<B200Vector<SCAL>&>(B200Vector<SCAL>::Cast(y)).DevW())); }
+    { Check (ngsb_csr_mult (A, B200Vector<SCAL>::Cast(x).Dev(), B200Vector<SCAL>::CastW(y).DevW())); }
     void MultAdd (double s, const BaseVector & x, BaseVector & y) const override
-    { double z[2] = {s,0}; Check (ngsb_csr_multadd (A, z, B200Vector<SCAL>::Cast(x).Dev(), const_cast<B200Vector<SCAL>&>(B200Vector<SCAL>::Cast(y)).DevW())); }
+    { double z[2] = {s,0}; Check (ngsb_csr_multadd (A, z, B200Vector<SCAL>::Cast(x).Dev(), B200Vector<SCAL>::CastW(y).DevW())); }
     void MultAdd (Complex s, const BaseVector & x, BaseVector & y) const override
-    { double z[2] = {s.real(),s.imag()}; Check (ngsb_csr_multadd (A, z, B200Vector<SCAL>::Cast(x).Dev(), const_cast<B200Vector<SCAL>&>(B200Vector<SCAL>::Cast(y)).DevW())); }
+    { double z[2] = {s.real(),s.imag()}; Check (ngsb_csr_multadd (A, z, B200Vector<SCAL>::Cast(x).Dev(), B200Vector<SCAL>::CastW(y).DevW())); }
     void MultTransAdd (double s, const BaseVector & x, BaseVector & y) const override
-    { double z[2] = {s,0}; Check (ngsb_csr_multtransadd (A, z, B200Vector<SCAL>::Cast(x).Dev(), const_cast<B200Vector<SCAL>&>(B200Vector<SCAL>::Cast(y)).DevW())); }
+    { double z[2] = {s,0}; Check (ngsb_csr_multtransadd (A, z, B200Vector<SCAL>::Cast(x).Dev(), B200Vector<SCAL>::CastW(y).DevW())); }
   };
 
   // ---- Jacobi: replaces DevDiagonalMatrix built from JacobiPrecond<TM> (keeps the freedofs mask) ------
@@ -179,9 +199,9 @@ namespace ngla
     AutoVector CreateRowVector () const override { return make_unique<B200Vector<SCAL>> (n, es); }
     AutoVector CreateColVector () const override { return make_unique<B200Vector<SCAL>> (n, es); }
     void Mult (const BaseVector & x, BaseVector & y) const override
-    { Check (ngsb_jacobi_mult (J, B200Vector<SCAL>::Cast(x).Dev(), const_cast<B200Vector<SCAL>&>(B200Vector<SCAL>::Cast(y)).DevW())); }
+    { Check (ngsb_jacobi_mult (J, B200Vector<SCAL>::Cast(x).Dev(), B200Vector<SCAL>::CastW(y).DevW())); }
     void MultAdd (double s, const BaseVector & x, BaseVector & y) const override
-    { double z[2] = {s,0}; Check (ngsb_jacobi_multadd (J, z, B200Vector<SCAL>::Cast(x).Dev(), const_cast<B200Vector<SCAL>&>(B200Vector<SCAL>::Cast(y)).DevW())); }
+    { double z[2] = {s,0}; Check (ngsb_jacobi_multadd (J, z, B200Vector<SCAL>::Cast(x).Dev(), B200Vector<SCAL>::CastW(y).DevW())); }
   };
 
   // ---- block Jacobi: replaces DevBlockJacobiMatrix (ngscuda/dev_blockjacobi.cpp:21-140) --------------------
@@ -218,11 +238,11 @@ namespace ngla
     AutoVector CreateRowVector () const override { return make_unique<B200Vector<double>> (n, 1); }
     AutoVector CreateColVector () const override { return make_unique<B200Vector<double>> (n, 1); }
     void MultAdd (double s, const BaseVector & x, BaseVector & y) const override
-    { Check (ngsb_blockjacobi_multadd (J, s, B200Vector<double>::Cast(x).Dev(), const_cast<B200Vector<double>&>(B200Vector<double>::Cast(y)).DevW(), 0)); }
+    { Check (ngsb_blockjacobi_multadd (J, s, B200Vector<double>::Cast(x).Dev(), B200Vector<double>::CastW(y).DevW(), 0)); }
     void MultTransAdd (double s, const BaseVector & x, BaseVector & y) const override
-    { Check (ngsb_blockjacobi_multadd (J, s, B200Vector<double>::Cast(x).Dev(), const_cast<B200Vector<double>&>(B200Vector<double>::Cast(y)).DevW(), 1)); }
+    { Check (ngsb_blockjacobi_multadd (J, s, B200Vector<double>::Cast(x).Dev(), B200Vector<double>::CastW(y).DevW(), 1)); }
     void Mult (const BaseVector & x, BaseVector & y) const override
-    { Check (ngsb_blockjacobi_mult (J, B200Vector<double>::Cast(x).Dev(), const_cast<B200Vector<double>&>(B200Vector<double>::Cast(y)).DevW(), 0)); }
+    { Check (ngsb_blockjacobi_mult (J, B200Vector<double>::Cast(x).Dev(), B200Vector<double>::CastW(y).DevW(), 0)); }
   };
 
   // ---- fused device CG: same interface as DevCGSolver (ngscuda/cuda_linalg.hpp:289-310) ----------------
@@ -244,7 +264,7 @@ namespace ngla
       auto C = dynamic_cast<const B200Jacobi<double>*> (c.get());
       if (!A) throw Exception ("B200CGSolver: matrix is not a B200SparseMatrix<double>");
       Check (ngsb_cg_solve (A->Handle(), C ? C->Handle() : nullptr, B200Vector<double>::Cast(f).Dev(),
-                            const_cast<B200Vector<double>&>(B200Vector<double>::Cast(u)).DevW(), prec, maxsteps,
+                            B200Vector<double>::CastW(u).DevW(), prec, maxsteps,
                             NGSB_IP_REAL, 1, &steps, nullptr, 0, nullptr));
     }
   };

@@ -44,7 +44,7 @@ with TaskManager():
 
     # ---- NGSolve's own CPU path
     gfu = GridFunction(fes)
-    inv = CGSolver(a.mat, jac, precision=1e-8, maxsteps=20000)
+    inv = CGSolver(a.mat, jac, precision=1e-8, maxsteps=20000, printrates=False)
     t0 = time.perf_counter()
     gfu.vec.data = inv * f.vec
     out.update(cpu_steps=inv.GetSteps(), cpu_solve_s=time.perf_counter() - t0)
@@ -56,7 +56,7 @@ with TaskManager():
     fdev = f.vec.CreateDeviceVector()
     out.update(upload_s=time.perf_counter() - t0, types=[type(adev).__name__, type(jdev).__name__, type(fdev).__name__],
                is_host_object=[adev is a.mat, jdev is jac])
-    invdev = CGSolver(adev, jdev, precision=1e-8, maxsteps=20000)        # NGSolve's C++ CG loop, every op a virtual call into libngsb200
+    invdev = CGSolver(adev, jdev, precision=1e-8, maxsteps=20000, printrates=False)        # NGSolve's C++ CG loop, every op a virtual call into libngsb200
     res = (invdev * fdev).Evaluate()
     t0 = time.perf_counter()
     res = (invdev * fdev).Evaluate()
@@ -79,12 +79,12 @@ with TaskManager():
     # ---- block Jacobi (the tutorial's second device example): BlockJacobiPrecond -> DevBlockJacobiMatrix
     blocks = fes.CreateSmoothingBlocks()
     bj = a.mat.CreateBlockSmoother(blocks)
-    invb = CGSolver(a.mat, bj, precision=1e-8, maxsteps=20000)
+    invb = CGSolver(a.mat, bj, precision=1e-8, maxsteps=20000, printrates=False)
     t0 = time.perf_counter()
     gfu.vec.data = invb * f.vec
     out.update(bj_cpu_steps=invb.GetSteps(), bj_cpu_solve_s=time.perf_counter() - t0)
     bjdev = bj.CreateDeviceMatrix()
-    invbd = CGSolver(adev, bjdev, precision=1e-8, maxsteps=20000)
+    invbd = CGSolver(adev, bjdev, precision=1e-8, maxsteps=20000, printrates=False)
     res4 = (invbd * fdev).Evaluate()
     t0 = time.perf_counter()
     res4 = (invbd * fdev).Evaluate()
