@@ -381,7 +381,7 @@ def run_b200(args):
     clocks = sampler.summary(*span) if rank == 0 else None
 
     cpu = None
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:      # the CPU baseline is reported at N = 1 only
         cpu = cpu_cg(args.cpu_iters, nnz_sum, global_ndof)
     if rank == 0:
         if world == 1:
