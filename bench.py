@@ -331,6 +331,15 @@ def run_b200(args):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
 
+    # DRAM traffic of the dominant kernel per launch from the committed `ncu --set full` capture of this very command
+    traffic, traffic_src = None, None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        if world == 1 and str(m) in tj and c16_entries > 0:
+            traffic, traffic_src = tj[str(m)]["traffic_bytes"], tj[str(m)]["capture"]
+    except Exception:
+        pass
+
     # ---- e2e: the C-ABI call a script's `gfu.vec.data = inv * f.vec` makes, host buffers, copies timed
     e2e = None
     if world == 1:
@@ -406,7 +415,7 @@ def run_b200(args):
                        "spmv_pct_of_8TBs": achieved / 8000.0 * 100.0,
                        "sell_padding": sell_entries / max(1, nnz_local) - 1.0, "sell_overflow_rows": sell_ovf},
             "roofline": {"bound": "hbm", "kernel": "sell_spmv_kernel (SELL-32 SpMV + fused <s,As> + CG alpha step)", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": b_spmv, "stored_bytes_per_launch": stream_bytes,
                          "achieved_on_stored_bytes": stream_bytes / t_spmv / 1e9,
                          "c16_share_of_entries": c16_entries / max(1, sell_entries),

@@ -940,8 +940,16 @@ int ngsb::gmres_solve_impl(const ngsb_csr *A, const ngsb_jacobi *C, const ngsb_v
     GM_CUDA(cudaMemcpyAsync(&hst, d_st, sizeof(hst), cudaMemcpyDeviceToHost, ctx->stream));
     GM_CUDA(cudaStreamSynchronize(ctx->stream));
     done = hst.done != 0;
+    // The host runs one step ahead of the device-side stopping rule: step j+1 is enqueued before the `done` flag of step j
+    // has been read back (every kernel of the step that touches solver state returns at once when the flag is set), so the
+    // stream never drains between steps.  The state is polled through two pinned slots.
+    GmresState *slot = reinterpret_cast<GmresState *>(ctx->h_pinned);
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    GM_CUDA(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
+    GM_CUDA(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+    int jh = hst.j, enq = 0;
     while (!done) {
-        j = hst.j;   // current column
+        j = jh;      // current column (the device's st->j as long as the loop condition holds)
         double *v = vi[j];
         // w = C A v: the product lands in `av` and the preconditioner writes w (no preconditioner: straight into w)
         GM_TRY(spmv(v, C ? av : w));
@@ -963,10 +971,23 @@ int ngsb::gmres_solve_impl(const ngsb_csr *A, const ngsb_jacobi *C, const ngsb_v
         GM_CUDA(new_basis_vector(&vn));
         vi.push_back(vn);
         GM_TRY(launch_axpby_dev(ctx, vn, w, N, d_st_scale, cplx, false, false));
-        GM_CUDA(cudaMemcpyAsync(&hst, d_st, sizeof(hst), cudaMemcpyDeviceToHost, ctx->stream));
-        GM_CUDA(cudaStreamSynchronize(ctx->stream));
-        done = hst.done != 0;
+        GM_CUDA(cudaMemcpyAsync(&slot[enq & 1], d_st, sizeof(GmresState), cudaMemcpyDeviceToHost, ctx->stream));
+        GM_CUDA(cudaEventRecord(ev[enq & 1], ctx->stream));
+        if (enq > 0) {
+            GM_CUDA(cudaEventSynchronize(ev[(enq - 1) & 1]));
+            done = slot[(enq - 1) & 1].done != 0;
+        }
+        enq++;
+        jh++;
+        if (jh >= ms) {       // the last column the arrays can hold: no further speculation
+            GM_CUDA(cudaStreamSynchronize(ctx->stream));
+            break;
+        }
     }
+    GM_CUDA(cudaMemcpyAsync(&hst, d_st, sizeof(hst), cudaMemcpyDeviceToHost, ctx->stream));
+    GM_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaEventDestroy(ev[0]);
+    cudaEventDestroy(ev[1]);
     // j-- ; back substitution ; x += y_i v_i
     {
         SpanGuard g(ctx, KC_OTHER);
