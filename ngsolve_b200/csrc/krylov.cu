@@ -829,8 +829,11 @@ int ngsb::gmres_solve_impl(const ngsb_csr *A, const ngsb_jacobi *C, const ngsb_v
     auto cleanup = [&]() {
         cudaStreamSynchronize(ctx->stream);
         cudaFree(d_st); cudaFree(d_h); cudaFree(d_gam); cudaFree(d_ci); cudaFree(d_si); cudaFree(d_y); cudaFree(d_hist); cudaFree(d_scale);
-        for (auto p : chunks) cudaFree(p);
-        cudaFree(av); cudaFree(w); cudaFree(r);
+        // the big buffers come from the stream-ordered pool: the next solve gets them back without mapping memory again
+        for (auto p : chunks) cudaFreeAsync(p, ctx->stream);
+        if (av) cudaFreeAsync(av, ctx->stream);
+        if (w) cudaFreeAsync(w, ctx->stream);
+        if (r) cudaFreeAsync(r, ctx->stream);
     };
 #define GM_CUDA(call)                                                                                      \
     do {                                                                                                   \
@@ -857,9 +860,20 @@ int ngsb::gmres_solve_impl(const ngsb_csr *A, const ngsb_jacobi *C, const ngsb_v
     GM_CUDA(cudaMalloc(&d_hist, sizeof(double) * (hist_cap + 1)));
     GM_CUDA(cudaMalloc(&d_scale, sizeof(double) * 2));
     const size_t vbytes = (nscal ? nscal : 2) * sizeof(double);
-    GM_CUDA(cudaMalloc(&av, vbytes));
-    GM_CUDA(cudaMalloc(&w, vbytes));
-    GM_CUDA(cudaMalloc(&r, vbytes));
+    {
+        // keep up to a fifth of the device memory in the default pool between solves (cudaMalloc/cudaFree of the multi-GB
+        // basis chunks cost tens of milliseconds each and drain the stream)
+        cudaMemPool_t pool = nullptr;
+        size_t free_b = 0, total_b = 0;
+        if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+            uint64_t thr = (uint64_t)total_b / 5;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+        cudaGetLastError();
+    }
+    GM_CUDA(cudaMallocAsync(&av, vbytes, ctx->stream));
+    GM_CUDA(cudaMallocAsync(&w, vbytes, ctx->stream));
+    GM_CUDA(cudaMallocAsync(&r, vbytes, ctx->stream));
     const size_t vstride = (vbytes + 255) & ~(size_t)255;
     const size_t per_chunk = std::max<size_t>(1, std::min<size_t>(8, ((size_t)4 << 30) / vstride));
     size_t chunk_used = per_chunk;
@@ -867,7 +881,7 @@ int ngsb::gmres_solve_impl(const ngsb_csr *A, const ngsb_jacobi *C, const ngsb_v
         if (chunk_used == per_chunk) {
             double *c = nullptr;
             const size_t want = std::min<size_t>(per_chunk, (size_t)ms + 1 > vi.size() ? (size_t)ms + 1 - vi.size() : 1);
-            cudaError_t e = cudaMalloc(&c, vstride * std::max<size_t>(1, want));
+            cudaError_t e = cudaMallocAsync(&c, vstride * std::max<size_t>(1, want), ctx->stream);
             if (e != cudaSuccess) return e;
             chunks.push_back(c);
             chunk_used = 0;
