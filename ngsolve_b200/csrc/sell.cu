@@ -364,6 +364,163 @@ __global__ void __launch_bounds__(256, MINB) sell_spmv_kernel(const SellParams p
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Real matrices, variant 3: the compressed stream (values, 16-bit offsets, bases) is staged through shared memory with
+// cp.async (LDGSTS), one private ring of STAGES chunks of 4 packets per warp.  The bytes in flight no longer live in
+// registers, so a warp keeps STAGES-1 chunks (2.6 KB each) on their way while it gathers x and multiplies the current
+// one; the ring runs across slice boundaries (the producer cursor of a warp is up to STAGES-1 chunks ahead of its
+// consumer cursor and looks up the offsets of its next slices itself).  Slices without 16-bit offsets are multiplied
+// with direct loads.  Same summation order as the other variants (bit-identical results).
+__device__ __forceinline__ void cp_async16(void *dst, const void *src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void *dst, const void *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void *dst, const void *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int STAGES, int MINB>
+__global__ void __launch_bounds__(256, MINB) sell_spmv_async_kernel(const SellParams p)
+{
+    constexpr int CH = 4;                                   // packets per chunk
+    constexpr int STAGE_BYTES = CH * 512 + CH * 128 + 64;   // values | offsets | bases (CH int2, padded)
+    extern __shared__ __align__(128) unsigned char smem_ring[];
+    __shared__ double red[64];
+    __shared__ int s_last;
+    if (p.state != nullptr && p.state->done) return;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned char *ring = smem_ring + (size_t)wid * STAGES * STAGE_BYTES;
+    const uint64_t stride = (uint64_t)gridDim.x * 8;
+    double dr = 0.0, di = 0.0;
+
+    // ---- producer cursor: next chunk to request = packets [pq, pq+CH) of compressed slice ps
+    uint64_t ps = (uint64_t)blockIdx.x * 8 + wid, poff = 0;
+    uint32_t pnp = 0, pq = 0;
+    auto producer_seek = [&]() {                            // advance ps to the next compressed slice with packets left
+        while (ps < p.nslices) {
+            if (p.slice_c16[ps]) {
+                poff = p.slice_off[ps];
+                pnp = (uint32_t)((p.slice_off[ps + 1] - poff) >> 6);
+                if (pnp > 0) { pq = 0; return; }
+            }
+            ps += stride;
+        }
+        pnp = 0; pq = 0;
+    };
+    auto produce = [&](int stage) {                         // one group per call, possibly empty (uniform group counting)
+        if (ps < p.nslices) {
+            unsigned char *st = ring + (size_t)stage * STAGE_BYTES;
+            const uint32_t n = min((uint32_t)CH, pnp - pq);
+            const char *vsrc = reinterpret_cast<const char *>(p.sval + poff) + (size_t)pq * 512 + lane * 16;
+            const char *hsrc = reinterpret_cast<const char *>(p.scol16 + poff) + (size_t)pq * 128 + lane * 4;
+#pragma unroll
+            for (uint32_t k = 0; k < (uint32_t)CH; k++)
+                if (k < n) {
+                    cp_async16(st + k * 512 + lane * 16, vsrc + k * 512);
+                    cp_async4(st + CH * 512 + k * 128 + lane * 4, hsrc + k * 128);
+                }
+            if ((uint32_t)lane < n) cp_async8(st + CH * 640 + lane * 8, p.sbase + (poff >> 5) + 2 * (size_t)(pq + lane));
+            pq += n;
+            if (pq >= pnp) { ps += stride; producer_seek(); }
+        }
+        cp_async_commit();
+    };
+    producer_seek();
+#pragma unroll
+    for (int k = 0; k < STAGES - 1; k++) produce(k);
+    int cstage = 0;
+
+    for (uint64_t s = (uint64_t)blockIdx.x * 8 + wid; s < p.nslices; s += stride) {
+        const uint64_t off = p.slice_off[s];
+        const uint32_t width = (uint32_t)((p.slice_off[s + 1] - off) >> 5);
+        const uint64_t src = p.slice_src[s];
+        const uint32_t slot = (uint32_t)(src * 32 + lane);
+        const uint32_t row = p.row_of[slot];
+        const uint32_t np = width >> 1;
+        double s0 = 0.0;
+        if (p.slice_c16[s]) {
+            for (uint32_t q = 0; q < np; q += CH) {
+                cp_async_wait<STAGES - 2>();
+                __syncwarp();
+                const unsigned char *st = ring + (size_t)cstage * STAGE_BYTES;
+                const uint32_t n = min((uint32_t)CH, np - q);
+                double2 v[CH];
+                double xa[CH], xb[CH];
+#pragma unroll
+                for (uint32_t k = 0; k < (uint32_t)CH; k++)
+                    if (k < n) {
+                        const unsigned int h = *reinterpret_cast<const unsigned int *>(st + CH * 512 + k * 128 + lane * 4);
+                        const int2 b = *reinterpret_cast<const int2 *>(st + CH * 640 + k * 8);
+                        xa[k] = __ldg(p.x + (b.x + (int)(h & 0xffffu)));
+                        xb[k] = __ldg(p.x + (b.y + (int)(h >> 16)));
+                        v[k] = *reinterpret_cast<const double2 *>(st + k * 512 + lane * 16);
+                    }
+#pragma unroll
+                for (uint32_t k = 0; k < (uint32_t)CH; k++)
+                    if (k < n) { s0 = fma(v[k].x, xa[k], s0); s0 = fma(v[k].y, xb[k], s0); }
+                __syncwarp();                                // every lane has read the stage: it can be refilled
+                produce((cstage + STAGES - 1) % STAGES);
+                cstage = (cstage + 1) % STAGES;
+            }
+        } else {
+            const double2 *v2 = reinterpret_cast<const double2 *>(p.sval + off) + lane;
+            const int2 *c2 = reinterpret_cast<const int2 *>(p.scol + off) + lane;
+            for (uint32_t q = 0; q < np; q++) {
+                const double2 va = ldg_stream_d2(v2 + q * 32);
+                const int2 ca = ldg_stream_i2(c2 + q * 32);
+                s0 = fma(va.x, __ldg(p.x + ca.x), s0);
+                s0 = fma(va.y, __ldg(p.x + ca.y), s0);
+            }
+        }
+        if (p.slice_ovf != nullptr) {
+            int k = p.slice_ovf[src];
+            if (k >= 0)
+                for (; (uint32_t)k < p.novf && (p.ovf_slot[k] >> 5) == src; k++)
+                    if (p.ovf_slot[k] == slot) s0 += p.ovf_sum[k];
+        }
+        if (row != 0xffffffffu) {
+            double r = p.sr * s0;
+            if (p.accumulate) r += p.y[row];
+            p.y[row] = r;
+            if (p.epi) dr = fma(p.dotvec[row], r, dr);
+        }
+    }
+    cp_async_wait<0>();
+    if (!p.epi) return;
+    dr = warp_sum_s(dr);
+    if (lane == 0) { red[wid] = dr; red[32 + wid] = di; }
+    __syncthreads();
+    if (wid == 0) {
+        const int nw = blockDim.x >> 5;
+        dr = lane < nw ? red[lane] : 0.0;
+        dr = warp_sum_s(dr);
+        if (lane == 0) {
+            p.partials[2 * blockIdx.x] = dr;
+            p.partials[2 * blockIdx.x + 1] = 0.0;
+            __threadfence();
+            s_last = (atomicAdd(p.counter, 1u) == gridDim.x - 1);
+        }
+    }
+    __syncthreads();
+    if (!s_last || threadIdx.x >= 32) return;
+    __threadfence();
+    double a = 0.0;
+    for (unsigned int k = threadIdx.x; k < gridDim.x; k += 32) a += __ldcg(&p.partials[2 * k]);
+    a = warp_sum_s(a);
+    if (threadIdx.x == 0) {
+        *p.counter = 0;
+        if (p.epi == EPI_DOT_OUT) { p.dot_out[0] = a; p.dot_out[1] = 0.0; }
+        else if (p.epi == EPI_CG_KSS) cg_finalize_kss(p.state, make_double2(a, 0.0));
+    }
+}
+
 // SparseMatrix<double>::MultAdd(FlatVector alpha, MultiVector x, MultiVector y) (linalg/sparsematrix.cpp:2274-2351): four
 // right-hand sides per sweep over the matrix; values and columns are read once, every row keeps four accumulators that
 // are summed in storage order exactly like the single-vector kernel (bit-identical results per vector).
@@ -859,6 +1016,25 @@ int sell_launch(const SpmvArgs &a)
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
     if (grid > (uint64_t)MAX_PARTIALS - 8) grid = MAX_PARTIALS - 8;
+    if (A->kind == NGSB_REAL && var == 3 && p.slice_c16 != nullptr) {
+        // cp.async-staged variant: `sell_stages` ring slots of 2624 bytes per warp
+        const long stages = ctx->sell_stages >= 2 && ctx->sell_stages <= 6 ? ctx->sell_stages : 4;
+        const size_t smem = (size_t)8 * stages * (4 * 512 + 4 * 128 + 64);
+        kern_t ak = stages == 2 ? sell_spmv_async_kernel<2, 2> : stages == 3 ? sell_spmv_async_kernel<3, 2> : stages == 4 ? sell_spmv_async_kernel<4, 2>
+                  : stages == 5 ? sell_spmv_async_kernel<5, 2> : sell_spmv_async_kernel<6, 1>;
+        NGSB_CUDA(cudaFuncSetAttribute(ak, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int aocc = 0;
+        NGSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&aocc, ak, 256, smem));
+        const long acps = ctx->spmv_ctas_per_sm > 0 ? ctx->spmv_ctas_per_sm : std::max(1, aocc);
+        uint64_t agrid = (uint64_t)ctx->sm_count * (uint64_t)acps;
+        if (agrid > need) agrid = need;
+        if (agrid < 1) agrid = 1;
+        if (agrid > (uint64_t)MAX_PARTIALS - 8) agrid = MAX_PARTIALS - 8;
+        SpanGuard g(ctx, KC_SPMV);
+        ak<<<(unsigned)agrid, 256, smem, ctx->stream>>>(p);
+        NGSB_CUDA(cudaGetLastError());
+        return NGSB_OK;
+    }
     SpanGuard g(ctx, KC_SPMV);
     kern<<<(unsigned)grid, 256, 0, ctx->stream>>>(p);
     NGSB_CUDA(cudaGetLastError());

@@ -156,3 +156,38 @@ def test_c16_column_compression_is_bit_exact_and_partial():
         ys.append(inv.GetSteps())
     ctx.set_option("sell_c16", 1)
     assert np.array_equal(ys[0], ys[3]) and np.array_equal(ys[1], ys[4]) and ys[2] == ys[5]
+
+
+@pytest.mark.parametrize("n", [(88, 88, 3), (5, 4, 3), (1, 1, 1)])
+def test_async_staged_variant_is_bit_exact(n):
+    """sell_variant = 3 (compressed stream staged through shared memory with cp.async, ring across slice boundaries) computes
+    the same sums in the same order as the default kernel: products, accumulating products and whole CG solves coincide"""
+    import ngsolve_b200.la as la
+    from ngsolve_b200 import workloads as W
+    ctx = la.default_context()
+    box = W.FemBox(n, order=3)
+    A, f = box.device_system(ctx)
+    jac = A.CreateSmoother(box.freedofs())
+    rng = np.random.default_rng(11)
+    x = la.BaseVector(rng.random(A.height), ctx=ctx)
+    y0 = rng.random(A.height)
+    out = {}
+    try:
+        for var, stages in ((0, 4), (3, 2), (3, 3), (3, 4), (3, 6)):
+            ctx.set_option("sell_variant", var)
+            ctx.set_option("sell_stages", stages)
+            y = A.CreateColVector()
+            A.Mult(x, y)
+            z = la.BaseVector(y0, ctx=ctx)
+            A.MultAdd(-0.5, x, z)
+            inv = la.CGSolver(A, jac, precision=1e-8, maxsteps=300)
+            u = f.CreateVector()
+            inv.Mult(f, u)
+            out[(var, stages)] = (y.NumPy().copy(), z.NumPy().copy(), u.NumPy().copy(), inv.GetSteps())
+    finally:
+        ctx.set_option("sell_variant", 0)
+        ctx.set_option("sell_stages", 4)
+    ref = out[(0, 4)]
+    for key, val in out.items():
+        assert np.array_equal(val[0], ref[0]) and np.array_equal(val[1], ref[1]), key
+        assert np.array_equal(val[2], ref[2]) and val[3] == ref[3], key

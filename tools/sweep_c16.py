@@ -38,7 +38,15 @@ def run(tag, **opts):
     print("%-46s %8.3f ms  alg %7.1f GB/s  stored %7.1f GB/s" % (tag, ms, alg / ms / 1e6, (stored if opts.get("sell_c16", 1) else alg) / ms / 1e6), flush=True)
 
 
+mode = sys.argv[2] if len(sys.argv) > 2 else "async"
 run("c16 off", sell_c16=0)
-for cps in (8, 6, 5, 4, 12):
-    for pf, nx in ((0, 0), (1, 0), (2, 0), (3, 0), (0, 8), (2, 8), (1, 8), (2, 16), (3, 16), (4, 8)):
-        run("c16 ctas/sm=%d pf_steps=%d pf_next=%d" % (cps, pf, nx), sell_c16=1, spmv_ctas_per_sm=cps, sell_pf_steps=pf, sell_pf_next=nx)
+run("c16 on, default kernel (registers)", sell_c16=1, spmv_ctas_per_sm=0)
+if mode == "prefetch":
+    for cps in (8, 6, 5, 4, 12):
+        for pf, nx in ((0, 0), (1, 0), (2, 0), (3, 0), (0, 8), (2, 8), (1, 8), (2, 16), (3, 16), (4, 8)):
+            run("c16 ctas/sm=%d pf_steps=%d pf_next=%d" % (cps, pf, nx), sell_c16=1, spmv_ctas_per_sm=cps, sell_pf_steps=pf, sell_pf_next=nx)
+else:
+    for stages in (2, 3, 4, 5, 6):
+        for cps in (0, 1, 2, 3, 4):
+            run("async staged: stages=%d ctas/sm=%d" % (stages, cps), sell_c16=1, sell_variant=3, sell_stages=stages, spmv_ctas_per_sm=cps)
+    ctx.set_option("sell_variant", 0)
