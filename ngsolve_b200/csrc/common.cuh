@@ -72,7 +72,6 @@ struct ngsb_ctx {
     long sell_variant = 0;       // inner-loop variant of the real SELL kernel (tuning)
     long sell_pf_steps = 0;      // compressed slices: in-slice L2 prefetch distance (steps of 4 packets), 0 = off
     long sell_pf_next = 0;       // compressed slices: packets of the next slice prefetched at slice start, 0 = off
-    long sell_stages = 4;        // ring depth of the cp.async-staged variant (sell_variant = 3)
     long sell_c16 = 1;           // 16-bit column offsets where a slice allows it (read at matrix creation and at launch)
     long spmv_tile = 0, spmv_ncw = 0, spmv_stages = 0, spmv_subwarp = 0;   // 0 = default; read when a matrix is created
     long timing = 0;

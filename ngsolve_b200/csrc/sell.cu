@@ -90,6 +90,42 @@ __device__ __forceinline__ unsigned int ldg_stream_u32(const unsigned int *p)
     return v;
 }
 
+// L2 eviction policies: the matrix stream is touched once (evict first), the x entries are re-used by neighbouring slices
+// (evict last) -- without hints the 57 GB stream pushes the few MB of live x lines out of the 126 MB L2
+__device__ __forceinline__ uint64_t l2_policy_evict_first()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+template <bool POL> __device__ __forceinline__ double2 ldp_d2(const double2 *p, uint64_t pol)
+{
+    double2 v;
+    if (POL) asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol));
+    else asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+template <bool POL> __device__ __forceinline__ unsigned int ldp_u32(const unsigned int *p, uint64_t pol)
+{
+    unsigned int v;
+    if (POL) asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    else asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+template <bool POL> __device__ __forceinline__ double ldp_x(const double *p, uint64_t pol)
+{
+    double v;
+    if (POL) asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+    else v = __ldg(p);
+    return v;
+}
+
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 __device__ __forceinline__ double warp_sum_s(double v)
@@ -101,7 +137,7 @@ __device__ __forceinline__ double warp_sum_s(double v)
 
 // VAR (tuning variants of the real-valued inner loop): 0 = 4 packets per step; 1 = 2 packets per step;
 // 2 = 4 packets per step with the next step's values/columns prefetched before the gathers of this one
-template <int KIND, int VAR, int MINB>
+template <int KIND, int VAR, int MINB, bool POL = false>
 __global__ void __launch_bounds__(256, MINB) sell_spmv_kernel(const SellParams p)
 {
     __shared__ double red[64];
@@ -124,6 +160,7 @@ __global__ void __launch_bounds__(256, MINB) sell_spmv_kernel(const SellParams p
             const int2 *b2 = reinterpret_cast<const int2 *>(p.sbase + (off >> 5));
             const uint32_t np = width >> 1;
             uint32_t q = 0;
+            const uint64_t polf = POL ? l2_policy_evict_first() : 0, poll = POL ? l2_policy_evict_last() : 0;
             if (p.pf_next > 0) {
                 // the compressed stream carries fewer bytes per dependent step, so the loads of one step no longer cover the DRAM
                 // latency: pull the head of this warp's next slice into L2 now (lane l fetches its own 128-byte line)
@@ -141,44 +178,44 @@ __global__ void __launch_bounds__(256, MINB) sell_spmv_kernel(const SellParams p
             const uint32_t pfd = (uint32_t)p.pf_steps * 4;
 #define NGSB_C16(h, b, c0, c1) { c0 = (b).x + (int)((h) & 0xffffu); c1 = (b).y + (int)((h) >> 16); }
             if (np >= 4) {
-                double2 va = ldg_stream_d2(v2), vb = ldg_stream_d2(v2 + 32), vc = ldg_stream_d2(v2 + 64), vd = ldg_stream_d2(v2 + 96);
+                double2 va = ldp_d2<POL>(v2, polf), vb = ldp_d2<POL>(v2 + 32, polf), vc = ldp_d2<POL>(v2 + 64, polf), vd = ldp_d2<POL>(v2 + 96, polf);
                 int ca0, ca1, cb0, cb1, cc0, cc1, cd0, cd1;
                 {
-                    const unsigned int ha = ldg_stream_u32(h2), hb = ldg_stream_u32(h2 + 32), hc = ldg_stream_u32(h2 + 64), hd = ldg_stream_u32(h2 + 96);
+                    const unsigned int ha = ldp_u32<POL>(h2, polf), hb = ldp_u32<POL>(h2 + 32, polf), hc = ldp_u32<POL>(h2 + 64, polf), hd = ldp_u32<POL>(h2 + 96, polf);
                     const int2 ba = __ldg(b2), bb = __ldg(b2 + 1), bc = __ldg(b2 + 2), bd = __ldg(b2 + 3);
                     NGSB_C16(ha, ba, ca0, ca1) NGSB_C16(hb, bb, cb0, cb1) NGSB_C16(hc, bc, cc0, cc1) NGSB_C16(hd, bd, cd0, cd1)
                 }
                 for (q = 4; q + 4 <= np; q += 4) {
-                    double x0 = __ldg(p.x + ca0), x1 = __ldg(p.x + ca1), x2 = __ldg(p.x + cb0), x3 = __ldg(p.x + cb1);
-                    double x4 = __ldg(p.x + cc0), x5 = __ldg(p.x + cc1), x6 = __ldg(p.x + cd0), x7 = __ldg(p.x + cd1);
+                    double x0 = ldp_x<POL>(p.x + ca0, poll), x1 = ldp_x<POL>(p.x + ca1, poll), x2 = ldp_x<POL>(p.x + cb0, poll), x3 = ldp_x<POL>(p.x + cb1, poll);
+                    double x4 = ldp_x<POL>(p.x + cc0, poll), x5 = ldp_x<POL>(p.x + cc1, poll), x6 = ldp_x<POL>(p.x + cd0, poll), x7 = ldp_x<POL>(p.x + cd1, poll);
                     if (pfd && q + pfd + 4 <= np) {
                         // 2 KB of values = 16 lines (lanes 0-15), 512 B of offsets = 4 lines (lanes 16-19) of the step `pf_steps` ahead
                         if (lane < 16) prefetch_l2(reinterpret_cast<const char *>(p.sval + off) + (size_t)(q + pfd) * 512 + lane * 128);
                         else if (lane < 20) prefetch_l2(reinterpret_cast<const char *>(p.scol16 + off) + (size_t)(q + pfd) * 128 + (lane - 16) * 128);
                     }
-                    double2 na = ldg_stream_d2(v2 + (q + 0) * 32), nb = ldg_stream_d2(v2 + (q + 1) * 32);
-                    double2 nc = ldg_stream_d2(v2 + (q + 2) * 32), nd = ldg_stream_d2(v2 + (q + 3) * 32);
-                    const unsigned int ha = ldg_stream_u32(h2 + (q + 0) * 32), hb = ldg_stream_u32(h2 + (q + 1) * 32);
-                    const unsigned int hc = ldg_stream_u32(h2 + (q + 2) * 32), hd = ldg_stream_u32(h2 + (q + 3) * 32);
+                    double2 na = ldp_d2<POL>(v2 + (q + 0) * 32, polf), nb = ldp_d2<POL>(v2 + (q + 1) * 32, polf);
+                    double2 nc = ldp_d2<POL>(v2 + (q + 2) * 32, polf), nd = ldp_d2<POL>(v2 + (q + 3) * 32, polf);
+                    const unsigned int ha = ldp_u32<POL>(h2 + (q + 0) * 32, polf), hb = ldp_u32<POL>(h2 + (q + 1) * 32, polf);
+                    const unsigned int hc = ldp_u32<POL>(h2 + (q + 2) * 32, polf), hd = ldp_u32<POL>(h2 + (q + 3) * 32, polf);
                     const int2 ba = __ldg(b2 + q), bb = __ldg(b2 + q + 1), bc = __ldg(b2 + q + 2), bd = __ldg(b2 + q + 3);
                     s0 = fma(va.x, x0, s0); s0 = fma(va.y, x1, s0); s0 = fma(vb.x, x2, s0); s0 = fma(vb.y, x3, s0);
                     s0 = fma(vc.x, x4, s0); s0 = fma(vc.y, x5, s0); s0 = fma(vd.x, x6, s0); s0 = fma(vd.y, x7, s0);
                     va = na; vb = nb; vc = nc; vd = nd;
                     NGSB_C16(ha, ba, ca0, ca1) NGSB_C16(hb, bb, cb0, cb1) NGSB_C16(hc, bc, cc0, cc1) NGSB_C16(hd, bd, cd0, cd1)
                 }
-                double x0 = __ldg(p.x + ca0), x1 = __ldg(p.x + ca1), x2 = __ldg(p.x + cb0), x3 = __ldg(p.x + cb1);
-                double x4 = __ldg(p.x + cc0), x5 = __ldg(p.x + cc1), x6 = __ldg(p.x + cd0), x7 = __ldg(p.x + cd1);
+                double x0 = ldp_x<POL>(p.x + ca0, poll), x1 = ldp_x<POL>(p.x + ca1, poll), x2 = ldp_x<POL>(p.x + cb0, poll), x3 = ldp_x<POL>(p.x + cb1, poll);
+                double x4 = ldp_x<POL>(p.x + cc0, poll), x5 = ldp_x<POL>(p.x + cc1, poll), x6 = ldp_x<POL>(p.x + cd0, poll), x7 = ldp_x<POL>(p.x + cd1, poll);
                 s0 = fma(va.x, x0, s0); s0 = fma(va.y, x1, s0); s0 = fma(vb.x, x2, s0); s0 = fma(vb.y, x3, s0);
                 s0 = fma(vc.x, x4, s0); s0 = fma(vc.y, x5, s0); s0 = fma(vd.x, x6, s0); s0 = fma(vd.y, x7, s0);
             }
             for (; q < np; q++) {
-                const double2 va = ldg_stream_d2(v2 + q * 32);
-                const unsigned int ha = ldg_stream_u32(h2 + q * 32);
+                const double2 va = ldp_d2<POL>(v2 + q * 32, polf);
+                const unsigned int ha = ldp_u32<POL>(h2 + q * 32, polf);
                 const int2 ba = __ldg(b2 + q);
                 int c0, c1;
                 NGSB_C16(ha, ba, c0, c1)
-                s0 = fma(va.x, __ldg(p.x + c0), s0);
-                s0 = fma(va.y, __ldg(p.x + c1), s0);
+                s0 = fma(va.x, ldp_x<POL>(p.x + c0, poll), s0);
+                s0 = fma(va.y, ldp_x<POL>(p.x + c1, poll), s0);
             }
 #undef NGSB_C16
         } else if (KIND == NGSB_REAL) {
@@ -361,163 +398,6 @@ __global__ void __launch_bounds__(256, MINB) sell_spmv_kernel(const SellParams p
         *p.counter = 0;
         if (p.epi == EPI_DOT_OUT) { p.dot_out[0] = a; p.dot_out[1] = b; }
         else if (p.epi == EPI_CG_KSS) cg_finalize_kss(p.state, make_double2(a, b));
-    }
-}
-
-// ------------------------------------------------------------------------------------------------------------------
-// Real matrices, variant 3: the compressed stream (values, 16-bit offsets, bases) is staged through shared memory with
-// cp.async (LDGSTS), one private ring of STAGES chunks of 4 packets per warp.  The bytes in flight no longer live in
-// registers, so a warp keeps STAGES-1 chunks (2.6 KB each) on their way while it gathers x and multiplies the current
-// one; the ring runs across slice boundaries (the producer cursor of a warp is up to STAGES-1 chunks ahead of its
-// consumer cursor and looks up the offsets of its next slices itself).  Slices without 16-bit offsets are multiplied
-// with direct loads.  Same summation order as the other variants (bit-identical results).
-__device__ __forceinline__ void cp_async16(void *dst, const void *src)
-{
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async8(void *dst, const void *src)
-{
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async4(void *dst, const void *src)
-{
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-template <int STAGES, int MINB>
-__global__ void __launch_bounds__(256, MINB) sell_spmv_async_kernel(const SellParams p)
-{
-    constexpr int CH = 4;                                   // packets per chunk
-    constexpr int STAGE_BYTES = CH * 512 + CH * 128 + 64;   // values | offsets | bases (CH int2, padded)
-    extern __shared__ __align__(128) unsigned char smem_ring[];
-    __shared__ double red[64];
-    __shared__ int s_last;
-    if (p.state != nullptr && p.state->done) return;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    unsigned char *ring = smem_ring + (size_t)wid * STAGES * STAGE_BYTES;
-    const uint64_t stride = (uint64_t)gridDim.x * 8;
-    double dr = 0.0, di = 0.0;
-
-    // ---- producer cursor: next chunk to request = packets [pq, pq+CH) of compressed slice ps
-    uint64_t ps = (uint64_t)blockIdx.x * 8 + wid, poff = 0;
-    uint32_t pnp = 0, pq = 0;
-    auto producer_seek = [&]() {                            // advance ps to the next compressed slice with packets left
-        while (ps < p.nslices) {
-            if (p.slice_c16[ps]) {
-                poff = p.slice_off[ps];
-                pnp = (uint32_t)((p.slice_off[ps + 1] - poff) >> 6);
-                if (pnp > 0) { pq = 0; return; }
-            }
-            ps += stride;
-        }
-        pnp = 0; pq = 0;
-    };
-    auto produce = [&](int stage) {                         // one group per call, possibly empty (uniform group counting)
-        if (ps < p.nslices) {
-            unsigned char *st = ring + (size_t)stage * STAGE_BYTES;
-            const uint32_t n = min((uint32_t)CH, pnp - pq);
-            const char *vsrc = reinterpret_cast<const char *>(p.sval + poff) + (size_t)pq * 512 + lane * 16;
-            const char *hsrc = reinterpret_cast<const char *>(p.scol16 + poff) + (size_t)pq * 128 + lane * 4;
-#pragma unroll
-            for (uint32_t k = 0; k < (uint32_t)CH; k++)
-                if (k < n) {
-                    cp_async16(st + k * 512 + lane * 16, vsrc + k * 512);
-                    cp_async4(st + CH * 512 + k * 128 + lane * 4, hsrc + k * 128);
-                }
-            if ((uint32_t)lane < n) cp_async8(st + CH * 640 + lane * 8, p.sbase + (poff >> 5) + 2 * (size_t)(pq + lane));
-            pq += n;
-            if (pq >= pnp) { ps += stride; producer_seek(); }
-        }
-        cp_async_commit();
-    };
-    producer_seek();
-#pragma unroll
-    for (int k = 0; k < STAGES - 1; k++) produce(k);
-    int cstage = 0;
-
-    for (uint64_t s = (uint64_t)blockIdx.x * 8 + wid; s < p.nslices; s += stride) {
-        const uint64_t off = p.slice_off[s];
-        const uint32_t width = (uint32_t)((p.slice_off[s + 1] - off) >> 5);
-        const uint64_t src = p.slice_src[s];
-        const uint32_t slot = (uint32_t)(src * 32 + lane);
-        const uint32_t row = p.row_of[slot];
-        const uint32_t np = width >> 1;
-        double s0 = 0.0;
-        if (p.slice_c16[s]) {
-            for (uint32_t q = 0; q < np; q += CH) {
-                cp_async_wait<STAGES - 2>();
-                __syncwarp();
-                const unsigned char *st = ring + (size_t)cstage * STAGE_BYTES;
-                const uint32_t n = min((uint32_t)CH, np - q);
-                double2 v[CH];
-                double xa[CH], xb[CH];
-#pragma unroll
-                for (uint32_t k = 0; k < (uint32_t)CH; k++)
-                    if (k < n) {
-                        const unsigned int h = *reinterpret_cast<const unsigned int *>(st + CH * 512 + k * 128 + lane * 4);
-                        const int2 b = *reinterpret_cast<const int2 *>(st + CH * 640 + k * 8);
-                        xa[k] = __ldg(p.x + (b.x + (int)(h & 0xffffu)));
-                        xb[k] = __ldg(p.x + (b.y + (int)(h >> 16)));
-                        v[k] = *reinterpret_cast<const double2 *>(st + k * 512 + lane * 16);
-                    }
-#pragma unroll
-                for (uint32_t k = 0; k < (uint32_t)CH; k++)
-                    if (k < n) { s0 = fma(v[k].x, xa[k], s0); s0 = fma(v[k].y, xb[k], s0); }
-                __syncwarp();                                // every lane has read the stage: it can be refilled
-                produce((cstage + STAGES - 1) % STAGES);
-                cstage = (cstage + 1) % STAGES;
-            }
-        } else {
-            const double2 *v2 = reinterpret_cast<const double2 *>(p.sval + off) + lane;
-            const int2 *c2 = reinterpret_cast<const int2 *>(p.scol + off) + lane;
-            for (uint32_t q = 0; q < np; q++) {
-                const double2 va = ldg_stream_d2(v2 + q * 32);
-                const int2 ca = ldg_stream_i2(c2 + q * 32);
-                s0 = fma(va.x, __ldg(p.x + ca.x), s0);
-                s0 = fma(va.y, __ldg(p.x + ca.y), s0);
-            }
-        }
-        if (p.slice_ovf != nullptr) {
-            int k = p.slice_ovf[src];
-            if (k >= 0)
-                for (; (uint32_t)k < p.novf && (p.ovf_slot[k] >> 5) == src; k++)
-                    if (p.ovf_slot[k] == slot) s0 += p.ovf_sum[k];
-        }
-        if (row != 0xffffffffu) {
-            double r = p.sr * s0;
-            if (p.accumulate) r += p.y[row];
-            p.y[row] = r;
-            if (p.epi) dr = fma(p.dotvec[row], r, dr);
-        }
-    }
-    cp_async_wait<0>();
-    if (!p.epi) return;
-    dr = warp_sum_s(dr);
-    if (lane == 0) { red[wid] = dr; red[32 + wid] = di; }
-    __syncthreads();
-    if (wid == 0) {
-        const int nw = blockDim.x >> 5;
-        dr = lane < nw ? red[lane] : 0.0;
-        dr = warp_sum_s(dr);
-        if (lane == 0) {
-            p.partials[2 * blockIdx.x] = dr;
-            p.partials[2 * blockIdx.x + 1] = 0.0;
-            __threadfence();
-            s_last = (atomicAdd(p.counter, 1u) == gridDim.x - 1);
-        }
-    }
-    __syncthreads();
-    if (!s_last || threadIdx.x >= 32) return;
-    __threadfence();
-    double a = 0.0;
-    for (unsigned int k = threadIdx.x; k < gridDim.x; k += 32) a += __ldcg(&p.partials[2 * k]);
-    a = warp_sum_s(a);
-    if (threadIdx.x == 0) {
-        *p.counter = 0;
-        if (p.epi == EPI_DOT_OUT) { p.dot_out[0] = a; p.dot_out[1] = 0.0; }
-        else if (p.epi == EPI_CG_KSS) cg_finalize_kss(p.state, make_double2(a, 0.0));
     }
 }
 
@@ -1004,37 +884,19 @@ int sell_launch(const SpmvArgs &a)
         switch (var) {
         case 1: kern = sell_spmv_kernel<NGSB_REAL, 0, 5>; break;
         case 2: kern = sell_spmv_kernel<NGSB_REAL, 1, 8>; break;
+        case 3: kern = sell_spmv_kernel<NGSB_REAL, 2, 4, true>; break;      // + L2 eviction policies in the compressed loop
         default: kern = sell_spmv_kernel<NGSB_REAL, 2, 4>; break;
         }
     } else if (A->kind == NGSB_COMPLEX) kern = var == 1 ? sell_spmv_kernel<NGSB_COMPLEX, 0, 5> : sell_spmv_kernel<NGSB_COMPLEX, 2, 4>;
     else kern = sell_spmv_kernel<NGSB_BLOCK3, 0, 5>;
     int occ = 0;
     NGSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, 0));
-    long cps = ctx->spmv_ctas_per_sm > 0 ? ctx->spmv_ctas_per_sm : (A->kind != NGSB_BLOCK3 && var == 0 ? 8 : (occ > 0 ? occ : 4));
+    long cps = ctx->spmv_ctas_per_sm > 0 ? ctx->spmv_ctas_per_sm : (A->kind != NGSB_BLOCK3 && (var == 0 || var == 3) ? 8 : (occ > 0 ? occ : 4));
     uint64_t grid = (uint64_t)ctx->sm_count * (uint64_t)cps;
     const uint64_t need = ((uint64_t)A->nslices + 7) / 8;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
     if (grid > (uint64_t)MAX_PARTIALS - 8) grid = MAX_PARTIALS - 8;
-    if (A->kind == NGSB_REAL && var == 3 && p.slice_c16 != nullptr) {
-        // cp.async-staged variant: `sell_stages` ring slots of 2624 bytes per warp
-        const long stages = ctx->sell_stages >= 2 && ctx->sell_stages <= 6 ? ctx->sell_stages : 4;
-        const size_t smem = (size_t)8 * stages * (4 * 512 + 4 * 128 + 64);
-        kern_t ak = stages == 2 ? sell_spmv_async_kernel<2, 2> : stages == 3 ? sell_spmv_async_kernel<3, 2> : stages == 4 ? sell_spmv_async_kernel<4, 2>
-                  : stages == 5 ? sell_spmv_async_kernel<5, 2> : sell_spmv_async_kernel<6, 1>;
-        NGSB_CUDA(cudaFuncSetAttribute(ak, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int aocc = 0;
-        NGSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&aocc, ak, 256, smem));
-        const long acps = ctx->spmv_ctas_per_sm > 0 ? ctx->spmv_ctas_per_sm : std::max(1, aocc);
-        uint64_t agrid = (uint64_t)ctx->sm_count * (uint64_t)acps;
-        if (agrid > need) agrid = need;
-        if (agrid < 1) agrid = 1;
-        if (agrid > (uint64_t)MAX_PARTIALS - 8) agrid = MAX_PARTIALS - 8;
-        SpanGuard g(ctx, KC_SPMV);
-        ak<<<(unsigned)agrid, 256, smem, ctx->stream>>>(p);
-        NGSB_CUDA(cudaGetLastError());
-        return NGSB_OK;
-    }
     SpanGuard g(ctx, KC_SPMV);
     kern<<<(unsigned)grid, 256, 0, ctx->stream>>>(p);
     NGSB_CUDA(cudaGetLastError());

@@ -557,7 +557,6 @@ extern "C" int ngsb_ctx_set_option(ngsb_ctx *ctx, const char *name, long value)
     else if (!strcmp(name, "sell_schedule")) { NGSB_REQUIRE(value >= 0 && value <= 2, "sell_schedule must be 0 (off), 1 (auto), 2 (on)"); ctx->sell_schedule = value; }
     else if (!strcmp(name, "sell_pf_steps")) { NGSB_REQUIRE(value >= 0 && value <= 16, "sell_pf_steps out of range"); ctx->sell_pf_steps = value; }
     else if (!strcmp(name, "sell_pf_next")) { NGSB_REQUIRE(value >= 0 && value <= 64, "sell_pf_next out of range"); ctx->sell_pf_next = value; }
-    else if (!strcmp(name, "sell_stages")) { NGSB_REQUIRE(value >= 2 && value <= 6, "sell_stages out of range"); ctx->sell_stages = value; }
     else if (!strcmp(name, "sell_c16")) { NGSB_REQUIRE(value == 0 || value == 1, "sell_c16 must be 0 or 1"); ctx->sell_c16 = value; }
     else if (!strcmp(name, "sell_sigma")) { NGSB_REQUIRE(value >= -1 && value <= (1 << 24), "sell_sigma out of range"); ctx->sell_sigma = value; }
     else if (!strcmp(name, "sell_cap")) { NGSB_REQUIRE(value >= 0 && value <= (1 << 20), "sell_cap out of range"); ctx->sell_cap = value; }

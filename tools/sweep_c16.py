@@ -46,7 +46,8 @@ if mode == "prefetch":
         for pf, nx in ((0, 0), (1, 0), (2, 0), (3, 0), (0, 8), (2, 8), (1, 8), (2, 16), (3, 16), (4, 8)):
             run("c16 ctas/sm=%d pf_steps=%d pf_next=%d" % (cps, pf, nx), sell_c16=1, spmv_ctas_per_sm=cps, sell_pf_steps=pf, sell_pf_next=nx)
 else:
-    for stages in (2, 3, 4, 5, 6):
-        for cps in (0, 1, 2, 3, 4):
-            run("async staged: stages=%d ctas/sm=%d" % (stages, cps), sell_c16=1, sell_variant=3, sell_stages=stages, spmv_ctas_per_sm=cps)
+    for rep in range(2):
+        for var in (0, 3):
+            for cps in (0, 6, 12):
+                run("variant %d (3 = L2 eviction policies) ctas/sm=%d" % (var, cps), sell_c16=1, sell_variant=var, spmv_ctas_per_sm=cps)
     ctx.set_option("sell_variant", 0)
