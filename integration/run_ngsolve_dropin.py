@@ -92,4 +92,58 @@ with TaskManager():
     gfu2.vec.data = res4
     diff.data = gfu.vec - gfu2.vec
     out.update(bj_rel_diff=Norm(diff) / Norm(gfu.vec))
+
+    # ---- the other two entry kinds through the same registry: Mat<3,3,double> (elasticity, H1 dim=3) and Complex (Helmholtz, GMRES)
+    def attempt(tag, fn):
+        try:
+            fn()
+        except Exception as e:                       # noqa: BLE001 -- report, keep the other results
+            out[tag + "_error"] = str(e)[:300]
+
+    def elasticity():
+        mesh2 = Mesh(unit_cube.GenerateMesh(maxh=0.12))
+        fe = H1(mesh2, order=2, dim=3, dirichlet="back")
+        uu, vv = fe.TnT()
+        E, nu = 210.0, 0.2
+        mu, lam = E / 2 / (1 + nu), E * nu / ((1 + nu) * (1 - 2 * nu))
+        eps = lambda w: 0.5 * (grad(w) + grad(w).trans)
+        aa = BilinearForm(2 * mu * InnerProduct(eps(uu), eps(vv)) * dx + lam * Trace(grad(uu)) * Trace(grad(vv)) * dx).Assemble()
+        ff = LinearForm(CoefficientFunction((0, 0, -1)) * vv * dx).Assemble()
+        jj = aa.mat.CreateSmoother(fe.FreeDofs())
+        g1 = GridFunction(fe)
+        ic = CGSolver(aa.mat, jj, precision=1e-8, maxsteps=20000, printrates=False)
+        g1.vec.data = ic * ff.vec
+        ad, jd, fd = aa.mat.CreateDeviceMatrix(), jj.CreateDeviceMatrix(), ff.vec.CreateDeviceVector()
+        idv = CGSolver(ad, jd, precision=1e-8, maxsteps=20000, printrates=False)
+        r = (idv * fd).Evaluate()
+        g2 = GridFunction(fe)
+        g2.vec.data = r
+        dd = g1.vec.CreateVector()
+        dd.data = g1.vec - g2.vec
+        out.update(b3_mat_type=type(aa.mat).__name__, b3_ndof=fe.ndof, b3_cpu_steps=ic.GetSteps(), b3_dev_steps=idv.GetSteps(),
+                   b3_rel_diff=Norm(dd) / Norm(g1.vec), b3_is_host_object=ad is aa.mat)
+
+    def helmholtz():
+        mesh3 = Mesh(unit_cube.GenerateMesh(maxh=0.12))
+        fe = H1(mesh3, order=3, complex=True)
+        uu, vv = fe.TnT()
+        om = 6.0
+        aa = BilinearForm(grad(uu) * grad(vv) * dx - om * om * uu * vv * dx - 1j * om * uu * vv * ds).Assemble()
+        ff = LinearForm(exp(-40 * ((x - 0.5) ** 2 + (y - 0.5) ** 2 + (z - 0.5) ** 2)) * vv * dx).Assemble()
+        jj = aa.mat.CreateSmoother(fe.FreeDofs())
+        g1 = GridFunction(fe)
+        ic = GMRESSolver(aa.mat, jj, printrates=False, precision=1e-8, maxsteps=400)
+        g1.vec.data = ic * ff.vec
+        ad, jd, fd = aa.mat.CreateDeviceMatrix(), jj.CreateDeviceMatrix(), ff.vec.CreateDeviceVector()
+        idv = GMRESSolver(ad, jd, printrates=False, precision=1e-8, maxsteps=400)
+        r = (idv * fd).Evaluate()
+        g2 = GridFunction(fe)
+        g2.vec.data = r
+        dd = g1.vec.CreateVector()
+        dd.data = g1.vec - g2.vec
+        out.update(z_mat_type=type(aa.mat).__name__, z_ndof=fe.ndof, z_cpu_gmres_steps=ic.GetSteps(), z_dev_gmres_steps=idv.GetSteps(),
+                   z_rel_diff=Norm(dd) / Norm(g1.vec), z_is_host_object=ad is aa.mat)
+
+    attempt("b3", elasticity)
+    attempt("z", helmholtz)
 print(json.dumps(out))
