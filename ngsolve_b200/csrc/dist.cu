@@ -879,7 +879,6 @@ extern "C" int ngsb_parmat_cg_solve(const ngsb_parmat *P, const ngsb_jacobi *C, 
         const void *key[8] = {u->d, d, w, s, as, C, (const void *)(intptr_t)ip_mode, d_hist};
         const bool hit = Pm->graph_exec && Pm->g_batch == batch && memcmp(key, Pm->g_key, sizeof(key)) == 0;
         if (!hit) {
-            if (Pm->graph_exec) { cudaGraphExecDestroy(Pm->graph_exec); Pm->graph_exec = nullptr; }
             cudaGraph_t graph = nullptr;
             const uint64_t launches_before = ctx->launches;
             cu(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
@@ -888,7 +887,15 @@ extern "C" int ngsb_parmat_cg_solve(const ngsb_parmat *P, const ngsb_jacobi *C, 
                 cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
                 ctx->launches = launches_before;
                 if (rc == NGSB_OK) cu(ce);
-                if (rc == NGSB_OK) cu(cudaGraphInstantiate(&Pm->graph_exec, graph, 0));
+                if (rc == NGSB_OK && Pm->graph_exec) {      // same topology, other pointers: update in place
+                    cudaGraphExecUpdateResultInfo info;
+                    if (cudaGraphExecUpdate(Pm->graph_exec, graph, &info) != cudaSuccess) {
+                        cudaGetLastError();
+                        cudaGraphExecDestroy(Pm->graph_exec);
+                        Pm->graph_exec = nullptr;
+                    }
+                }
+                if (rc == NGSB_OK && !Pm->graph_exec) cu(cudaGraphInstantiate(&Pm->graph_exec, graph, 0));
                 if (graph) cudaGraphDestroy(graph);
                 if (rc == NGSB_OK) { memcpy(Pm->g_key, key, sizeof(key)); Pm->g_batch = batch; }
             }

@@ -466,3 +466,26 @@ def test_projector_and_diagonal_matrix(la):
     r = np.asarray(g["f"]) - oA.mult(u.NumPy())
     assert np.linalg.norm(r[free]) <= 1e-6 * np.linalg.norm(np.asarray(g["f"])[free])
     assert 10 < inv.iterations < 3000
+
+
+def test_cg_graph_is_updated_for_fresh_result_vectors(la):
+    """`u = (inv * f).Evaluate()` hands a new result vector to every solve: the instantiated CUDA graph of the iteration
+    batch is updated in place (cudaGraphExecUpdate) and the solves are identical to a solve into a fixed vector"""
+    g = load_golden("poisson_h1p3")
+    A = host_matrix(la, g)
+    dev = A.CreateDeviceMatrix()
+    jac = A.CreateSmoother(la.BitArray(g["freebits"]))
+    inv = la.CGSolver(dev, jac, precision=1e-10, maxsteps=1000)
+    f = vec(la, g, g["f"])
+    u0 = f.CreateVector()
+    inv.Mult(f, u0)
+    ref, steps = u0.NumPy().copy(), inv.GetSteps()
+    keep = []
+    for k in range(4):
+        fk = vec(la, g, (k + 1.0) * g["f"])             # new rhs vector, new result vector
+        uk = (inv * fk).Evaluate()
+        keep.append(uk)                                  # keep them alive so that the allocator cannot hand back the same address
+        assert inv.GetSteps() == steps
+        assert relerr(uk.NumPy().reshape(-1), (k + 1.0) * ref) <= 1e-12
+    inv.Mult(f, u0)
+    assert np.array_equal(u0.NumPy(), ref)
