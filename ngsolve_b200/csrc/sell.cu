@@ -885,6 +885,8 @@ int sell_launch(const SpmvArgs &a)
         case 1: kern = sell_spmv_kernel<NGSB_REAL, 0, 5>; break;
         case 2: kern = sell_spmv_kernel<NGSB_REAL, 1, 8>; break;
         case 3: kern = sell_spmv_kernel<NGSB_REAL, 2, 4, true>; break;      // + L2 eviction policies in the compressed loop
+        case 4: kern = sell_spmv_kernel<NGSB_REAL, 2, 5>; break;            // pipelined loop squeezed into 48 registers (5 CTAs/SM)
+        case 5: kern = sell_spmv_kernel<NGSB_REAL, 2, 6>; break;            // ... 40 registers (6 CTAs/SM)
         default: kern = sell_spmv_kernel<NGSB_REAL, 2, 4>; break;
         }
     } else if (A->kind == NGSB_COMPLEX) kern = var == 1 ? sell_spmv_kernel<NGSB_COMPLEX, 0, 5> : sell_spmv_kernel<NGSB_COMPLEX, 2, 4>;
