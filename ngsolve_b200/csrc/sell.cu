@@ -177,7 +177,34 @@ __global__ void __launch_bounds__(256, MINB) sell_spmv_kernel(const SellParams p
             }
             const uint32_t pfd = (uint32_t)p.pf_steps * 4;
 #define NGSB_C16(h, b, c0, c1) { c0 = (b).x + (int)((h) & 0xffffu); c1 = (b).y + (int)((h) >> 16); }
-            if (np >= 4) {
+            if (VAR == 4 && np >= 4) {
+                // "late values": only the index stream (4 + 8 registers) is prefetched one step ahead; the values of a step are
+                // requested together with its x gathers.  Same bytes in flight per warp and step as the value-prefetching loop
+                // below, 16 registers fewer -> 5 resident CTAs instead of 4.
+                int ca0, ca1, cb0, cb1, cc0, cc1, cd0, cd1;
+                {
+                    const unsigned int ha = ldp_u32<POL>(h2, polf), hb = ldp_u32<POL>(h2 + 32, polf), hc = ldp_u32<POL>(h2 + 64, polf), hd = ldp_u32<POL>(h2 + 96, polf);
+                    const int2 ba = __ldg(b2), bb = __ldg(b2 + 1), bc = __ldg(b2 + 2), bd = __ldg(b2 + 3);
+                    NGSB_C16(ha, ba, ca0, ca1) NGSB_C16(hb, bb, cb0, cb1) NGSB_C16(hc, bc, cc0, cc1) NGSB_C16(hd, bd, cd0, cd1)
+                }
+                for (q = 0; q + 4 <= np; q += 4) {
+                    const double x0 = ldp_x<POL>(p.x + ca0, poll), x1 = ldp_x<POL>(p.x + ca1, poll), x2 = ldp_x<POL>(p.x + cb0, poll), x3 = ldp_x<POL>(p.x + cb1, poll);
+                    const double x4 = ldp_x<POL>(p.x + cc0, poll), x5 = ldp_x<POL>(p.x + cc1, poll), x6 = ldp_x<POL>(p.x + cd0, poll), x7 = ldp_x<POL>(p.x + cd1, poll);
+                    const double2 va = ldp_d2<POL>(v2 + (q + 0) * 32, polf), vb = ldp_d2<POL>(v2 + (q + 1) * 32, polf);
+                    const double2 vc = ldp_d2<POL>(v2 + (q + 2) * 32, polf), vd = ldp_d2<POL>(v2 + (q + 3) * 32, polf);
+                    const bool more = q + 8 <= np;
+                    unsigned int ha = 0, hb = 0, hc = 0, hd = 0;
+                    int2 ba = make_int2(0, 0), bb = ba, bc = ba, bd = ba;
+                    if (more) {
+                        ha = ldp_u32<POL>(h2 + (q + 4) * 32, polf); hb = ldp_u32<POL>(h2 + (q + 5) * 32, polf);
+                        hc = ldp_u32<POL>(h2 + (q + 6) * 32, polf); hd = ldp_u32<POL>(h2 + (q + 7) * 32, polf);
+                        ba = __ldg(b2 + q + 4); bb = __ldg(b2 + q + 5); bc = __ldg(b2 + q + 6); bd = __ldg(b2 + q + 7);
+                    }
+                    s0 = fma(va.x, x0, s0); s0 = fma(va.y, x1, s0); s0 = fma(vb.x, x2, s0); s0 = fma(vb.y, x3, s0);
+                    s0 = fma(vc.x, x4, s0); s0 = fma(vc.y, x5, s0); s0 = fma(vd.x, x6, s0); s0 = fma(vd.y, x7, s0);
+                    if (more) { NGSB_C16(ha, ba, ca0, ca1) NGSB_C16(hb, bb, cb0, cb1) NGSB_C16(hc, bc, cc0, cc1) NGSB_C16(hd, bd, cd0, cd1) }
+                }
+            } else if (np >= 4) {
                 double2 va = ldp_d2<POL>(v2, polf), vb = ldp_d2<POL>(v2 + 32, polf), vc = ldp_d2<POL>(v2 + 64, polf), vd = ldp_d2<POL>(v2 + 96, polf);
                 int ca0, ca1, cb0, cb1, cc0, cc1, cd0, cd1;
                 {
@@ -249,7 +276,7 @@ __global__ void __launch_bounds__(256, MINB) sell_spmv_kernel(const SellParams p
                     double x0 = __ldg(p.x + ca.x), x1 = __ldg(p.x + ca.y), x2 = __ldg(p.x + cb.x), x3 = __ldg(p.x + cb.y);
                     s0 = fma(va.x, x0, s0); s0 = fma(va.y, x1, s0); s0 = fma(vb.x, x2, s0); s0 = fma(vb.y, x3, s0);
                 }
-            if (VAR == 0)
+            if (VAR == 0 || VAR == 4)
             for (; q + 4 <= np; q += 4) {
                 double2 va = ldg_stream_d2(v2 + (q + 0) * 32), vb = ldg_stream_d2(v2 + (q + 1) * 32);
                 double2 vc = ldg_stream_d2(v2 + (q + 2) * 32), vd = ldg_stream_d2(v2 + (q + 3) * 32);
@@ -898,8 +925,9 @@ int sell_launch(const SpmvArgs &a)
         case 1: kern = sell_spmv_kernel<NGSB_REAL, 0, 5>; break;
         case 2: kern = sell_spmv_kernel<NGSB_REAL, 1, 8>; break;
         case 3: kern = sell_spmv_kernel<NGSB_REAL, 2, 4, true>; break;      // + L2 eviction policies in the compressed loop
-        case 4: kern = sell_spmv_kernel<NGSB_REAL, 2, 5>; break;            // pipelined loop squeezed into 48 registers (5 CTAs/SM)
-        case 5: kern = sell_spmv_kernel<NGSB_REAL, 2, 6>; break;            // ... 40 registers (6 CTAs/SM)
+        case 4: kern = sell_spmv_kernel<NGSB_REAL, 4, 5>; break;            // compressed loop with late values: 48 registers, 5 CTAs/SM
+        case 5: kern = sell_spmv_kernel<NGSB_REAL, 4, 4>; break;            // the same loop at 4 CTAs/SM (A/B)
+        case 6: kern = sell_spmv_kernel<NGSB_REAL, 4, 6>; break;            // ... at 6 CTAs/SM (40 registers)
         default: kern = sell_spmv_kernel<NGSB_REAL, 2, 4>; break;
         }
     } else if (A->kind == NGSB_COMPLEX) kern = var == 1 ? sell_spmv_kernel<NGSB_COMPLEX, 0, 5> : sell_spmv_kernel<NGSB_COMPLEX, 2, 4>;

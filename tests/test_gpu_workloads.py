@@ -173,7 +173,7 @@ def test_kernel_variants_are_bit_exact(n):
     y0 = rng.random(A.height)
     out = {}
     try:
-        for var in (0, 1, 2, 3, 4, 5):
+        for var in (0, 1, 2, 3, 4, 5, 6):
             ctx.set_option("sell_variant", var)
             y = A.CreateColVector()
             A.Mult(x, y)

@@ -47,7 +47,7 @@ if mode == "prefetch":
             run("c16 ctas/sm=%d pf_steps=%d pf_next=%d" % (cps, pf, nx), sell_c16=1, spmv_ctas_per_sm=cps, sell_pf_steps=pf, sell_pf_next=nx)
 else:
     for rep in range(2):
-        for var in (0, 4, 5):
-            for cps in (0, 10, 12):
+        for var in (0, 4, 5, 6):
+            for cps in (0, 5, 6, 8, 10, 12, 15):
                 run("variant %d (3 = L2 eviction policies) ctas/sm=%d" % (var, cps), sell_c16=1, sell_variant=var, spmv_ctas_per_sm=cps)
     ctx.set_option("sell_variant", 0)
