@@ -45,6 +45,10 @@ if mode == "prefetch":
     for cps in (8, 6, 5, 4, 12):
         for pf, nx in ((0, 0), (1, 0), (2, 0), (3, 0), (0, 8), (2, 8), (1, 8), (2, 16), (3, 16), (4, 8)):
             run("c16 ctas/sm=%d pf_steps=%d pf_next=%d" % (cps, pf, nx), sell_c16=1, spmv_ctas_per_sm=cps, sell_pf_steps=pf, sell_pf_next=nx)
+elif mode == "grid":
+    for rep in range(2):
+        for cps in (8, 10, 11, 12, 13, 14, 15, 16, 18, 19, 20, 23, 24, 27, 28, 31, 32, 40, 48, 64, 27):
+            run("default kernel, grid = %d CTAs/SM" % cps, sell_c16=1, sell_variant=0, spmv_ctas_per_sm=cps)
 else:
     for rep in range(2):
         for var in (0, 4, 5, 6):
