@@ -104,7 +104,7 @@ inline size_t kind_scalars(int kind) { return kind == NGSB_REAL ? 1 : (kind == N
 inline size_t kind_matscalars(int kind) { return kind == NGSB_REAL ? 1 : (kind == NGSB_COMPLEX ? 2 : 9); }
 inline bool kind_valid(int kind) { return kind == NGSB_REAL || kind == NGSB_COMPLEX || kind == NGSB_BLOCK3; }
 
-static const int MAX_PARTIALS = 4096;
+static const int MAX_PARTIALS = 16384;
 
 // RAII-less helper: record a timed span around a launch when ctx->timing is on
 struct SpanGuard {

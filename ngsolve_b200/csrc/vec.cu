@@ -551,7 +551,7 @@ extern "C" int ngsb_ctx_set_option(ngsb_ctx *ctx, const char *name, long value)
     NGSB_REQUIRE(ctx && name, "ngsb_ctx_set_option: NULL argument");
     if (!strcmp(name, "spmv_algo")) { NGSB_REQUIRE(value >= 0 && value <= 3, "spmv_algo must be 0 (auto = SELL), 1 (sub-warp CSR), 2 (TMA-streamed CSR), 3 (SELL)"); ctx->spmv_algo = value; }
     else if (!strcmp(name, "cg_batch")) { NGSB_REQUIRE(value >= 1 && value <= 4096, "cg_batch out of range"); ctx->cg_batch = value; }
-    else if (!strcmp(name, "spmv_ctas_per_sm")) { NGSB_REQUIRE(value >= 0 && value <= 16, "spmv_ctas_per_sm out of range"); ctx->spmv_ctas_per_sm = value; }
+    else if (!strcmp(name, "spmv_ctas_per_sm")) { NGSB_REQUIRE(value >= 0 && value <= 110, "spmv_ctas_per_sm out of range"); ctx->spmv_ctas_per_sm = value; }
     else if (!strcmp(name, "timing")) { ctx->timing = value ? 1 : 0; }
     else if (!strcmp(name, "sell_variant")) { NGSB_REQUIRE(value >= 0 && value <= 8, "sell_variant out of range"); ctx->sell_variant = value; }
     else if (!strcmp(name, "sell_schedule")) { NGSB_REQUIRE(value >= 0 && value <= 2, "sell_schedule must be 0 (off), 1 (auto), 2 (on)"); ctx->sell_schedule = value; }

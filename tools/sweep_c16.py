@@ -47,7 +47,7 @@ if mode == "prefetch":
             run("c16 ctas/sm=%d pf_steps=%d pf_next=%d" % (cps, pf, nx), sell_c16=1, spmv_ctas_per_sm=cps, sell_pf_steps=pf, sell_pf_next=nx)
 elif mode == "grid":
     for rep in range(2):
-        for cps in (8, 10, 11, 12, 13, 14, 15, 16, 18, 19, 20, 23, 24, 27, 28, 31, 32, 40, 48, 64, 27):
+        for cps in (8, 16, 20, 24, 28, 32, 36, 40, 48, 56, 64, 80, 96, 110):
             run("default kernel, grid = %d CTAs/SM" % cps, sell_c16=1, sell_variant=0, spmv_ctas_per_sm=cps)
 else:
     for rep in range(2):
