@@ -69,7 +69,7 @@ def tiled_fixture(name, copies):
     return RP, COL, VAL, np.tile(g["f"], copies), np.tile(bits, copies)
 
 
-def run(cfg, scale):
+def run(cfg, scale, spmv_only=False):
     ctx = la.default_context()
     t0 = time.perf_counter()
     name = cfg["name"]
@@ -101,6 +101,8 @@ def run(cfg, scale):
                spmv_ms=ms, spmv_bytes=b, spmv_gbs=gbs, spmv_frac_of_measured_peak=gbs / peak(), spmv_pct_of_8TBs=gbs / 80.0,
                sell_padding=ent / max(1, A.nze) - 1.0, sell_overflow_rows=ovf, setup_s=setup,
                stored_bytes=sb, spmv_gbs_on_stored_bytes=sb / ms / 1e6, c16_share_of_entries=c16 / max(1, ent))
+    if spmv_only:
+        return out
     u = f.CreateVector()
     K = cfg["steps"]
     if cfg["solver"] == "cg":
@@ -155,10 +157,16 @@ def main():
     ap.add_argument("which", nargs="*", default=["c1", "c2", "c4", "c5"])
     ap.add_argument("--out", default=None)
     ap.add_argument("--scale", type=float, default=1.0, help="scale the number of rows (smoke runs)")
+    ap.add_argument("--opt", action="append", default=[], help="context option name=value (e.g. spmv_ctas_per_sm=96), repeatable")
+    ap.add_argument("--spmv-only", action="store_true")
     a = ap.parse_args()
     lines = []
+    for o in a.opt:
+        name, val = o.split("=")
+        la.default_context().set_option(name, int(val))
     for k in a.which:
-        r = run(CONFIGS[k], a.scale)
+        r = run(CONFIGS[k], a.scale, a.spmv_only)
+        r["options"] = a.opt
         print(json.dumps(r), flush=True)
         lines.append(r)
         import gc
