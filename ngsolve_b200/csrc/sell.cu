@@ -17,8 +17,8 @@
 // longer than `cap` keep their first cap entries in the slice and the rest in a small overflow CSR
 // that a second kernel reduces beforehand.
 //
-// The kernel is persistent (grid = SMs x resident CTAs, 8 slices per CTA step, interleaved so that
-// the CTAs sweep the matrix as one moving window and x lines are shared through L1/L2) and fuses
+// Grid-stride kernel (about 96 CTAs per SM, 8 slices per CTA step, interleaved so that the resident CTAs sweep each
+// stripe of the schedule as one moving window and x lines are shared through L1/L2); it fuses
 // y = s A x (+ y), the dot <dotvec, result> and the CG scalar step (deterministic last-block finish).
 #include "spmv.cuh"
 
@@ -932,9 +932,12 @@ int sell_launch(const SpmvArgs &a)
         }
     } else if (A->kind == NGSB_COMPLEX) kern = var == 1 ? sell_spmv_kernel<NGSB_COMPLEX, 0, 5> : sell_spmv_kernel<NGSB_COMPLEX, 2, 4>;
     else kern = sell_spmv_kernel<NGSB_BLOCK3, 0, 5>;
-    int occ = 0;
-    NGSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, 0));
-    long cps = ctx->spmv_ctas_per_sm > 0 ? ctx->spmv_ctas_per_sm : (A->kind != NGSB_BLOCK3 && (var == 0 || var == 3) ? 8 : (occ > 0 ? occ : 4));
+    // Grid: CTA b walks the slices b*8+w, b*8+w + 8*grid, ... so the CTAs resident at one time form a window of adjacent
+    // slices inside every stripe of 8*grid slices.  With a small (persistent) grid the whole schedule is swept once per
+    // wave of CTAs and x is fetched again each time; with ~96 CTAs per SM there are only a few dozen wide stripes, every
+    // window slides through its stripe once and the x lines are re-used out of L2.  Measured at 111 M dofs: 10.66 ms with
+    // 8 CTAs/SM, 9.31 ms with 96 (profiles/r1_sweep_c16_grid_size.txt); 3x3 blocks +18 %, complex +9 %.
+    long cps = ctx->spmv_ctas_per_sm > 0 ? ctx->spmv_ctas_per_sm : 96;
     uint64_t grid = (uint64_t)ctx->sm_count * (uint64_t)cps;
     const uint64_t need = ((uint64_t)A->nslices + 7) / 8;
     if (grid > need) grid = need;
@@ -955,7 +958,7 @@ int sell_launch_multi4(const ngsb_csr *A, const double *const x[4], double *cons
     p.slice_off = A->d_slice_off; p.slice_src = A->d_slice_src; p.row_of = A->d_row_of; p.scol = A->d_scol; p.sval = A->d_sval;
     p.nslices = A->nslices;
     for (int k = 0; k < 4; k++) { p.x[k] = x[k]; p.y[k] = y[k]; p.alpha[k] = alpha[k]; }
-    uint64_t grid = (uint64_t)ctx->sm_count * 4;
+    uint64_t grid = (uint64_t)ctx->sm_count * (uint64_t)(ctx->spmv_ctas_per_sm > 0 ? ctx->spmv_ctas_per_sm : 96);
     const uint64_t need = ((uint64_t)A->nslices + 7) / 8;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
