@@ -41,6 +41,8 @@ def parse():
     ap.add_argument("--size", type=int, default=160, help="cubes per axis of the global grid; dofs = (3*size+1)^3 "
                     "(160 -> 111 M dofs; divisible by 8 so that the z-slabs of the multi-GPU runs are equal)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--opt", action="append", default=[], help="library option name=value set on the context before the matrix "
+                    "is created (e.g. dist_overlap=1, spmv_ctas_per_sm=64); repeatable; recorded in config.options")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-full-solve", action="store_true")
     ap.add_argument("--cpu-iters", type=int, default=150)
@@ -234,6 +236,9 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = la.Context(local_rank)
+    for o in args.opt:
+        name, val = o.split("=")
+        ctx.set_option(name, int(val))
     m, K, Wm = args.size, args.steps, args.warmup
     G = (m, m, m)
     t_setup = time.perf_counter()
@@ -408,7 +413,9 @@ def run_b200(args):
             "config": {"workload": workload_name(m), "global_dofs": global_ndof, "nnz_total": nnz_sum, "rows_per_gpu": ndof_local,
                        "precond": "Jacobi (freedofs-masked)",
                        "partition": "1 box" if world == 1 else "%d z-slabs of elements, %s" % (world, "interface exchange + scalar all-reduces by P2P stores "
-                                    "into peer memory inside the solver kernels (no NCCL call per iteration)" if pmat.peer_memory else "NCCL send/recv halo + NCCL all-reduce"),
+                                    "into peer memory inside the solver kernels (no NCCL call per iteration)" if pmat.peer_memory else "NCCL send/recv halo + NCCL all-reduce")
+                                    + ("; interface slices first, pushed while the interior slices are multiplied (%d + %d slices)" % pmat.overlap[1:] if pmat.overlap[0] else ""),
+                       "options": list(args.opt),
                        "l2": "inputs (%.1f GB per GPU) far larger than the 126 MB L2" % (b_spmv / 1e9),
                        "setup_s": setup_s, "full_solve": full,
                        "cg_gbs_per_gpu": b_cg * value / 1e9, "cg_bytes_per_iteration_per_gpu": b_cg,

@@ -75,7 +75,7 @@ void *ngsb_ctx_stream(ngsb_ctx *ctx);                   /* cudaStream_t */
 /* kernels of this library launched on ctx so far (bench.py's gpu_launches) */
 int ngsb_ctx_launch_count(const ngsb_ctx *ctx, uint64_t *count);
 /* tuning knobs: "spmv_algo" (0 auto = 3; 1 sub-warp CSR; 2 TMA-streamed CSR; 3 SELL-32),
- * "cg_batch", "spmv_ctas_per_sm", "timing", and -- read when a matrix is created --
+ * "cg_batch", "spmv_ctas_per_sm", "timing", "dist_overlap" (0/1, read by ngsb_parmat_create), and -- read when a matrix is created --
  * "sell_cap", "spmv_tile", "spmv_ncw", "spmv_stages", "spmv_subwarp" (0 = default).
  * Unknown names fail with NGSB_ERR_INVALID. */
 int ngsb_ctx_set_option(ngsb_ctx *ctx, const char *name, long value);
@@ -275,6 +275,11 @@ int ngsb_parmat_create_ex(ngsb_comm *comm, const ngsb_csr *local, const uint64_t
 int ngsb_parmat_destroy(ngsb_parmat *P);
 int ngsb_parmat_info(const ngsb_parmat *P, int *peer_memory, int *n_neighbours, size_t *n_exchange,
                      size_t *n_interface);
+/* option "dist_overlap" (set on the context before ngsb_parmat_create, peer-memory data path): the CG product runs the
+ * SELL slices holding interface rows first, pushes them, and runs the interior slices while the values travel -- the
+ * overlap the reference gets from MPI_Isend/Irecv around its local MultAdd (parallel/parallelvvector.cpp:452-475).
+ * Reports whether the split is active and the two slice counts. */
+int ngsb_parmat_overlap_info(const ngsb_parmat *P, int *enabled, size_t *interface_slices, size_t *interior_slices);
 /* masterdofs bytes as the reference derives them (lowest rank owns), n entries */
 int ngsb_parmat_masterdofs(const ngsb_parmat *P, uint8_t *ismaster);
 /* JacobiPrecond of a ParallelMatrix: diagonal summed over the sharing ranks, then inverted

@@ -95,6 +95,7 @@ PROTOTYPES = {
     "ngsb_parmat_create": [_vp, _vp, _vp, _vp, _pvp],
     "ngsb_parmat_create_ex": [_vp, _vp, _vp, _vp, _vp, _vp, _pvp],
     "ngsb_parmat_info": [_vp, C.POINTER(_i), C.POINTER(_i), C.POINTER(_sz), C.POINTER(_sz)],
+    "ngsb_parmat_overlap_info": [_vp, C.POINTER(_i), C.POINTER(_sz), C.POINTER(_sz)],
     "ngsb_parmat_destroy": [_vp],
     "ngsb_parmat_masterdofs": [_vp, _vp],
     "ngsb_parmat_jacobi_create": [_vp, _vp, _pvp],

@@ -66,10 +66,17 @@ struct ngsb_parmat {
     char *peer_halo[NGSB_MAX_RANKS] = {};         // mapped, per neighbour index
     char *d_local = nullptr;                      // local only: sequence number + CTA counters
     PeerHalo *d_H = nullptr;
+    // interface-first split of the local product (option "dist_overlap", peer-memory mode): scheduled SELL slices that
+    // hold at least one interface row / all the others, both in ascending schedule order
+    bool overlap = false;
+    uint32_t *d_list_bnd = nullptr, *d_list_int = nullptr;
+    uint32_t n_bnd = 0, n_int = 0;
+    double *d_red_b = nullptr;                    // <s, A s> over the interface slices (2 doubles)
     // cached CUDA graph of one batch of CG iterations (peer-memory mode)
     cudaGraphExec_t graph_exec = nullptr;
     const void *g_key[8] = {};
     long g_batch = 0;
+    uint64_t g_launches = 0;                      // kernels in one batch of the captured graph
 };
 
 namespace ngsb {
@@ -273,15 +280,18 @@ __global__ void __launch_bounds__(256) halo_push_kernel(const PeerHalo *__restri
 }
 
 // second half: wait for the neighbours' flags, add the received copies (ascending rank order per dof).  The last CTA
-// completes the exchange and, inside the CG loop (fin = 1), finishes kss = <s, A s>: all-reduce + al = wd / kss.
+// completes the exchange and, inside the CG loop (fin >= 1), finishes kss = <s, A s>: all-reduce + al = wd / kss.
+// fin = 2 (interface-first split): the local dot is complete only after the interior product that ran behind the push,
+// so this kernel publishes the partial (`red`) itself before it waits.
 __global__ void __launch_bounds__(256) halo_unpack_kernel(const PeerHalo *__restrict__ H, double *__restrict__ v,
                                                          const int32_t *__restrict__ if_dof, const uint32_t *__restrict__ if_first,
                                                          const uint32_t *__restrict__ if_pos, size_t nif, int es, CgState *st,
-                                                         const PeerReduce *R, int fin)
+                                                         const PeerReduce *R, int fin, const double *red)
 {
     if (st && st->done) return;
     const unsigned long long s = *(volatile unsigned long long *)H->seq + 1;
     const unsigned long long par = s & 1;
+    if (fin == 2 && R && blockIdx.x == 0 && threadIdx.x == 0) pr_push(*R, red[0], red[1]);
     if ((int)threadIdx.x < H->npeers) peer_wait(H->flags + par * NGSB_MAX_RANKS + H->peer_rank[threadIdx.x], s, H->err);
     __syncthreads();
     const double *recv = H->recv + par * H->stride;
@@ -301,7 +311,7 @@ __global__ void __launch_bounds__(256) halo_unpack_kernel(const PeerHalo *__rest
         if (t == gridDim.x - 1) {
             H->counter[1] = 0;
             *(volatile unsigned long long *)H->seq = s;
-            if (fin == 1 && R && st) {
+            if (fin >= 1 && R && st) {
                 double2 tot = pr_wait_sum(*R);
                 cg_finalize_kss(st, tot);
             }
@@ -343,8 +353,8 @@ static int cumulate_es(const ngsb_parmat *P, double *v, int es, CgState *st = nu
         SpanGuard g(ctx, KC_OTHER);
         const PeerReduce *R = fin ? comm->d_R : nullptr;
         halo_push_kernel<<<halo_grid(ctx, P->nex), 256, 0, ctx->stream>>>(P->d_H, v, P->d_exdofs, P->nex, es, st, R, red);
-        halo_unpack_kernel<<<halo_grid(ctx, P->nif), 256, 0, ctx->stream>>>(P->d_H, v, P->d_if_dof, P->d_if_first, P->d_if_pos, P->nif, es, st, R, fin);
-        ctx->launches += 2;
+        halo_unpack_kernel<<<halo_grid(ctx, P->nif), 256, 0, ctx->stream>>>(P->d_H, v, P->d_if_dof, P->d_if_first, P->d_if_pos, P->nif, es, st, R, fin, red);
+        ctx->launches += 1;          // two kernels, one counted by the SpanGuard
         NGSB_CUDA(cudaGetLastError());
         return NGSB_OK;
     }
@@ -387,6 +397,26 @@ static int cumulate_es(const ngsb_parmat *P, double *v, int es, CgState *st = nu
 }
 
 static int cumulate_raw(const ngsb_parmat *P, double *v) { return cumulate_es(P, v, P->es); }
+
+// the two halves of the peer-memory Cumulate as separate calls (interface-first split of the CG product): the push
+// carries no scalar, the unpack publishes `red` itself (fin = 2) and finishes kss
+static int halo_push_only(const ngsb_parmat *P, const double *v, CgState *st)
+{
+    ngsb_ctx *ctx = P->comm->ctx;
+    SpanGuard g(ctx, KC_OTHER);
+    halo_push_kernel<<<halo_grid(ctx, P->nex), 256, 0, ctx->stream>>>(P->d_H, v, P->d_exdofs, P->nex, P->es, st, nullptr, nullptr);
+    NGSB_CUDA(cudaGetLastError());
+    return NGSB_OK;
+}
+static int halo_unpack_fin(const ngsb_parmat *P, double *v, CgState *st, const double *red)
+{
+    ngsb_ctx *ctx = P->comm->ctx;
+    SpanGuard g(ctx, KC_OTHER);
+    halo_unpack_kernel<<<halo_grid(ctx, P->nif), 256, 0, ctx->stream>>>(P->d_H, v, P->d_if_dof, P->d_if_first, P->d_if_pos, P->nif, P->es, st,
+                                                                        P->comm->d_R, 2, red);
+    NGSB_CUDA(cudaGetLastError());
+    return NGSB_OK;
+}
 
 __global__ void mask_zero_kernel(double *v, const uint8_t *master, size_t n, int es)
 {
@@ -612,6 +642,54 @@ static int parmat_setup_p2p(ngsb_parmat *P, const uint64_t *ex_first)
     return NGSB_OK;
 }
 
+// option "dist_overlap": which scheduled SELL slices hold an interface row (they are multiplied first and pushed)
+__global__ void __launch_bounds__(256) mark_interface_slices_kernel(const uint32_t *__restrict__ slice_src, const uint32_t *__restrict__ row_of,
+                                                                   const uint8_t *__restrict__ is_if, uint32_t nslices, uint8_t *__restrict__ flag)
+{
+    const uint64_t t = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (t >= nslices) return;                      // uniform per warp
+    const uint32_t row = row_of[(uint64_t)slice_src[t] * 32 + lane];
+    const bool hit = row != 0xffffffffu && is_if[row] != 0;
+    const unsigned m = __ballot_sync(0xffffffffu, hit);
+    if (lane == 0) flag[t] = m ? 1 : 0;
+}
+
+static int parmat_setup_overlap(ngsb_parmat *P, const std::vector<int32_t> &if_dof)
+{
+    const ngsb_csr *A = P->local;
+    ngsb_ctx *ctx = P->comm->ctx;
+    const uint32_t ns = A->nslices;
+    std::vector<uint8_t> is_if(P->n, 0), flag(ns, 0);
+    for (int32_t d : if_dof) is_if[d] = 1;
+    uint8_t *d_is = nullptr, *d_flag = nullptr;
+    NGSB_CUDA(cudaMalloc(&d_is, std::max<size_t>(16, P->n)));
+    if (cudaMalloc(&d_flag, ns) != cudaSuccess) { cudaFree(d_is); set_error("ngsb_parmat_create: out of memory"); return NGSB_ERR_NOMEM; }
+    cudaError_t e = cudaMemcpyAsync(d_is, is_if.data(), P->n, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+        mark_interface_slices_kernel<<<(unsigned)(((uint64_t)ns * 32 + 255) / 256), 256, 0, ctx->stream>>>(A->d_slice_src, A->d_row_of, d_is, ns, d_flag);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(flag.data(), d_flag, ns, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_is);
+    cudaFree(d_flag);
+    if (e != cudaSuccess) { set_error("ngsb_parmat_create (interface slices): %s", cudaGetErrorString(e)); return NGSB_ERR_CUDA; }
+    std::vector<uint32_t> bnd, inner;
+    for (uint32_t t = 0; t < ns; t++) (flag[t] ? bnd : inner).push_back(t);
+    if (bnd.empty() || inner.empty()) return NGSB_OK;           // nothing to overlap: one launch as usual
+    P->n_bnd = (uint32_t)bnd.size();
+    P->n_int = (uint32_t)inner.size();
+    NGSB_CUDA(cudaMalloc(&P->d_list_bnd, bnd.size() * sizeof(uint32_t)));
+    NGSB_CUDA(cudaMalloc(&P->d_list_int, inner.size() * sizeof(uint32_t)));
+    NGSB_CUDA(cudaMalloc(&P->d_red_b, 2 * sizeof(double)));
+    NGSB_CUDA(cudaMemset(P->d_red_b, 0, 2 * sizeof(double)));
+    NGSB_CUDA(cudaMemcpy(P->d_list_bnd, bnd.data(), bnd.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    NGSB_CUDA(cudaMemcpy(P->d_list_int, inner.data(), inner.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    P->overlap = true;
+    return NGSB_OK;
+}
+
 extern "C" int ngsb_parmat_create_ex(ngsb_comm *comm, const ngsb_csr *local, const uint64_t *ex_first, const int32_t *ex_dofs,
                                      int (*allgather)(void *user, const void *send, void *recv, size_t bytes_per_rank), void *user,
                                      ngsb_parmat **out)
@@ -687,6 +765,9 @@ extern "C" int ngsb_parmat_create_ex(ngsb_comm *comm, const ngsb_csr *local, con
         comm->boot_user = nullptr;
         if (rc == NGSB_OK && !P->p2p && !comm->comm) { set_error("ngsb_parmat_create: could not map the neighbours' receive areas and there is no NCCL communicator"); rc = NGSB_ERR_COMM; }
     }
+    if (rc == NGSB_OK && P->p2p && np > 1 && ctx->dist_overlap && local->nslices > 0 && !if_dof.empty() &&
+        (ctx->spmv_algo == 0 || ctx->spmv_algo == 3))
+        rc = parmat_setup_overlap(P, if_dof);
     if (rc == NGSB_OK && !P->p2p && np > 1) {
         if (cudaMalloc(&P->d_send, std::max<size_t>(16, nex * P->es * sizeof(double))) != cudaSuccess) rc = NGSB_ERR_NOMEM;
         if (rc == NGSB_OK && cudaMalloc(&P->d_recv, std::max<size_t>(16, nex * P->es * sizeof(double))) != cudaSuccess) rc = NGSB_ERR_NOMEM;
@@ -714,6 +795,7 @@ extern "C" int ngsb_parmat_destroy(ngsb_parmat *P)
     cudaFree(P->d_H); cudaFree(P->d_local); cudaFree(P->halo_mem);
     cudaFree(P->d_exdofs); cudaFree(P->d_send); cudaFree(P->d_recv);
     cudaFree(P->d_if_dof); cudaFree(P->d_if_first); cudaFree(P->d_if_pos); cudaFree(P->d_master);
+    cudaFree(P->d_list_bnd); cudaFree(P->d_list_int); cudaFree(P->d_red_b);
     delete P;
     return NGSB_OK;
 }
@@ -725,6 +807,15 @@ extern "C" int ngsb_parmat_info(const ngsb_parmat *P, int *peer_memory, int *n_n
     if (n_neighbours) *n_neighbours = (int)P->peers.size();
     if (n_exchange) *n_exchange = P->nex;
     if (n_interface) *n_interface = P->nif;
+    return NGSB_OK;
+}
+
+extern "C" int ngsb_parmat_overlap_info(const ngsb_parmat *P, int *enabled, size_t *interface_slices, size_t *interior_slices)
+{
+    NGSB_REQUIRE(P, "ngsb_parmat_overlap_info: NULL argument");
+    if (enabled) *enabled = P->overlap ? 1 : 0;
+    if (interface_slices) *interface_slices = P->n_bnd;
+    if (interior_slices) *interior_slices = P->n_int;
     return NGSB_OK;
 }
 
@@ -793,6 +884,21 @@ static int enqueue_par_iteration(const ngsb_parmat *P, const CgVecs &v, double *
     memset(&a, 0, sizeof(a));
     a.A = A; a.x = v.s; a.y = as; a.sr = 1.0; a.accumulate = false;
     a.epi = EPI_DOT_OUT; a.dotvec = v.s; a.dot_conj = v.ip_mode == NGSB_IP_COMPLEX_CONJ; a.dot_out = comm->d_red; a.state = v.state;
+    if (P->overlap) {
+        // interface rows first, their values leave for the neighbours, interior rows while they travel; the neighbours'
+        // values have landed long before the unpack kernel asks for them
+        SpmvArgs b = a;
+        b.slice_list = P->d_list_bnd; b.nlist = P->n_bnd; b.dot_out = P->d_red_b;
+        NGSB_TRY(spmv_launch(b));                                               // as(interface slices), partial <s,as>
+        NGSB_TRY(halo_push_only(P, as, v.state));
+        a.slice_list = P->d_list_int; a.nlist = P->n_int; a.dot_add = P->d_red_b; a.skip_overflow = true;
+        NGSB_TRY(spmv_launch(a));                                               // as(interior slices), local <s,as> complete
+        NGSB_TRY(halo_unpack_fin(P, as, v.state, comm->d_red));                 // as -> CUMULATED; kss all-reduced, al = wd/kss
+        NGSB_TRY(cg_launch_fused(ctx, A->kind, 1, v, 0));
+        NGSB_TRY(cg_launch_finalize(ctx, 2, v.state, comm->d_red, v.hist, comm->d_R));
+        NGSB_TRY(cg_launch_dir(ctx, A->kind, v));
+        return NGSB_OK;
+    }
     NGSB_TRY(spmv_launch(a));                                                   // as = A s (DISTRIBUTED), local <s,as>
     if (P->p2p) {
         NGSB_TRY(cumulate_es(P, as, P->es, v.state, comm->d_red, 1));           // as -> CUMULATED; kss all-reduced, al = wd/kss
@@ -885,6 +991,7 @@ extern "C" int ngsb_parmat_cg_solve(const ngsb_parmat *P, const ngsb_jacobi *C, 
             if (rc == NGSB_OK) {
                 for (long k = 0; k < batch && rc == NGSB_OK; k++) rc = enqueue_par_iteration(P, v, as);
                 cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
+                Pm->g_launches = ctx->launches - launches_before;
                 ctx->launches = launches_before;
                 if (rc == NGSB_OK) cu(ce);
                 if (rc == NGSB_OK && Pm->graph_exec) {      // same topology, other pointers: update in place
@@ -911,7 +1018,7 @@ extern "C" int ngsb_parmat_cg_solve(const ngsb_parmat *P, const ngsb_jacobi *C, 
         if (enq < max_batches) {
             if (use_graph) {
                 cu(cudaGraphLaunch(Pm->graph_exec, ctx->stream));
-                ctx->launches += 6 * batch;
+                ctx->launches += Pm->g_launches;
             } else {
                 for (long k = 0; k < batch && rc == NGSB_OK; k++) rc = enqueue_par_iteration(P, v, as);
             }

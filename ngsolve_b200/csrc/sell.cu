@@ -56,6 +56,9 @@ struct SellParams {
     CgState *state;
     double *partials;
     unsigned int *counter;
+    const uint32_t *slice_list;   // LIST kernels: scheduled positions to process (ascending), nlist of them
+    uint32_t nlist;
+    const double *dot_add;        // (re,im) added to the fused dot by the finishing thread, or NULL
 };
 
 __device__ __forceinline__ double2 ldg_stream_d2(const double2 *p)
@@ -137,7 +140,8 @@ __device__ __forceinline__ double warp_sum_s(double v)
 
 // VAR (tuning variants of the real-valued inner loop): 0 = 4 packets per step; 1 = 2 packets per step;
 // 2 = 4 packets per step with the next step's values/columns prefetched before the gathers of this one
-template <int KIND, int VAR, int MINB, bool POL = false>
+// LIST: walk p.slice_list instead of the whole schedule (interface-first split of the distributed product)
+template <int KIND, int VAR, int MINB, bool POL = false, bool LIST = false>
 __global__ void __launch_bounds__(256, MINB) sell_spmv_kernel(const SellParams p)
 {
     __shared__ double red[64];
@@ -145,7 +149,9 @@ __global__ void __launch_bounds__(256, MINB) sell_spmv_kernel(const SellParams p
     if (p.state != nullptr && p.state->done) return;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     double dr = 0.0, di = 0.0;
-    for (uint64_t s = (uint64_t)blockIdx.x * 8 + wid; s < p.nslices; s += (uint64_t)gridDim.x * 8) {
+    const uint64_t nwalk = LIST ? (uint64_t)p.nlist : (uint64_t)p.nslices;
+    for (uint64_t it = (uint64_t)blockIdx.x * 8 + wid; it < nwalk; it += (uint64_t)gridDim.x * 8) {
+        const uint64_t s = LIST ? (uint64_t)p.slice_list[it] : it;
         const uint64_t off = p.slice_off[s];
         const uint32_t width = (uint32_t)((p.slice_off[s + 1] - off) >> 5);     // entries per lane
         const uint64_t src = p.slice_src[s];
@@ -161,7 +167,7 @@ __global__ void __launch_bounds__(256, MINB) sell_spmv_kernel(const SellParams p
             const uint32_t np = width >> 1;
             uint32_t q = 0;
             const uint64_t polf = POL ? l2_policy_evict_first() : 0, poll = POL ? l2_policy_evict_last() : 0;
-            if (p.pf_next > 0) {
+            if (!LIST && p.pf_next > 0) {
                 // the compressed stream carries fewer bytes per dependent step, so the loads of one step no longer cover the DRAM
                 // latency: pull the head of this warp's next slice into L2 now (lane l fetches its own 128-byte line)
                 const uint64_t sn = s + (uint64_t)gridDim.x * 8;
@@ -423,6 +429,7 @@ __global__ void __launch_bounds__(256, MINB) sell_spmv_kernel(const SellParams p
     b = warp_sum_s(b);
     if (threadIdx.x == 0) {
         *p.counter = 0;
+        if (p.dot_add != nullptr) { a += p.dot_add[0]; b += p.dot_add[1]; }
         if (p.epi == EPI_DOT_OUT) { p.dot_out[0] = a; p.dot_out[1] = b; }
         else if (p.epi == EPI_CG_KSS) cg_finalize_kss(p.state, make_double2(a, b));
     }
@@ -907,7 +914,9 @@ int sell_launch(const SpmvArgs &a)
     p.accumulate = a.accumulate ? 1 : 0; p.epi = a.epi; p.dot_conj = a.dot_conj;
     p.dotvec = a.dotvec; p.dot_out = a.dot_out; p.state = a.state;
     p.partials = ctx->d_partials; p.counter = ctx->d_counter;
-    if (A->novf) {
+    p.slice_list = a.slice_list; p.nlist = a.nlist; p.dot_add = a.dot_add;
+    const bool list = a.slice_list != nullptr;
+    if (A->novf && !a.skip_overflow) {
         SpanGuard g(ctx, KC_SPMV);
         if (A->kind == NGSB_REAL) sell_overflow_kernel<NGSB_REAL><<<A->novf, 256, 0, ctx->stream>>>(A->d_ovf_ptr, A->d_ovf_col, A->d_ovf_val, a.x, A->d_ovf_sum, a.state);
         else if (A->kind == NGSB_COMPLEX) sell_overflow_kernel<NGSB_COMPLEX><<<A->novf, 256, 0, ctx->stream>>>(A->d_ovf_ptr, A->d_ovf_col, A->d_ovf_val, a.x, A->d_ovf_sum, a.state);
@@ -918,7 +927,12 @@ int sell_launch(const SpmvArgs &a)
     typedef void (*kern_t)(const SellParams);
     kern_t kern;
     const long var = ctx->sell_variant;
-    if (A->kind == NGSB_REAL) {
+    if (list) {
+        // interface-first split: the default loops only
+        if (A->kind == NGSB_REAL) kern = sell_spmv_kernel<NGSB_REAL, 2, 4, false, true>;
+        else if (A->kind == NGSB_COMPLEX) kern = sell_spmv_kernel<NGSB_COMPLEX, 2, 4, false, true>;
+        else kern = sell_spmv_kernel<NGSB_BLOCK3, 0, 5, false, true>;
+    } else if (A->kind == NGSB_REAL) {
         // default (0): software-pipelined loop, 64 registers, 4 resident CTAs, grid of 8 CTAs per SM --
         // best of the variants swept on B200 at 6-101 M rows (profiles/r1_sweep_sell_variants.txt)
         switch (var) {
@@ -939,7 +953,7 @@ int sell_launch(const SpmvArgs &a)
     // 8 CTAs/SM, 9.31 ms with 96 (profiles/r1_sweep_c16_grid_size.txt); 3x3 blocks +18 %, complex +9 %.
     long cps = ctx->spmv_ctas_per_sm > 0 ? ctx->spmv_ctas_per_sm : 96;
     uint64_t grid = (uint64_t)ctx->sm_count * (uint64_t)cps;
-    const uint64_t need = ((uint64_t)A->nslices + 7) / 8;
+    const uint64_t need = ((uint64_t)(list ? a.nlist : A->nslices) + 7) / 8;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
     if (grid > (uint64_t)MAX_PARTIALS - 8) grid = MAX_PARTIALS - 8;

@@ -553,6 +553,7 @@ int spmv_launch(const SpmvArgs &a)
     p.stages = A->stages;
 
     if ((ctx->spmv_algo == 0 || ctx->spmv_algo == 3) && !a.use_range) return sell_launch(a);
+    NGSB_REQUIRE(a.slice_list == nullptr, "SpMV: a slice list needs the SELL kernel (spmv_algo 0 or 3)");
     const bool stream = ctx->spmv_algo != 1;
     if (stream) {
         if (A->nlong > 0 && !a.use_range) {

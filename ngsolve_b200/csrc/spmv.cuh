@@ -78,6 +78,14 @@ struct SpmvArgs {
     // row subset for the distributed path (interior/boundary split); nblocks==0 -> all
     uint32_t block_begin, block_end;
     bool use_range;
+    // SELL only: restrict the product to the scheduled slices slice_list[0 .. nlist) (ascending positions of the schedule).
+    // The distributed CG multiplies the slices that hold interface rows first, pushes them to the neighbours and
+    // multiplies the interior slices while the values travel (dist.cu).  dot_add: (re,im) added to the fused dot of this
+    // launch (the partial of the other half); skip_overflow: the overflow sums were already computed by the first half.
+    const uint32_t *slice_list;
+    uint32_t nlist;
+    const double *dot_add;
+    bool skip_overflow;
 };
 
 int spmv_launch(const SpmvArgs &a);

@@ -108,6 +108,13 @@ class ParallelMatrix(la.BaseMatrix):
         check(_capi.lib().ngsb_parmat_info(self.handle, C.byref(pm), None, None, None))
         return bool(pm.value)
 
+    @property
+    def overlap(self):
+        """(active, interface slices, interior slices) of the interface-first split (Context option dist_overlap=1)"""
+        on, nb, ni = C.c_int(), C.c_size_t(), C.c_size_t()
+        check(_capi.lib().ngsb_parmat_overlap_info(self.handle, C.byref(on), C.byref(nb), C.byref(ni)))
+        return bool(on.value), nb.value, ni.value
+
     def MasterDofs(self):
         out = np.empty(self.height, dtype=np.uint8)
         check(_capi.lib().ngsb_parmat_masterdofs(self.handle, la._np_ptr(out)))

@@ -45,6 +45,8 @@ def _worker(rank, world, port, cfg, out):
     import ngsolve_b200.la as la
     from ngsolve_b200 import workloads as W, parallel as par
     ctx = la.Context(dev)
+    if cfg.get("overlap"):
+        ctx.set_option("dist_overlap", 1)
     G = tuple(cfg.get("G", G_DEFAULT))
     boxes = [W.FemBox(n, offset=o, global_n=G, **_box_kw(cfg)) for n, o in W.slab_partition(G, world)]
     box = boxes[rank]
@@ -54,6 +56,13 @@ def _worker(rank, world, port, cfg, out):
     pmat = par.ParallelMatrix(A, pd, comm)
     assert pmat.peer_memory == (cfg["p2p"] != 0), "data path: peer_memory=%s, wanted p2p=%d" % (pmat.peer_memory, cfg["p2p"])
     assert np.array_equal(pmat.MasterDofs(), pd.MasterDofs())
+    if cfg.get("overlap"):
+        on, nb, ni = pmat.overlap
+        # tiny slabs may have no interior slice at all: that rank then keeps the single launch (ranks may mix both forms)
+        assert on or cfg["overlap"] == "maybe"
+        assert not on or (nb > 0 and ni > 0 and nb + ni == (box.ndof + 31) // 32), (on, nb, ni, box.ndof)
+    else:
+        assert not pmat.overlap[0]
     jac = pmat.CreateSmoother(box.freedofs())
     u = f.CreateVector()
     if cfg["solver"] == "cg":
@@ -131,6 +140,16 @@ def test_two_ranks_on_one_gpu_peer_memory(case):
     context switch -> keep the GMRES systems small: step j has j+2 reductions)"""
     extra = dict(G=(6, 5, 8)) if case["solver"] == "gmres" else {}
     _run(dict(case, devices="same", p2p=1, **extra))
+
+
+@pytest.mark.parametrize("case", CASES[:3], ids=IDS[:3])
+def test_two_ranks_interface_first_overlap(case):
+    """option dist_overlap: interface slices, push, interior slices, unpack -- same solve as the one-GPU solver"""
+    _run(dict(case, devices="same", p2p=1, overlap=True))
+
+
+def test_four_ranks_interface_first_overlap():
+    _run(dict(order=2, kind=REAL, solver="cg", devices="same", p2p=1, G=(4, 4, 12), overlap="maybe"), world=4)
 
 
 def test_four_ranks_on_one_gpu_peer_memory():
