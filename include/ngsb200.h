@@ -75,7 +75,8 @@ void *ngsb_ctx_stream(ngsb_ctx *ctx);                   /* cudaStream_t */
 /* kernels of this library launched on ctx so far (bench.py's gpu_launches) */
 int ngsb_ctx_launch_count(const ngsb_ctx *ctx, uint64_t *count);
 /* tuning knobs: "spmv_algo" (0 auto = 3; 1 sub-warp CSR; 2 TMA-streamed CSR; 3 SELL-32),
- * "cg_batch", "spmv_ctas_per_sm", "timing", "dist_overlap" (0/1, read by ngsb_parmat_create), and -- read when a matrix is created --
+ * "cg_batch", "spmv_ctas_per_sm", "timing", "cg_fold_u" (0/1: the CG direction kernel also does u += al s, 10 instead
+ * of 11 vector passes per iteration), "dist_overlap" (0/1, read by ngsb_parmat_create), and -- read when a matrix is created --
  * "sell_cap", "spmv_tile", "spmv_ncw", "spmv_stages", "spmv_subwarp" (0 = default).
  * Unknown names fail with NGSB_ERR_INVALID. */
 int ngsb_ctx_set_option(ngsb_ctx *ctx, const char *name, long value);

@@ -20,7 +20,9 @@ struct CgState {
     int nhist;         // history entries written (capped by hist_cap)
     int hist_cap;
     int cplx;          // scalars are complex
-    int pad[2];
+    int u_pending;     // option cg_fold_u: the loop ended in this iteration and `u += al s` is still owed by its
+                       // direction kernel (set by cg_finalize_wdn, cleared by the next update kernel's early exit)
+    int pad;
 };
 
 #ifdef __CUDACC__
@@ -80,5 +82,6 @@ __device__ __forceinline__ void cg_finalize_wdn(CgState *st, double2 total, doub
     if (st->nhist < st->hist_cap) hist[st->nhist] = cg_abs(st->wdn, st->cplx);
     st->nhist++;
     cg_eval_loop_condition(st);
+    if (st->done) st->u_pending = 1;
 }
 #endif

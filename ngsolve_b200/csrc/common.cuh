@@ -74,6 +74,7 @@ struct ngsb_ctx {
     long sell_pf_next = 0;       // compressed slices: packets of the next slice prefetched at slice start, 0 = off
     long sell_c16 = 1;           // 16-bit column offsets where a slice allows it (read at matrix creation and at launch)
     long spmv_tile = 0, spmv_ncw = 0, spmv_stages = 0, spmv_subwarp = 0;   // 0 = default; read when a matrix is created
+    long cg_fold_u = 0;          // CG: `u += al s` in the direction kernel instead of the update kernel (10 vector passes, not 11)
     long dist_overlap = 0;       // distributed CG: interface slices first, push, interior slices while the values travel
                                  // (read when a parallel matrix is created; peer-memory data path only)
     long timing = 0;

@@ -74,7 +74,7 @@ struct ngsb_parmat {
     double *d_red_b = nullptr;                    // <s, A s> over the interface slices (2 doubles)
     // cached CUDA graph of one batch of CG iterations (peer-memory mode)
     cudaGraphExec_t graph_exec = nullptr;
-    const void *g_key[8] = {};
+    const void *g_key[9] = {};
     long g_batch = 0;
     uint64_t g_launches = 0;                      // kernels in one batch of the captured graph
 };
@@ -967,6 +967,7 @@ extern "C" int ngsb_parmat_cg_solve(const ngsb_parmat *P, const ngsb_jacobi *C, 
     v.partials = ctx->d_partials;
     v.counter = ctx->d_counter;
     v.ip_mode = ip_mode;
+    v.fold_u = ctx->cg_fold_u ? 1 : 0;
 
     // u = 0; d = f, cumulated by the Jacobi application (linalg/jacobi.cpp:78)
     cu(cudaMemsetAsync(u->d, 0, nscal * sizeof(double), ctx->stream));
@@ -982,7 +983,7 @@ extern "C" int ngsb_parmat_cg_solve(const ngsb_parmat *P, const ngsb_jacobi *C, 
     ngsb_parmat *Pm = const_cast<ngsb_parmat *>(P);
     const bool use_graph = P->p2p && !ctx->timing && getenv("NGSB_NO_CUDA_GRAPH") == nullptr && batch > 1;
     if (rc == NGSB_OK && use_graph) {
-        const void *key[8] = {u->d, d, w, s, as, C, (const void *)(intptr_t)ip_mode, d_hist};
+        const void *key[9] = {u->d, d, w, s, as, C, (const void *)(intptr_t)ip_mode, d_hist, (const void *)(intptr_t)ctx->cg_fold_u};
         const bool hit = Pm->graph_exec && Pm->g_batch == batch && memcmp(key, Pm->g_key, sizeof(key)) == 0;
         if (!hit) {
             cudaGraph_t graph = nullptr;

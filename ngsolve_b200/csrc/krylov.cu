@@ -35,7 +35,7 @@ struct Workspace {
     double *g_ptrs[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     long g_batch = 0;
     int g_ip = -1;
-    long g_algo = -1, g_cps = -1;
+    long g_algo = -1, g_cps = -1, g_fold = -1;
 };
 
 static void ws_free(void *p)
@@ -201,12 +201,16 @@ __device__ __forceinline__ void prec_entry(const CgVecs &v, uint64_t i, const do
 
 // MODE 0: init      d = f (or f - as when !initialize, flag in `sub`), w = C d, s = w, <w,d>
 // MODE 1: update    u += al s, d -= al as, w = C d, <d,w>
-template <int KIND, int MODE>
+// FOLD (MODE 1):    without `u += al s` -- the direction kernel of the same iteration does it (cg_dir_kernel<., true>)
+template <int KIND, int MODE, bool FOLD = false>
 __global__ void __launch_bounds__(256) cg_fused_kernel(const CgVecs v, int sub)
 {
     constexpr int ES = KIND == NGSB_REAL ? 1 : (KIND == NGSB_COMPLEX ? 2 : 3);
     CgState *st = v.state;
-    if (MODE == 1 && st->done) return;
+    if (MODE == 1 && st->done) {
+        if (FOLD && blockIdx.x == 0 && threadIdx.x == 0) st->u_pending = 0;     // the owed update ran in the previous iteration
+        return;
+    }
     const double alr = MODE == 1 ? st->al[0] : 0.0;
     const double ali = MODE == 1 ? st->al[1] : 0.0;
     const bool conj = v.ip_mode == NGSB_IP_COMPLEX_CONJ;
@@ -224,18 +228,20 @@ __global__ void __launch_bounds__(256) cg_fused_kernel(const CgVecs v, int sub)
         double acc1 = 0.0;
         const uint64_t hi2 = lo + ((hi - lo) & ~(uint64_t)1);
         for (uint64_t i = lo + 2 * (uint64_t)threadIdx.x; i < hi2; i += 2 * (uint64_t)blockDim.x) {
-            const double2 s2 = *reinterpret_cast<const double2 *>(v.s + i);
             const double2 a2 = *reinterpret_cast<const double2 *>(v.as + i);
             const double2 m2 = *reinterpret_cast<const double2 *>(v.invdiag + i);
-            double2 u2 = *reinterpret_cast<double2 *>(v.u + i);
             double2 d2 = *reinterpret_cast<double2 *>(v.d + i);
-            u2.x += alr * s2.x; u2.y += alr * s2.y;
+            if (!FOLD) {
+                const double2 s2 = *reinterpret_cast<const double2 *>(v.s + i);
+                double2 u2 = *reinterpret_cast<double2 *>(v.u + i);
+                u2.x += alr * s2.x; u2.y += alr * s2.y;
+                *reinterpret_cast<double2 *>(v.u + i) = u2;
+            }
             d2.x -= alr * a2.x; d2.y -= alr * a2.y;
             unsigned bits = v.bits ? (unsigned)(v.bits[i >> 3] >> (i & 7)) : 3u;
             double2 w2;
             w2.x = (bits & 1u) ? m2.x * d2.x : 0.0;
             w2.y = (bits & 2u) ? m2.y * d2.y : 0.0;
-            *reinterpret_cast<double2 *>(v.u + i) = u2;
             *reinterpret_cast<double2 *>(v.d + i) = d2;
             *reinterpret_cast<double2 *>(v.w + i) = w2;
             if (v.master == nullptr || v.master[i]) accr = fma(d2.x, w2.x, accr);
@@ -243,7 +249,7 @@ __global__ void __launch_bounds__(256) cg_fused_kernel(const CgVecs v, int sub)
         }
         if (hi2 < hi && threadIdx.x == 0) {      // odd tail of the last chunk
             const uint64_t i = hi2;
-            v.u[i] += alr * v.s[i];
+            if (!FOLD) v.u[i] += alr * v.s[i];
             const double dn = v.d[i] - alr * v.as[i];
             const double wn = (v.bits == nullptr || bit_test_k(v.bits, i)) ? v.invdiag[i] * dn : 0.0;
             v.d[i] = dn;
@@ -263,16 +269,18 @@ __global__ void __launch_bounds__(256) cg_fused_kernel(const CgVecs v, int sub)
             }
         } else {
             if (KIND == NGSB_COMPLEX) {
-                double sr = v.s[2 * i], si = v.s[2 * i + 1];
                 double ar = v.as[2 * i], ai = v.as[2 * i + 1];
-                v.u[2 * i] += alr * sr - ali * si;
-                v.u[2 * i + 1] += alr * si + ali * sr;
+                if (!FOLD) {
+                    double sr = v.s[2 * i], si = v.s[2 * i + 1];
+                    v.u[2 * i] += alr * sr - ali * si;
+                    v.u[2 * i + 1] += alr * si + ali * sr;
+                }
                 dn[0] = v.d[2 * i] - (alr * ar - ali * ai);
                 dn[1] = v.d[2 * i + 1] - (alr * ai + ali * ar);
             } else {
 #pragma unroll
                 for (int c = 0; c < ES; c++) {
-                    v.u[ES * i + c] += alr * v.s[ES * i + c];
+                    if (!FOLD) v.u[ES * i + c] += alr * v.s[ES * i + c];
                     dn[c] = v.d[ES * i + c] - alr * v.as[ES * i + c];
                 }
             }
@@ -306,31 +314,53 @@ __global__ void __launch_bounds__(256) cg_fused_kernel(const CgVecs v, int sub)
 }
 
 // s = be*s + w   (`s *= be; s += w`, linalg/cg.cpp:611-612: two roundings, kept)
-template <bool CPLX>
-__global__ void __launch_bounds__(256) cg_dir_kernel(double *__restrict__ s, const double *__restrict__ w, uint64_t N,
+// FOLD: also u += al*s with the s of this iteration (read before it is overwritten) -- the update the fused kernel left
+// out; when the loop ended in this iteration (done && u_pending) only that update runs.
+template <bool CPLX, bool FOLD>
+__global__ void __launch_bounds__(256) cg_dir_kernel(double *__restrict__ s, const double *__restrict__ w, double *__restrict__ u, uint64_t N,
                                                     const CgState *__restrict__ st)
 {
-    if (st->done) return;
+    const bool only_u = st->done != 0;
+    if (only_u && !(FOLD && st->u_pending)) return;
     const double ber = st->be[0], bei = st->be[1];
+    const double alr = st->al[0], ali = st->al[1];
     uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (CPLX) {
         double2 *s2 = reinterpret_cast<double2 *>(s);
         const double2 *w2 = reinterpret_cast<const double2 *>(w);
         for (; i < N; i += stride) {
-            double2 a = s2[i], b = w2[i];
+            double2 a = s2[i];
+            if (FOLD) {
+                const double sr = a.x, si = a.y;
+                u[2 * i] += alr * sr - ali * si;
+                u[2 * i + 1] += alr * si + ali * sr;
+                if (only_u) continue;
+            }
+            double2 b = w2[i];
             double pr = a.x * ber - a.y * bei, pi = a.x * bei + a.y * ber;
             s2[i] = make_double2(__dadd_rn(pr, b.x), __dadd_rn(pi, b.y));
         }
     } else {
         uint64_t n2 = N / 2;
         double2 *s2 = reinterpret_cast<double2 *>(s);
+        double2 *u2p = reinterpret_cast<double2 *>(u);
         const double2 *w2 = reinterpret_cast<const double2 *>(w);
         for (uint64_t k = i; k < n2; k += stride) {
-            double2 a = s2[k], b = w2[k];
+            double2 a = s2[k];
+            if (FOLD) {
+                double2 u2 = u2p[k];
+                u2.x += alr * a.x; u2.y += alr * a.y;
+                u2p[k] = u2;
+                if (only_u) continue;
+            }
+            double2 b = w2[k];
             s2[k] = make_double2(__dadd_rn(__dmul_rn(a.x, ber), b.x), __dadd_rn(__dmul_rn(a.y, ber), b.y));
         }
-        if (i == 0 && (N & 1)) s[N - 1] = __dadd_rn(__dmul_rn(s[N - 1], ber), w[N - 1]);
+        if (i == 0 && (N & 1)) {
+            if (FOLD) u[N - 1] += alr * s[N - 1];
+            if (!only_u) s[N - 1] = __dadd_rn(__dmul_rn(s[N - 1], ber), w[N - 1]);
+        }
     }
 }
 
@@ -349,6 +379,13 @@ static int launch_cg_fused(ngsb_ctx *ctx, int kind, const CgVecs &v, int sub)
 {
     SpanGuard g(ctx, KC_CGUPDATE);
     int grid = reduce_grid(ctx, v.n);
+    if (MODE == 1 && v.fold_u) {
+        if (kind == NGSB_REAL) cg_fused_kernel<NGSB_REAL, 1, true><<<grid, 256, 0, ctx->stream>>>(v, sub);
+        else if (kind == NGSB_COMPLEX) cg_fused_kernel<NGSB_COMPLEX, 1, true><<<grid, 256, 0, ctx->stream>>>(v, sub);
+        else cg_fused_kernel<NGSB_BLOCK3, 1, true><<<grid, 256, 0, ctx->stream>>>(v, sub);
+        NGSB_CUDA(cudaGetLastError());
+        return NGSB_OK;
+    }
     if (kind == NGSB_REAL) cg_fused_kernel<NGSB_REAL, MODE><<<grid, 256, 0, ctx->stream>>>(v, sub);
     else if (kind == NGSB_COMPLEX) cg_fused_kernel<NGSB_COMPLEX, MODE><<<grid, 256, 0, ctx->stream>>>(v, sub);
     else cg_fused_kernel<NGSB_BLOCK3, MODE><<<grid, 256, 0, ctx->stream>>>(v, sub);
@@ -389,8 +426,13 @@ static int launch_cg_dir(ngsb_ctx *ctx, int kind, const CgVecs &v)
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     const double *w = v.invdiag ? v.w : v.d;
-    if (cplx) cg_dir_kernel<true><<<(int)blocks, 256, 0, ctx->stream>>>(v.s, w, N, v.state);
-    else cg_dir_kernel<false><<<(int)blocks, 256, 0, ctx->stream>>>(v.s, w, N, v.state);
+    if (v.fold_u) {
+        if (cplx) cg_dir_kernel<true, true><<<(int)blocks, 256, 0, ctx->stream>>>(v.s, w, v.u, N, v.state);
+        else cg_dir_kernel<false, true><<<(int)blocks, 256, 0, ctx->stream>>>(v.s, w, v.u, N, v.state);
+    } else {
+        if (cplx) cg_dir_kernel<true, false><<<(int)blocks, 256, 0, ctx->stream>>>(v.s, w, v.u, N, v.state);
+        else cg_dir_kernel<false, false><<<(int)blocks, 256, 0, ctx->stream>>>(v.s, w, v.u, N, v.state);
+    }
     NGSB_CUDA(cudaGetLastError());
     return NGSB_OK;
 }
@@ -444,6 +486,7 @@ int cg_solve_device(const ngsb_csr *A, const ngsb_jacobi *C, const double *f, do
     v.partials = ctx->d_partials;
     v.counter = ctx->d_counter;
     v.ip_mode = ip_mode;
+    v.fold_u = ctx->cg_fold_u ? 1 : 0;
 
     int sub = 0;
     if (initialize) {
@@ -463,7 +506,7 @@ int cg_solve_device(const ngsb_csr *A, const ngsb_jacobi *C, const double *f, do
     if (use_graph) {
         double *key[6] = {u, d, w, s, as, (double *)f};
         bool hit = ws->graph_exec && ws->g_A == A && ws->g_C == C && ws->g_batch == batch && ws->g_ip == ip_mode &&
-                   ws->g_algo == ctx->spmv_algo && ws->g_cps == ctx->spmv_ctas_per_sm && memcmp(key, ws->g_ptrs, sizeof(key)) == 0;
+                   ws->g_algo == ctx->spmv_algo && ws->g_cps == ctx->spmv_ctas_per_sm && ws->g_fold == ctx->cg_fold_u && memcmp(key, ws->g_ptrs, sizeof(key)) == 0;
         if (!hit) {
             cudaGraph_t graph = nullptr;
             uint64_t launches_before = ctx->launches;
@@ -485,7 +528,7 @@ int cg_solve_device(const ngsb_csr *A, const ngsb_jacobi *C, const double *f, do
             if (!updated) NGSB_CUDA(cudaGraphInstantiate(&ws->graph_exec, graph, 0));
             cudaGraphDestroy(graph);
             ws->g_A = A; ws->g_C = C; ws->g_batch = batch; ws->g_ip = ip_mode;
-            ws->g_algo = ctx->spmv_algo; ws->g_cps = ctx->spmv_ctas_per_sm;
+            ws->g_algo = ctx->spmv_algo; ws->g_cps = ctx->spmv_ctas_per_sm; ws->g_fold = ctx->cg_fold_u;
             memcpy(ws->g_ptrs, key, sizeof(key));
         }
     }

@@ -21,6 +21,8 @@ struct CgVecs {
     double *partials;
     unsigned int *counter;
     int ip_mode;
+    int fold_u;                // option cg_fold_u: `u += al s` moves from the update kernel into the direction kernel, which
+                               // reads s anyway (10 instead of 11 vector passes per iteration, same arithmetic per entry)
 };
 
 // mode 0: init (d = f [- as], w = C d, s = w, <w,d>), mode 1: update (u, d, w, <d,w>)

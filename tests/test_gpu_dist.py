@@ -47,6 +47,8 @@ def _worker(rank, world, port, cfg, out):
     ctx = la.Context(dev)
     if cfg.get("overlap"):
         ctx.set_option("dist_overlap", 1)
+    if cfg.get("fold"):
+        ctx.set_option("cg_fold_u", 1)
     G = tuple(cfg.get("G", G_DEFAULT))
     boxes = [W.FemBox(n, offset=o, global_n=G, **_box_kw(cfg)) for n, o in W.slab_partition(G, world)]
     box = boxes[rank]
@@ -149,7 +151,12 @@ def test_two_ranks_interface_first_overlap(case):
 
 
 def test_four_ranks_interface_first_overlap():
-    _run(dict(order=2, kind=REAL, solver="cg", devices="same", p2p=1, G=(4, 4, 12), overlap="maybe"), world=4)
+    """... together with cg_fold_u (u += al s in the direction kernel)"""
+    _run(dict(order=2, kind=REAL, solver="cg", devices="same", p2p=1, G=(4, 4, 12), overlap="maybe", fold=True), world=4)
+
+
+def test_two_ranks_cg_fold_u():
+    _run(dict(CASES[1], devices="same", p2p=1, fold=True))
 
 
 def test_four_ranks_on_one_gpu_peer_memory():

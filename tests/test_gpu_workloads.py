@@ -190,3 +190,42 @@ def test_kernel_variants_are_bit_exact(n):
         assert np.array_equal(val[0], ref[0]) and np.array_equal(val[1], ref[1]), key
         # the fused <s, A s> is summed per CTA and the variants use different grids: same steps, solution to rounding
         assert abs(val[3] - ref[3]) <= 1 and np.max(np.abs(val[2] - ref[2])) <= 1e-9 * np.max(np.abs(ref[2])), key
+
+
+@pytest.mark.parametrize("kind", [0, 1, 3], ids=["real", "complex", "block3"])
+@pytest.mark.parametrize("stop", ["precision", "maxsteps", "batches"])
+def test_cg_fold_u_is_the_same_solve(kind, stop):
+    """option cg_fold_u: `u += al s` runs in the direction kernel (which reads s anyway) instead of the update kernel.
+    Same arithmetic per entry -> same steps, the same residual history bit for bit, and the same solution (bit-identical
+    for real entries; complex products may contract differently, 1e-14); the update owed by the iteration that ends the
+    loop (precision reached or maxsteps) must not be lost, and later batch iterations must not repeat it."""
+    import ngsolve_b200.la as la
+    from ngsolve_b200 import workloads as W
+    ctx = la.default_context()
+    box = W.FemBox((9, 8, 7), order=2, kind=kind, mass=(1.0 + 0.5j) if kind == 1 else 0.5, lame=(1.0, 0.7))
+    A, f = box.device_system(ctx)
+    jac = A.CreateSmoother(box.freedofs())
+    kw = dict(precision=1e-9, maxsteps=2000) if stop != "maxsteps" else dict(precision=1e-30, maxsteps=37)
+    out = []
+    try:
+        for fold in (0, 1):
+            ctx.set_option("cg_fold_u", fold)
+            for batch in ((16,) if stop != "batches" else (1, 5)):      # 1: no CUDA graph, 5: the loop ends inside a batch
+                ctx.set_option("cg_batch", batch)
+                inv = la.CGSolver(A, jac, **kw)
+                u = f.CreateVector()
+                inv.Mult(f, u)
+                out.append((inv.GetSteps(), np.array(inv.history), u.NumPy().copy()))
+    finally:
+        ctx.set_option("cg_fold_u", 0)
+        ctx.set_option("cg_batch", 16)
+    ref = out[0]
+    assert ref[0] > 10
+    if stop == "maxsteps":
+        assert ref[0] == 38        # GetSteps() = maxsteps + 1 (linalg/cg.cpp:593: n++ in the failing test)
+    for steps, hist, u in out[1:]:
+        assert steps == ref[0] and np.array_equal(hist, ref[1])
+        if kind == 1:
+            assert np.max(np.abs(u - ref[2])) <= 1e-14 * np.max(np.abs(ref[2]))
+        else:
+            assert np.array_equal(u, ref[2])
