@@ -86,6 +86,13 @@ __device__ __forceinline__ int ldg_stream_i(const int *p)
     return v;
 }
 
+__device__ __forceinline__ unsigned short ldg_stream_u16(const unsigned short *p)
+{
+    unsigned short v;
+    asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(v) : "l"(p));
+    return v;
+}
+
 __device__ __forceinline__ unsigned int ldg_stream_u32(const unsigned int *p)
 {
     unsigned int v;
@@ -299,6 +306,44 @@ __global__ void __launch_bounds__(256, MINB) sell_spmv_kernel(const SellParams p
                 s0 = fma(va.x, __ldg(p.x + ca.x), s0);
                 s0 = fma(va.y, __ldg(p.x + ca.y), s0);
             }
+        } else if (KIND == NGSB_COMPLEX && p.slice_c16 != nullptr && p.slice_c16[s]) {
+            // compressed complex slice: 16 B value + 2 B column offset per lane and step, one 32-bit base per warp and step
+            // (18.125 instead of 20 bytes per entry); same loop structure and summation order as the 32-bit branch below
+            const double2 *v2 = reinterpret_cast<const double2 *>(p.sval) + off + lane;
+            const unsigned short *h1 = p.scol16 + off + lane;
+            const int *b1 = p.sbase + (off >> 5);
+            const double2 *x2 = reinterpret_cast<const double2 *>(p.x);
+            uint32_t q = 0;
+            if (width >= 4) {
+                double2 va = ldg_stream_d2(v2), vb = ldg_stream_d2(v2 + 32), vc = ldg_stream_d2(v2 + 64), vd = ldg_stream_d2(v2 + 96);
+                int ca = __ldg(b1) + (int)ldg_stream_u16(h1), cb = __ldg(b1 + 1) + (int)ldg_stream_u16(h1 + 32);
+                int cc = __ldg(b1 + 2) + (int)ldg_stream_u16(h1 + 64), cd = __ldg(b1 + 3) + (int)ldg_stream_u16(h1 + 96);
+                for (q = 4; q + 4 <= width; q += 4) {
+                    double2 xa = __ldg(x2 + ca), xb = __ldg(x2 + cb), xc = __ldg(x2 + cc), xd = __ldg(x2 + cd);
+                    double2 na = ldg_stream_d2(v2 + (q + 0) * 32), nb = ldg_stream_d2(v2 + (q + 1) * 32);
+                    double2 nc = ldg_stream_d2(v2 + (q + 2) * 32), nd = ldg_stream_d2(v2 + (q + 3) * 32);
+                    const unsigned short ha = ldg_stream_u16(h1 + (q + 0) * 32), hb = ldg_stream_u16(h1 + (q + 1) * 32);
+                    const unsigned short hc = ldg_stream_u16(h1 + (q + 2) * 32), hd = ldg_stream_u16(h1 + (q + 3) * 32);
+                    const int ba = __ldg(b1 + q), bb = __ldg(b1 + q + 1), bc = __ldg(b1 + q + 2), bd = __ldg(b1 + q + 3);
+                    s0 += va.x * xa.x - va.y * xa.y; s1 += va.x * xa.y + va.y * xa.x;
+                    s0 += vb.x * xb.x - vb.y * xb.y; s1 += vb.x * xb.y + vb.y * xb.x;
+                    s0 += vc.x * xc.x - vc.y * xc.y; s1 += vc.x * xc.y + vc.y * xc.x;
+                    s0 += vd.x * xd.x - vd.y * xd.y; s1 += vd.x * xd.y + vd.y * xd.x;
+                    va = na; vb = nb; vc = nc; vd = nd;
+                    ca = ba + (int)ha; cb = bb + (int)hb; cc = bc + (int)hc; cd = bd + (int)hd;
+                }
+                double2 xa = __ldg(x2 + ca), xb = __ldg(x2 + cb), xc = __ldg(x2 + cc), xd = __ldg(x2 + cd);
+                s0 += va.x * xa.x - va.y * xa.y; s1 += va.x * xa.y + va.y * xa.x;
+                s0 += vb.x * xb.x - vb.y * xb.y; s1 += vb.x * xb.y + vb.y * xb.x;
+                s0 += vc.x * xc.x - vc.y * xc.y; s1 += vc.x * xc.y + vc.y * xc.x;
+                s0 += vd.x * xd.x - vd.y * xd.y; s1 += vd.x * xd.y + vd.y * xd.x;
+            }
+            for (; q < width; q++) {
+                double2 va = ldg_stream_d2(v2 + q * 32);
+                double2 xa = __ldg(x2 + (__ldg(b1 + q) + (int)ldg_stream_u16(h1 + q * 32)));
+                s0 += va.x * xa.x - va.y * xa.y;
+                s1 += va.x * xa.y + va.y * xa.x;
+            }
         } else if (KIND == NGSB_COMPLEX) {
             const double2 *v2 = reinterpret_cast<const double2 *>(p.sval) + off + lane;
             const int *c1 = p.scol + off + lane;
@@ -345,18 +390,28 @@ __global__ void __launch_bounds__(256, MINB) sell_spmv_kernel(const SellParams p
         } else {
             // 3x3 blocks: nine component planes per entry, [j][k][lane]
             const double *v = p.sval + off * 9 + lane;
-            const int *c1 = p.scol + off + lane;
-            for (uint32_t q = 0; q < width; q++) {
-                const double *m = v + (size_t)q * 9 * 32;
-                const double *xv = p.x + 3 * (size_t)ldg_stream_i(c1 + q * 32);
-                double m0 = ldg_stream_d(m), m1 = ldg_stream_d(m + 32), m2 = ldg_stream_d(m + 64);
-                double m3 = ldg_stream_d(m + 96), m4 = ldg_stream_d(m + 128), m5 = ldg_stream_d(m + 160);
-                double m6 = ldg_stream_d(m + 192), m7 = ldg_stream_d(m + 224), m8 = ldg_stream_d(m + 256);
-                double x0 = __ldg(xv), x1 = __ldg(xv + 1), x2 = __ldg(xv + 2);
-                s0 += m0 * x0 + m1 * x1 + m2 * x2;
-                s1 += m3 * x0 + m4 * x1 + m5 * x2;
-                s2 += m6 * x0 + m7 * x1 + m8 * x2;
+#define NGSB_B3_ENTRY(col)                                                                                       \
+            {                                                                                                    \
+                const double *m = v + (size_t)q * 9 * 32;                                                        \
+                const double *xv = p.x + 3 * (size_t)(col);                                                      \
+                double m0 = ldg_stream_d(m), m1 = ldg_stream_d(m + 32), m2 = ldg_stream_d(m + 64);               \
+                double m3 = ldg_stream_d(m + 96), m4 = ldg_stream_d(m + 128), m5 = ldg_stream_d(m + 160);        \
+                double m6 = ldg_stream_d(m + 192), m7 = ldg_stream_d(m + 224), m8 = ldg_stream_d(m + 256);       \
+                double x0 = __ldg(xv), x1 = __ldg(xv + 1), x2 = __ldg(xv + 2);                                   \
+                s0 += m0 * x0 + m1 * x1 + m2 * x2;                                                               \
+                s1 += m3 * x0 + m4 * x1 + m5 * x2;                                                               \
+                s2 += m6 * x0 + m7 * x1 + m8 * x2;                                                               \
             }
+            if (p.slice_c16 != nullptr && p.slice_c16[s]) {
+                // compressed slice (option sell_c16_all): 74.1 instead of 76 bytes per entry
+                const unsigned short *h1 = p.scol16 + off + lane;
+                const int *b1 = p.sbase + (off >> 5);
+                for (uint32_t q = 0; q < width; q++) NGSB_B3_ENTRY(__ldg(b1 + q) + (int)ldg_stream_u16(h1 + q * 32))
+            } else {
+                const int *c1 = p.scol + off + lane;
+                for (uint32_t q = 0; q < width; q++) NGSB_B3_ENTRY(ldg_stream_i(c1 + q * 32))
+            }
+#undef NGSB_B3_ENTRY
         }
         if (p.slice_ovf != nullptr) {
             int k = p.slice_ovf[src];
@@ -663,6 +718,7 @@ __global__ void __launch_bounds__(256) sell_ovf_copy_kernel(const uint64_t *__re
 // (smallest column of the step) + 16-bit offset when all steps of the slice allow it; otherwise the slice keeps its 32-bit
 // columns.  One warp per scheduled slice.  Neighbouring rows of a finite-element numbering couple to neighbouring dofs, so
 // the spread inside one step is small except where rows of different structure meet.
+template <bool PAIRED>     // PAIRED: real layout (columns in packets of two per lane), else [j][lane] (complex, 3x3 blocks)
 __global__ void __launch_bounds__(256) sell_compress_kernel(const uint64_t *__restrict__ slice_off, uint32_t nslices, const int32_t *__restrict__ scol,
                                                            uint16_t *__restrict__ scol16, int32_t *__restrict__ sbase, uint8_t *__restrict__ slice_c16)
 {
@@ -673,7 +729,8 @@ __global__ void __launch_bounds__(256) sell_compress_kernel(const uint64_t *__re
     const uint32_t width = (uint32_t)((slice_off[s + 1] - off) >> 5);
     bool ok = true;
     for (uint32_t j = 0; j < width; j++) {
-        const int32_t c = scol[off + ((uint64_t)(j >> 1) * 32 + lane) * 2 + (j & 1)];
+        const uint64_t pos = PAIRED ? off + ((uint64_t)(j >> 1) * 32 + lane) * 2 + (j & 1) : off + (uint64_t)j * 32 + lane;
+        const int32_t c = scol[pos];
         int32_t mn = c, mx = c;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -684,7 +741,7 @@ __global__ void __launch_bounds__(256) sell_compress_kernel(const uint64_t *__re
     }
     if (ok)
         for (uint32_t j = 0; j < width; j++) {
-            const uint64_t pos = off + ((uint64_t)(j >> 1) * 32 + lane) * 2 + (j & 1);
+            const uint64_t pos = PAIRED ? off + ((uint64_t)(j >> 1) * 32 + lane) * 2 + (j & 1) : off + (uint64_t)j * 32 + lane;
             const int32_t c = scol[pos];
             int32_t mn = c;
 #pragma unroll
@@ -827,7 +884,8 @@ int sell_build(ngsb_csr *A, const uint64_t *h_rowptr)
     NGSB_CUDA(cudaGetLastError());
     // ---- 3b. 16-bit column offsets for the real kernel (option sell_c16, default on)
     A->sell_c16_entries = 0;
-    if (A->kind == NGSB_REAL && ctx->sell_c16 != 0 && A->sell_entries > 0) {
+    // complex and 3x3-block matrices ([j][lane] columns): option sell_c16_all, default off until measured
+    if ((A->kind == NGSB_REAL ? ctx->sell_c16 != 0 : ctx->sell_c16_all != 0) && A->sell_entries > 0) {
         unsigned long long *d_cnt = nullptr;
         NGSB_CUDA(cudaMalloc(&A->d_scol16, (A->sell_entries + 64) * sizeof(uint16_t)));
         NGSB_CUDA(cudaMalloc(&A->d_sbase, (A->sell_entries / 32 + 8) * sizeof(int32_t)));
@@ -836,7 +894,8 @@ int sell_build(ngsb_csr *A, const uint64_t *h_rowptr)
         NGSB_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), ctx->stream));
         NGSB_CUDA(cudaMemsetAsync(A->d_scol16, 0, (A->sell_entries + 64) * sizeof(uint16_t), ctx->stream));
         NGSB_CUDA(cudaMemsetAsync(A->d_sbase, 0, (A->sell_entries / 32 + 8) * sizeof(int32_t), ctx->stream));
-        sell_compress_kernel<<<grid_slots, 256, 0, ctx->stream>>>(A->d_slice_off, ns, A->d_scol, A->d_scol16, A->d_sbase, A->d_slice_c16);
+        if (A->kind == NGSB_REAL) sell_compress_kernel<true><<<grid_slots, 256, 0, ctx->stream>>>(A->d_slice_off, ns, A->d_scol, A->d_scol16, A->d_sbase, A->d_slice_c16);
+        else sell_compress_kernel<false><<<grid_slots, 256, 0, ctx->stream>>>(A->d_slice_off, ns, A->d_scol, A->d_scol16, A->d_sbase, A->d_slice_c16);
         sell_c16_count_kernel<<<grid_sl, 256, 0, ctx->stream>>>(A->d_slice_off, A->d_slice_c16, ns, d_cnt);
         NGSB_CUDA(cudaGetLastError());
         unsigned long long cnt = 0;
@@ -907,7 +966,7 @@ int sell_launch(const SpmvArgs &a)
     p.slice_ovf = A->novf ? A->d_slice_ovf : nullptr;
     p.ovf_slot = A->d_ovf_slot; p.ovf_sum = A->d_ovf_sum; p.novf = A->novf;
     p.nslices = A->nslices; p.nrows = A->h;
-    if (A->sell_c16_entries > 0 && ctx->sell_c16 != 0) { p.scol16 = A->d_scol16; p.sbase = A->d_sbase; p.slice_c16 = A->d_slice_c16; }
+    if (A->sell_c16_entries > 0 && (A->kind == NGSB_REAL ? ctx->sell_c16 != 0 : ctx->sell_c16_all != 0)) { p.scol16 = A->d_scol16; p.sbase = A->d_sbase; p.slice_c16 = A->d_slice_c16; }
     p.pf_steps = (int)ctx->sell_pf_steps;
     p.pf_next = (int)ctx->sell_pf_next;
     p.x = a.x; p.y = a.y; p.sr = a.sr; p.si = A->kind == NGSB_COMPLEX ? a.si : 0.0;

@@ -921,7 +921,7 @@ extern "C" int ngsb_csr_stream_bytes(const ngsb_csr *A, double *bytes, uint64_t 
     const double b = A->kind == NGSB_BLOCK3 ? 3.0 : 1.0;
     const double per_entry = b * b * S + 4.0;
     const double c16 = (double)A->sell_c16_entries, rest = (double)A->sell_entries - c16;
-    *bytes = c16 * (8.0 + 2.0 + 4.0 / 32.0) + rest * per_entry + 4.0 * (double)A->h + (double)(A->w + A->h) * b * S;
+    *bytes = c16 * (b * b * S + 2.0 + 4.0 / 32.0) + rest * per_entry + 4.0 * (double)A->h + (double)(A->w + A->h) * b * S;
     if (c16_entries) *c16_entries = A->sell_c16_entries;
     return NGSB_OK;
 }

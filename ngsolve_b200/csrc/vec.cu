@@ -560,6 +560,7 @@ extern "C" int ngsb_ctx_set_option(ngsb_ctx *ctx, const char *name, long value)
     else if (!strcmp(name, "sell_pf_steps")) { NGSB_REQUIRE(value >= 0 && value <= 16, "sell_pf_steps out of range"); ctx->sell_pf_steps = value; }
     else if (!strcmp(name, "sell_pf_next")) { NGSB_REQUIRE(value >= 0 && value <= 64, "sell_pf_next out of range"); ctx->sell_pf_next = value; }
     else if (!strcmp(name, "sell_c16")) { NGSB_REQUIRE(value == 0 || value == 1, "sell_c16 must be 0 or 1"); ctx->sell_c16 = value; }
+    else if (!strcmp(name, "sell_c16_all")) { NGSB_REQUIRE(value == 0 || value == 1, "sell_c16_all must be 0 or 1"); ctx->sell_c16_all = value; }
     else if (!strcmp(name, "sell_sigma")) { NGSB_REQUIRE(value >= -1 && value <= (1 << 24), "sell_sigma out of range"); ctx->sell_sigma = value; }
     else if (!strcmp(name, "sell_cap")) { NGSB_REQUIRE(value >= 0 && value <= (1 << 20), "sell_cap out of range"); ctx->sell_cap = value; }
     else if (!strcmp(name, "spmv_tile")) { NGSB_REQUIRE(value == 0 || (value >= 256 && value <= 8192 && value % 256 == 0), "spmv_tile out of range"); ctx->spmv_tile = value; }

@@ -229,3 +229,44 @@ def test_cg_fold_u_is_the_same_solve(kind, stop):
             assert np.max(np.abs(u - ref[2])) <= 1e-14 * np.max(np.abs(ref[2]))
         else:
             assert np.array_equal(u, ref[2])
+
+
+@pytest.mark.parametrize("kind", [1, 3], ids=["complex", "block3"])
+@pytest.mark.parametrize("n", [(32, 32, 2), (6, 5, 4)], ids=["150k-rows-p4", "small-p3"])
+def test_c16_all_complex_and_block_entries(kind, n):
+    """option sell_c16_all: 16-bit column offsets for Complex and Mat<3,3> matrices too (18.1 / 74.1 instead of 20 / 76
+    bytes per entry).  Same summation order: Mult, MultAdd and the CG solve are bit-identical with the option off."""
+    import ngsolve_b200.la as la
+    from ngsolve_b200 import workloads as W
+    ctx = la.default_context()
+    box = W.FemBox(n, order=4 if n[0] > 10 else 3, kind=kind, mass=(1.0 + 0.5j) if kind == 1 else 0.5, lame=(1.0, 0.7))
+    rng = np.random.default_rng(7)
+    xs = rng.random(box.ndof * box.entrysize) if kind != 1 else rng.random(box.ndof) + 1j * rng.random(box.ndof)
+    y0 = rng.random(box.ndof * box.entrysize) if kind != 1 else rng.random(box.ndof) - 1j * rng.random(box.ndof)
+    res = []
+    try:
+        for on in (1, 0):
+            ctx.set_option("sell_c16_all", on)
+            A, f = box.device_system(ctx)
+            x = la.BaseVector(xs, entrysize=box.entrysize, ctx=ctx)
+            y = A.CreateColVector()
+            A.Mult(x, y)
+            z = la.BaseVector(y0, entrysize=box.entrysize, ctx=ctx)
+            A.MultAdd(-0.75, x, z)
+            sb, n16 = A.StreamBytes()
+            ent = A.Layout()[0]
+            if on:
+                assert n16 > 0.5 * ent and sb < A.MultBytes() * 1.03, (n16, ent, sb, A.MultBytes())
+                if n[0] < 10:
+                    assert n16 == ent
+            else:
+                assert n16 == 0
+            inv = la.CGSolver(A, A.CreateSmoother(box.freedofs()), precision=1e-8, maxsteps=400)
+            u = f.CreateVector()
+            inv.Mult(f, u)
+            res.append((y.NumPy().copy(), z.NumPy().copy(), u.NumPy().copy(), inv.GetSteps()))
+    finally:
+        ctx.set_option("sell_c16_all", 0)
+    for a, b in zip(res[0][:3], res[1][:3]):
+        assert np.array_equal(a, b)
+    assert res[0][3] == res[1][3]
