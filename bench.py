@@ -30,6 +30,7 @@ import numpy as np  # noqa: E402
 
 METRIC = "cg_iterations_per_s"
 UNIT = "iterations/s"
+SAMPLE_M_T1 = 20         # single-thread CPU sample: 0.23 M dofs, 10.7 M non-zeros (128 MB of matrix)
 SAMPLE_M = 50            # CPU sample: (3*50+1)^3 = 3.4 M dofs, 163 M non-zeros (2 GB of matrix: far out of the host caches)
 
 
@@ -86,7 +87,19 @@ def cpu_cg_reference(iters, warmup, full_nnz):
         return None
     raw, nnz, n = d["it_per_s"], d["nnz"], d["ndof"]
     b_iter = nnz * 12 + n * (4 + 8 + 8) + 21 * n * 8
-    return dict(value=raw * nnz / full_nnz, unit=UNIT, cores=d["threads"], kind="reference",
+    # SURVEY 8d asks for T = 1 beside T = all cores: a second process (one thread count per process, 8a1) on a smaller sample
+    one = None
+    try:
+        r1 = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "ref_cpu_cg.py"), "--m", str(SAMPLE_M_T1), "--iters", "20",
+                             "--warmup", "2", "--threads", "1"], env=env, capture_output=True, text=True, timeout=300)
+        d1 = json.loads(r1.stdout.strip().splitlines()[-1])
+        one = dict(value=d1["it_per_s"] * d1["nnz"] / full_nnz, raw_iterations_per_s=d1["it_per_s"], cores=1, sample_ndof=d1["ndof"],
+                   sample_nnz=d1["nnz"], spmv_gbs=d1["spmv_gbs"],
+                   sample="same solver with SetNumThreads(1), 20 iterations on the %.2fM-dof system (%d^3 cubes), scaled by nnz"
+                          % (d1["ndof"] / 1e6, SAMPLE_M_T1))
+    except Exception as e:                    # noqa: BLE001
+        sys.stderr.write("single-thread reference run unavailable: %r\n" % (e,))
+    return dict(value=raw * nnz / full_nnz, unit=UNIT, cores=d["threads"], kind="reference", single_thread=one,
                 sample="NGSolve %s C++ CGSolver + JacobiPrecond under TaskManager(%d threads), %d iterations on the %.2fM-dof system of the same "
                        "family (%d^3 cubes, injected by CreateFromCOO): %.1f it/s = %.1f GB/s of the reference's per-iteration traffic, SpMV alone "
                        "%.2f ms = %.1f GB/s; scaled by nnz ratio %.4g to the full size"

@@ -30,9 +30,10 @@ def peak():
     return float(json.load(open(p))["hbm_gbs"]) if os.path.exists(p) else 6650.0
 
 
-def time_mult(ctx, A, x, y, reps=30):
+def time_mult(ctx, A, x, y, reps=50):
+    # SURVEY 8d metric 1: median of >= 50 CUDA-event-timed Mult calls after 5 warm-ups, same x/y buffers
     st = torch.cuda.ExternalStream(ctx.stream)
-    for _ in range(3):
+    for _ in range(5):
         A.Mult(x, y)
     ctx.sync()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
