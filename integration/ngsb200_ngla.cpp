@@ -35,6 +35,29 @@ namespace ngla
   template <typename SCAL> constexpr int KindOf (int es)
   { return std::is_same_v<SCAL,Complex> ? NGSB_COMPLEX : (es == 3 ? NGSB_BLOCK3 : NGSB_REAL); }
 
+  // BaseScalar kept on the device (linalg/basescalar.hpp:17-29; ngscuda's UnifiedScalar, ngscuda/unifiedvector.hpp:113-136):
+  // a solver written with vec.InnerProduct(other, scal) / vec.Add(scal, other) never brings its scalars to the host
+  class B200Scalar : public BaseScalar
+  {
+    ngsb_scalar * h = nullptr;
+    bool cplx;
+  public:
+    B200Scalar (bool acplx) : cplx(acplx) { Check (ngsb_scalar_create (TheCtx(), &h)); }
+    ~B200Scalar () { ngsb_scalar_destroy (h); }
+    ngsb_scalar * Handle () const { return h; }
+    bool IsComplex () const override { return cplx; }
+    void Set (double d) override { double z[2] = {d,0}; cplx = false; Check (ngsb_scalar_set (h, z)); }
+    void Set (Complex c) override { double z[2] = {c.real(),c.imag()}; cplx = true; Check (ngsb_scalar_set (h, z)); }
+    double GetD () const override { double z[2]; Check (ngsb_scalar_get (h, z)); return z[0]; }        // synchronises
+    Complex GetC () const override { double z[2]; Check (ngsb_scalar_get (h, z)); return Complex (z[0], z[1]); }
+    static B200Scalar & Cast (BaseScalar & s)
+    {
+      auto p = dynamic_cast<B200Scalar*> (&s);
+      if (!p) throw Exception ("B200Vector: scalar is not a device scalar (use vec.CreateScalar())");
+      return *p;
+    }
+  };
+
   // ---- vector: host mirror + dirty flags like UnifiedVector (ngscuda/unifiedvector.hpp:8-98) ----------
   template <typename SCAL>
   class B200Vector : public S_BaseVector<SCAL>
@@ -121,6 +144,14 @@ namespace ngla
     Complex InnerProductC (const BaseVector & v2, bool conjugate = false) const override
     { double out[2]; Check (ngsb_vec_dot (Dev(), Cast(v2).Dev(), conjugate, out)); return Complex (out[0], out[1]); }
     double L2Norm () const override { double n; Check (ngsb_vec_nrm2 (Dev(), &n)); return n; }
+    // the scalar-by-reference variants (linalg/basevector.cpp:259-298): result / factor stay in device memory
+    void InnerProduct (const BaseVector & v2, BaseScalar & scal, bool conjugate = false) const override
+    { Check (ngsb_vec_dot_dev (Dev(), Cast(v2).Dev(), conjugate, B200Scalar::Cast(scal).Handle())); }
+    BaseVector & Scale (BaseScalar & scal) override
+    { Check (ngsb_vec_scale_dev (DevW(), B200Scalar::Cast(scal).Handle())); return *this; }
+    BaseVector & Add (BaseScalar & scal, const BaseVector & v) override
+    { Check (ngsb_vec_axpy_dev (DevW(), B200Scalar::Cast(scal).Handle(), Cast(v).Dev())); return *this; }
+    shared_ptr<BaseScalar> CreateScalar () const override { return make_shared<B200Scalar> (std::is_same_v<SCAL,Complex>); }
     AutoVector CreateVector () const override { return make_unique<B200Vector<SCAL>> (this->size, EntryScalars()); }
     AutoVector Range (T_Range<size_t> r) const override
     {

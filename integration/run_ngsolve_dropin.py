@@ -93,6 +93,26 @@ with TaskManager():
     diff.data = gfu.vec - gfu2.vec
     out.update(bj_rel_diff=Norm(diff) / Norm(gfu.vec))
 
+    # ---- device-resident scalars (BaseScalar hooks, linalg/basevector.cpp:259-298): one CG-style step without host scalars
+    try:
+        sc, sc2 = fdev.CreateScalar(), fdev.CreateScalar()
+        w = fdev.CreateVector()
+        w.data = jdev * fdev
+        fdev.InnerProduct(w, sc)                       # <f, C f> stays on the device
+        host_ip = InnerProduct(fdev, w)
+        t = fdev.CreateVector()
+        t.data = fdev
+        t.Add(sc, w)                                   # t = f + <f, C f> * C f with the device scalar
+        t2 = fdev.CreateVector()
+        t2.data = fdev + host_ip * w
+        dd = t.CreateVector()
+        dd.data = t - t2
+        t.InnerProduct(t, sc2)
+        out.update(scalar_type=type(sc).__name__, scalar_ip_rel_err=abs(sc.__float__() - host_ip) / abs(host_ip) if hasattr(sc, "__float__") else None,
+                   scalar_axpy_rel_diff=Norm(dd) / Norm(t2), scalar_str=str(sc2))
+    except Exception as e:                           # noqa: BLE001 -- report, keep the other results
+        out["scalar_error"] = str(e)[:300]
+
     # ---- the other two entry kinds through the same registry: Mat<3,3,double> (elasticity, H1 dim=3) and Complex (Helmholtz, GMRES)
     def attempt(tag, fn):
         try:
