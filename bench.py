@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-full-solve", action="store_true")
     ap.add_argument("--cpu-iters", type=int, default=150)
+    ap.add_argument("--cpu-sample", type=int, default=SAMPLE_M, help="cubes per axis of the CPU arm's sample system")
+    ap.add_argument("--cpu-sample-t1", type=int, default=SAMPLE_M_T1, help="the same for the single-thread run")
     return ap.parse_args()
 
 
@@ -465,11 +467,12 @@ def emit(line):
 def main():
     # stdout carries exactly one JSON line: native libraries (the NCCL version banner, ...) write to fd 1 directly, so
     # fd 1 is pointed at stderr for the whole run and the line goes to a saved duplicate of the original stdout
-    global _REAL_STDOUT
+    global _REAL_STDOUT, SAMPLE_M, SAMPLE_M_T1
     sys.stdout.flush()
     _REAL_STDOUT = os.dup(1)
     os.dup2(2, 1)
     args = parse()
+    SAMPLE_M, SAMPLE_M_T1 = args.cpu_sample, args.cpu_sample_t1
     if args.impl == "reference":
         run_reference(args)
     else:
