@@ -74,11 +74,24 @@ int ngsb_ctx_device(const ngsb_ctx *ctx, int *device, int *sm_count);
 void *ngsb_ctx_stream(ngsb_ctx *ctx);                   /* cudaStream_t */
 /* kernels of this library launched on ctx so far (bench.py's gpu_launches) */
 int ngsb_ctx_launch_count(const ngsb_ctx *ctx, uint64_t *count);
-/* tuning knobs: "spmv_algo" (0 auto = 3; 1 sub-warp CSR; 2 TMA-streamed CSR; 3 SELL-32),
- * "cg_batch", "spmv_ctas_per_sm", "timing", "cg_fold_u" (0/1: the CG direction kernel also does u += al s, 10 instead
- * of 11 vector passes per iteration), "dist_overlap" (0/1, read by ngsb_parmat_create), and -- read when a matrix is created --
- * "sell_cap", "spmv_tile", "spmv_ncw", "spmv_stages", "spmv_subwarp" (0 = default).
- * Unknown names fail with NGSB_ERR_INVALID. */
+/* options (name, long value); unknown names fail with NGSB_ERR_INVALID.
+ *   read at every launch / solve:
+ *     "spmv_algo"        0 auto (= 3), 1 sub-warp CSR, 2 TMA-streamed CSR, 3 SELL-32
+ *     "spmv_ctas_per_sm" grid of the SpMV kernels in CTAs per SM, 0 = default (96 for SELL)
+ *     "cg_batch"         CG iterations per CUDA graph / between two polls of the device stop flag (default 16)
+ *     "cg_fold_u"        0/1: the CG direction kernel also does u += al s (10 instead of 11 vector passes per iteration)
+ *     "sell_variant"     inner-loop variant of the real SELL kernel (0 default; 1-6 kept for A/B, all bit-identical)
+ *     "sell_pf_steps", "sell_pf_next"   L2 prefetch distances of the compressed loop (0 = off, default)
+ *     "sell_c16"         0/1: use the 16-bit column offsets of real matrices (default 1; also read at creation)
+ *     "timing"           0/1: record an event pair around every launch (ngsb_ctx_kernel_time)
+ *   read when a matrix is created:
+ *     "sell_c16_all"     0/1: 16-bit column offsets for Complex and Mat<3,3> matrices too (default 0; must still be on at launch)
+ *     "sell_cap"         longest row part kept in a slice, 0 = max(64, 4 x mean row length) or the longest row when cheap
+ *     "sell_sigma"       rows sorted by length inside windows of this many rows, -1 = automatic, 0/1 = off
+ *     "sell_schedule"    slices ordered by their smallest first column: 0 off, 1 automatic, 2 on
+ *     "spmv_tile", "spmv_ncw", "spmv_stages", "spmv_subwarp"   CSR kernels, 0 = default
+ *   read by ngsb_parmat_create:
+ *     "dist_overlap"     0/1: interface slices first, pushed while the interior slices are multiplied (default 0) */
 int ngsb_ctx_set_option(ngsb_ctx *ctx, const char *name, long value);
 /* device time in ms of the kernels recorded since the last reset for a class
  * ("spmv", "cgupdate", "all"); only meaningful when option "timing" is 1. */

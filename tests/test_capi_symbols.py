@@ -47,3 +47,13 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in txt.replace("ngs_oracle", "oracle") or f == "__init__.py" and False, os.path.join(dirpath, f)
+
+
+def test_every_option_is_documented_in_the_header():
+    """ngsb_ctx_set_option's accepted names (csrc/vec.cu) all appear in the option list of include/ngsb200.h"""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    names = re.findall(r'strcmp\(name, "([a-z0-9_]+)"\)', open(os.path.join(root, "ngsolve_b200", "csrc", "vec.cu")).read())
+    header = open(os.path.join(root, "include", "ngsb200.h")).read()
+    assert len(names) >= 15
+    assert [n for n in names if '"%s"' % n not in header] == []
