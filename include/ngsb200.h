@@ -85,6 +85,11 @@ int ngsb_ctx_launch_count(const ngsb_ctx *ctx, uint64_t *count);
  *     "sell_c16"         0/1: use the 16-bit column offsets of real matrices (default 1; also read at creation)
  *     "timing"           0/1: record an event pair around every launch (ngsb_ctx_kernel_time)
  *   read when a matrix is created:
+ *     "reorder"          internal dof reordering of square matrices (csrc/reorder.cu): -1 automatic (default), 0 off, 1 always.
+ *                        The matrix keeps the caller's numbering at the interface; products and the fused solvers run on
+ *                        P A P^T with P = Cuthill-McKee of the pattern (ngsb_csr_rcm).  Automatic = at least
+ *                        "reorder_min_rows" rows (default 32768) and fewer than half of the natural 32-row slices fit for
+ *                        16-bit column offsets -- the signature of netgen's entity-by-entity numbering
  *     "sell_c16_all"     0/1: 16-bit column offsets for Complex and Mat<3,3> matrices too (default 0; must still be on at launch)
  *     "sell_cap"         longest row part kept in a slice, 0 = max(64, 4 x mean row length) or the longest row when cheap
  *     "sell_sigma"       rows sorted by length inside windows of this many rows, -1 = automatic, 0/1 = off
@@ -162,8 +167,15 @@ int ngsb_csr_multadd(const ngsb_csr *A, const double s[2], const ngsb_vec *x, ng
 /* BaseMatrix::Mult (= SetZero + MultAdd(1)), linalg/basematrix.cpp:120-127.   y = A*x */
 int ngsb_csr_mult(const ngsb_csr *A, const ngsb_vec *x, ngsb_vec *y);
 /* SparseMatrix::Reorder(perm): linalg/sparsematrix_impl.hpp:762-783.
- * new(i, inv[c]) = old(perm[i], c); perm is a host array of `height` indices. */
+ * new(i, inv[c]) = old(perm[i], c); perm is a host array of `height` indices.  Done on the device. */
 int ngsb_csr_reorder(const ngsb_csr *A, const uint64_t *perm, ngsb_csr **out);
+/* The bandwidth-reducing permutation option "reorder" uses, in the form Reorder() takes (new row k = old row perm[k]).
+ * The reference computes none (its dof numbering is netgen's, comp/h1hofespace.cpp:833-880); this is level-synchronous
+ * Cuthill-McKee on the device, specified serially in oracle/ngs_oracle.c (orc_rcm) and equal to it bit for bit. */
+int ngsb_csr_rcm(const ngsb_csr *A, uint64_t *perm);
+/* whether products of A run on an internally reordered copy, its permutation (perm may be NULL), and the share of natural
+ * 32-row slices fit for 16-bit column offsets that the automatic mode looked at (-1: not evaluated) */
+int ngsb_csr_reorder_info(const ngsb_csr *A, int *reordered, uint64_t *perm, double *natural_c16_share);
 /* copy the device CSR back (pattern parity checks): any pointer may be NULL */
 int ngsb_csr_download(const ngsb_csr *A, uint64_t *rowptr, int32_t *col, void *val);
 /* device layout diagnostics: padded entries of the SELL-32 copy the default SpMV kernel streams,

@@ -63,6 +63,8 @@ PROTOTYPES = {
     "ngsb_csr_multadd": [_vp, C.POINTER(_d), _vp, _vp],
     "ngsb_csr_mult": [_vp, _vp, _vp],
     "ngsb_csr_reorder": [_vp, _vp, _pvp],
+    "ngsb_csr_rcm": [_vp, _vp],
+    "ngsb_csr_reorder_info": [_vp, _vp, _vp, _vp],
     "ngsb_csr_download": [_vp, _vp, _vp, _vp],
     "ngsb_csr_mult_bytes": [_vp, C.POINTER(_d)],
     "ngsb_csr_stream_bytes": [_vp, C.POINTER(_d), C.POINTER(C.c_uint64)],

@@ -78,6 +78,9 @@ struct ngsb_ctx {
     long cg_fold_u = 0;          // CG: `u += al s` in the direction kernel instead of the update kernel (10 vector passes, not 11)
     long dist_overlap = 0;       // distributed CG: interface slices first, push, interior slices while the values travel
                                  // (read when a parallel matrix is created; peer-memory data path only)
+    long reorder = -1;           // internal Cuthill-McKee reordering of square matrices: 0 off, 1 always, -1 automatic
+                                 // (read when a matrix is created)
+    long reorder_min_rows = 32768;   // automatic mode: smaller matrices keep their numbering
     long timing = 0;
     // reduction workspace (partials + counters), pinned host scratch
     double *d_partials = nullptr;   // 2 * max_partials doubles

@@ -697,6 +697,8 @@ extern "C" int ngsb_parmat_create_ex(ngsb_comm *comm, const ngsb_csr *local, con
     NGSB_REQUIRE(comm && local && ex_first && out, "ngsb_parmat_create: NULL argument");
     NGSB_REQUIRE(local->ctx == comm->ctx, "ngsb_parmat_create: matrix and communicator belong to different contexts");
     NGSB_REQUIRE(local->h == local->w, "ngsb_parmat_create: local matrix must be square");
+    NGSB_REQUIRE(local->inner == nullptr, "ngsb_parmat_create: the local matrix is internally reordered; create it with option reorder = 0 "
+                 "(the exchange tables index the caller's numbering)");
     NGSB_REQUIRE(comm->comm || allgather || comm->nranks == 1, "ngsb_parmat_create: this communicator has no NCCL; pass the bootstrap all-gather");
     ngsb_ctx *ctx = comm->ctx;
     NGSB_CUDA(cudaSetDevice(ctx->device));
@@ -983,7 +985,9 @@ extern "C" int ngsb_parmat_cg_solve(const ngsb_parmat *P, const ngsb_jacobi *C, 
     ngsb_parmat *Pm = const_cast<ngsb_parmat *>(P);
     const bool use_graph = P->p2p && !ctx->timing && getenv("NGSB_NO_CUDA_GRAPH") == nullptr && batch > 1;
     if (rc == NGSB_OK && use_graph) {
-        const void *key[9] = {u->d, d, w, s, as, C, (const void *)(intptr_t)ip_mode, d_hist, (const void *)(intptr_t)ctx->cg_fold_u};
+        // the preconditioner enters by its unique id, never by its address (a re-created object may get the same one back)
+        const void *key[9] = {u->d, d, w, s, as, (const void *)(uintptr_t)(C ? C->uid : 0), (const void *)(intptr_t)ip_mode, d_hist,
+                              (const void *)(intptr_t)(ctx->cg_fold_u | (ctx->sell_variant << 4) | (ctx->sell_c16 << 12) | (ctx->spmv_ctas_per_sm << 16))};
         const bool hit = Pm->graph_exec && Pm->g_batch == batch && memcmp(key, Pm->g_key, sizeof(key)) == 0;
         if (!hit) {
             cudaGraph_t graph = nullptr;

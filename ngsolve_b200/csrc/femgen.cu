@@ -29,7 +29,7 @@
 namespace ngsb {
 
 int csr_adopt_device(ngsb_ctx *ctx, size_t h, size_t w, size_t nnz, uint64_t *d_rowptr, int32_t *d_col, double *d_val, int kind,
-                     ngsb_csr **out);   // spmv.cu
+                     ngsb_csr **out, bool allow_reorder = true);   // spmv.cu
 
 static const int NBLOCKS = 26;   // 1 vertex + 7 edge + 12 face + 6 cell entity types
 static const int MAXTETS = 24;

@@ -175,6 +175,7 @@ using namespace ngsb;
 int ngsb::jacobi_alloc(ngsb_ctx *ctx, size_t n, int kind, const uint8_t *freebits, ngsb_jacobi **out)
 {
     ngsb_jacobi *J = new ngsb_jacobi();
+    J->uid = ngsb::next_uid();
     J->ctx = ctx;
     J->n = n;
     J->kind = kind;
@@ -263,6 +264,36 @@ int jacobi_build(const ngsb_csr *A, const uint8_t *freebits, int (*cumulate)(voi
 }
 } // namespace ngsb
 
+namespace ngsb {
+int jacobi_for_inner(const ngsb_jacobi *J, const ngsb_csr *A, const ngsb_jacobi **out)
+{
+    NGSB_REQUIRE(A->inner && A->d_perm, "jacobi_for_inner: matrix is not reordered");
+    if (J->permuted && J->permuted_for == A->uid) { *out = J->permuted; return NGSB_OK; }
+    if (J->permuted) { ngsb_jacobi_destroy(J->permuted); J->permuted = nullptr; }
+    ngsb_ctx *ctx = J->ctx;
+    ngsb_jacobi *P = new ngsb_jacobi();
+    P->ctx = ctx; P->n = J->n; P->kind = J->kind; P->uid = next_uid();
+    const size_t ms = kind_matscalars(J->kind);
+    cudaError_t e = cudaMalloc(&P->d_invdiag, std::max<size_t>(1, J->n * ms) * sizeof(double));
+    if (e == cudaSuccess && J->d_bits) e = cudaMalloc(&P->d_bits, (J->n + 7) / 8 + 8);
+    if (e != cudaSuccess) { ngsb_jacobi_destroy(P); set_error("jacobi_for_inner: cudaMalloc failed: %s", cudaGetErrorString(e)); return NGSB_ERR_NOMEM; }
+    int rc = NGSB_OK;
+    if (ms == 9) {
+        // 3x3 blocks: three gathers of Vec<3> rows do not apply; move the nine doubles as three interleaved triples
+        for (int k = 0; k < 3 && rc == NGSB_OK; k++) rc = launch_perm_gather_strided(ctx, J->d_invdiag + 3 * k, A->d_perm, J->n, 3, 9, P->d_invdiag + 3 * k);
+    } else rc = launch_perm_gather(ctx, J->d_invdiag, A->d_perm, J->n, (int)ms, P->d_invdiag);
+    if (rc == NGSB_OK && J->d_bits) {
+        cudaMemsetAsync(P->d_bits, 0, (J->n + 7) / 8 + 8, ctx->stream);
+        rc = launch_perm_bits(ctx, J->d_bits, A->d_perm, J->n, P->d_bits);
+    }
+    if (rc != NGSB_OK) { ngsb_jacobi_destroy(P); return rc; }
+    J->permuted = P;
+    J->permuted_for = A->uid;
+    *out = P;
+    return NGSB_OK;
+}
+} // namespace ngsb
+
 extern "C" int ngsb_jacobi_create_from_csr(const ngsb_csr *A, const uint8_t *freebits, ngsb_jacobi **out)
 {
     NGSB_REQUIRE(A && out, "ngsb_jacobi_create_from_csr: NULL argument");
@@ -277,6 +308,7 @@ extern "C" int ngsb_jacobi_destroy(ngsb_jacobi *J)
     cudaStreamSynchronize(J->ctx->stream);
     cudaFree(J->d_invdiag);
     cudaFree(J->d_bits);
+    if (J->permuted) ngsb_jacobi_destroy(J->permuted);
     delete J;
     return NGSB_OK;
 }

@@ -30,12 +30,29 @@ struct Workspace {
     double *d_hist = nullptr;
     size_t hist_cap = 0;
     cudaGraphExec_t graph_exec = nullptr;
-    // key of the cached graph
-    const void *g_A = nullptr, *g_C = nullptr;
+    // key of the cached graph: the unique ids of matrix and preconditioner (never their addresses -- a destroyed and
+    // re-created object may get the same address back), the vectors, and every option the captured launches read
+    uint64_t g_A = 0, g_C = 0;
     double *g_ptrs[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    long g_batch = 0;
-    int g_ip = -1;
-    long g_algo = -1, g_cps = -1, g_fold = -1;
+    long g_opts[10] = {-1, -1, -1, -1, -1, -1, -1, -1, -1, -1};
+};
+
+// buffers taken from the workspace go back on every exit path
+struct BufLease {
+    ngsb_ctx *ctx;
+    std::vector<std::pair<size_t, double *>> held;
+    explicit BufLease(ngsb_ctx *c) : ctx(c) {}
+    int get(size_t nscal, double **out)
+    {
+        NGSB_TRY(ws_get_buf(ctx, nscal, out));
+        held.emplace_back(nscal, *out);
+        return NGSB_OK;
+    }
+    ~BufLease() { for (auto &b : held) ws_put_buf(ctx, b.first, b.second); }
+};
+struct EventPair {
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    ~EventPair() { if (ev[0]) cudaEventDestroy(ev[0]); if (ev[1]) cudaEventDestroy(ev[1]); }
 };
 
 static void ws_free(void *p)
@@ -451,6 +468,8 @@ static int enqueue_iteration(ngsb_ctx *ctx, const ngsb_csr *A, const CgVecs &v, 
     return NGSB_OK;
 }
 
+static bool sell_path(const ngsb_ctx *ctx) { return ctx->spmv_algo == 0 || ctx->spmv_algo == 3; }
+
 int cg_solve_device(const ngsb_csr *A, const ngsb_jacobi *C, const double *f, double *u, double prec, int maxsteps,
                     int ip_mode, int initialize, int *steps, double *history, int hist_cap, int *nhist)
 {
@@ -460,11 +479,26 @@ int cg_solve_device(const ngsb_csr *A, const ngsb_jacobi *C, const double *f, do
     if (hist_cap < 0) hist_cap = 0;
     if (!history) hist_cap = 0;
     NGSB_TRY(ws_state_impl(ctx, (size_t)hist_cap));
+    BufLease lease(ctx);
+    // internally reordered matrix (reorder.cu): the whole loop runs in the permuted numbering -- f and the start value are
+    // gathered once, every iteration multiplies P A P^T directly (no per-product gather), u is scattered back at the end
+    const ngsb_csr *Auser = A;
+    double *u_user = u;
+    if (A->inner && sell_path(ctx)) {
+        const int es = (int)kind_scalars(A->kind);
+        double *fp = nullptr, *up = nullptr;
+        NGSB_TRY(lease.get(nscal, &fp));
+        NGSB_TRY(lease.get(nscal, &up));
+        NGSB_TRY(launch_perm_gather(ctx, f, A->d_perm, A->h, es, fp));
+        if (!initialize) NGSB_TRY(launch_perm_gather(ctx, u, A->d_perm, A->h, es, up));
+        if (C) NGSB_TRY(jacobi_for_inner(C, A, &C));
+        f = fp; u = up; A = A->inner;
+    }
     double *w = nullptr, *s = nullptr, *d = nullptr, *as = nullptr;
-    NGSB_TRY(ws_get_buf(ctx, nscal, &s));
-    NGSB_TRY(ws_get_buf(ctx, nscal, &d));
-    NGSB_TRY(ws_get_buf(ctx, nscal, &as));
-    if (C) NGSB_TRY(ws_get_buf(ctx, nscal, &w));
+    NGSB_TRY(lease.get(nscal, &s));
+    NGSB_TRY(lease.get(nscal, &d));
+    NGSB_TRY(lease.get(nscal, &as));
+    if (C) NGSB_TRY(lease.get(nscal, &w));
 
     CgState *hs = ws->h_state;
     memset(hs, 0, sizeof(CgState));
@@ -505,8 +539,10 @@ int cg_solve_device(const ngsb_csr *A, const ngsb_jacobi *C, const double *f, do
     const bool use_graph = !ctx->timing && getenv("NGSB_NO_CUDA_GRAPH") == nullptr && batch > 1;
     if (use_graph) {
         double *key[6] = {u, d, w, s, as, (double *)f};
-        bool hit = ws->graph_exec && ws->g_A == A && ws->g_C == C && ws->g_batch == batch && ws->g_ip == ip_mode &&
-                   ws->g_algo == ctx->spmv_algo && ws->g_cps == ctx->spmv_ctas_per_sm && ws->g_fold == ctx->cg_fold_u && memcmp(key, ws->g_ptrs, sizeof(key)) == 0;
+        const long opts[10] = {batch, (long)ip_mode, ctx->spmv_algo, ctx->spmv_ctas_per_sm, ctx->cg_fold_u, ctx->sell_variant, ctx->sell_c16,
+                               ctx->sell_c16_all, ctx->sell_pf_steps, ctx->sell_pf_next};
+        bool hit = ws->graph_exec && ws->g_A == A->uid && ws->g_C == (C ? C->uid : 0) && memcmp(opts, ws->g_opts, sizeof(opts)) == 0 &&
+                   memcmp(key, ws->g_ptrs, sizeof(key)) == 0;
         if (!hit) {
             cudaGraph_t graph = nullptr;
             uint64_t launches_before = ctx->launches;
@@ -527,13 +563,14 @@ int cg_solve_device(const ngsb_csr *A, const ngsb_jacobi *C, const double *f, do
             }
             if (!updated) NGSB_CUDA(cudaGraphInstantiate(&ws->graph_exec, graph, 0));
             cudaGraphDestroy(graph);
-            ws->g_A = A; ws->g_C = C; ws->g_batch = batch; ws->g_ip = ip_mode;
-            ws->g_algo = ctx->spmv_algo; ws->g_cps = ctx->spmv_ctas_per_sm; ws->g_fold = ctx->cg_fold_u;
+            ws->g_A = A->uid; ws->g_C = C ? C->uid : 0;
+            memcpy(ws->g_opts, opts, sizeof(opts));
             memcpy(ws->g_ptrs, key, sizeof(key));
         }
     }
 
-    cudaEvent_t ev[2];
+    EventPair evp;
+    cudaEvent_t *ev = evp.ev;
     NGSB_CUDA(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
     NGSB_CUDA(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
     long enq = 0;          // batches enqueued
@@ -569,8 +606,8 @@ int cg_solve_device(const ngsb_csr *A, const ngsb_jacobi *C, const double *f, do
     }
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
     if (rc == NGSB_OK && e != cudaSuccess) { set_error("CG: %s", cudaGetErrorString(e)); rc = NGSB_ERR_CUDA; }
-    cudaEventDestroy(ev[0]);
-    cudaEventDestroy(ev[1]);
+    if (rc == NGSB_OK && Auser != A)       // back into the caller's numbering: u_user[j] = u[iperm[j]]
+        rc = launch_perm_gather(ctx, u, Auser->d_iperm, Auser->h, (int)kind_scalars(A->kind), u_user);
     if (rc == NGSB_OK) {
         NGSB_CUDA(cudaMemcpyAsync(&hs[3], ws->d_state, sizeof(CgState), cudaMemcpyDeviceToHost, ctx->stream));
         NGSB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -583,10 +620,6 @@ int cg_solve_device(const ngsb_csr *A, const ngsb_jacobi *C, const double *f, do
             NGSB_CUDA(cudaStreamSynchronize(ctx->stream));
         }
     }
-    ws_put_buf(ctx, nscal, s);
-    ws_put_buf(ctx, nscal, d);
-    ws_put_buf(ctx, nscal, as);
-    if (w) ws_put_buf(ctx, nscal, w);
     return rc;
 }
 
@@ -856,6 +889,23 @@ int ngsb::gmres_solve_impl(const ngsb_csr *A, const ngsb_jacobi *C, const ngsb_v
     NGSB_REQUIRE(maxsteps >= 1, "GMRESSolver::Mult: maxsteps < 1");
     ngsb_ctx *ctx = A->ctx;
     NGSB_CUDA(cudaSetDevice(ctx->device));
+    if (A->inner && !dist && sell_path(ctx)) {
+        // internally reordered matrix: the whole solve in the permuted numbering (see cg_solve_device)
+        const size_t nsc = A->h * kind_scalars(A->kind);
+        const int es = (int)kind_scalars(A->kind);
+        BufLease lease(ctx);
+        double *fp = nullptr, *xp = nullptr;
+        NGSB_TRY(lease.get(nsc, &fp));
+        NGSB_TRY(lease.get(nsc, &xp));
+        NGSB_TRY(launch_perm_gather(ctx, fvec->d, A->d_perm, A->h, es, fp));
+        if (!initialize) NGSB_TRY(launch_perm_gather(ctx, xvec->d, A->d_perm, A->h, es, xp));
+        const ngsb_jacobi *Cp = nullptr;
+        if (C) NGSB_TRY(jacobi_for_inner(C, A, &Cp));
+        ngsb_vec fv = *fvec, xv = *xvec;
+        fv.d = fp; fv.storage.reset(); xv.d = xp; xv.storage.reset();
+        NGSB_TRY(gmres_solve_impl(A->inner, Cp, &fv, &xv, prec, maxsteps, initialize, steps, history, hist_cap, nhist, nullptr));
+        return launch_perm_gather(ctx, xp, A->d_iperm, A->h, es, xvec->d);
+    }
     const uint8_t *master = dist ? dist->master : nullptr;
     const PeerReduce *R = dist ? dist->R : nullptr;
     const unsigned mask_div = (unsigned)(A->kind == NGSB_BLOCK3 ? 3 : 1);
@@ -1008,7 +1058,8 @@ int ngsb::gmres_solve_impl(const ngsb_csr *A, const ngsb_jacobi *C, const ngsb_v
     // has been read back (every kernel of the step that touches solver state returns at once when the flag is set), so the
     // stream never drains between steps.  The state is polled through two pinned slots.
     GmresState *slot = reinterpret_cast<GmresState *>(ctx->h_pinned);
-    cudaEvent_t ev[2] = {nullptr, nullptr};
+    EventPair evp;             // destroyed on every exit path
+    cudaEvent_t *ev = evp.ev;
     GM_CUDA(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
     GM_CUDA(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
     int jh = hst.j, enq = 0;
@@ -1050,8 +1101,6 @@ int ngsb::gmres_solve_impl(const ngsb_csr *A, const ngsb_jacobi *C, const ngsb_v
     }
     GM_CUDA(cudaMemcpyAsync(&hst, d_st, sizeof(hst), cudaMemcpyDeviceToHost, ctx->stream));
     GM_CUDA(cudaStreamSynchronize(ctx->stream));
-    cudaEventDestroy(ev[0]);
-    cudaEventDestroy(ev[1]);
     // j-- ; back substitution ; x += y_i v_i
     {
         SpanGuard g(ctx, KC_OTHER);

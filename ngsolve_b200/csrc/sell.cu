@@ -962,7 +962,7 @@ int sell_launch(const SpmvArgs &a)
     ngsb_ctx *ctx = A->ctx;
     SellParams p;
     memset(&p, 0, sizeof(p));
-    p.slice_off = A->d_slice_off; p.slice_src = A->d_slice_src; p.row_of = A->d_row_of; p.scol = A->d_scol; p.sval = A->d_sval;
+    p.slice_off = A->d_slice_off; p.slice_src = A->d_slice_src; p.row_of = a.user_rows ? A->d_row_user : A->d_row_of; p.scol = A->d_scol; p.sval = A->d_sval;
     p.slice_ovf = A->novf ? A->d_slice_ovf : nullptr;
     p.ovf_slot = A->d_ovf_slot; p.ovf_sum = A->d_ovf_sum; p.novf = A->novf;
     p.nslices = A->nslices; p.nrows = A->h;

@@ -552,7 +552,20 @@ int spmv_launch(const SpmvArgs &a)
     p.tile = A->tile;
     p.stages = A->stages;
 
-    if ((ctx->spmv_algo == 0 || ctx->spmv_algo == 3) && !a.use_range) return sell_launch(a);
+    if ((ctx->spmv_algo == 0 || ctx->spmv_algo == 3) && !a.use_range) {
+        if (A->inner != nullptr) {
+            // internally reordered matrix: x into the permuted numbering (one gather pass), the product on P A P^T, rows written
+            // back through the slot -> caller-row table
+            NGSB_REQUIRE(a.slice_list == nullptr, "SpMV: slice lists are not available on a reordered matrix");
+            ngsb_csr *in = A->inner;
+            NGSB_TRY(launch_perm_gather(ctx, a.x, A->d_perm, A->w, (int)kind_scalars(A->kind), in->d_xperm));
+            SpmvArgs b = a;
+            b.A = in; b.x = in->d_xperm; b.user_rows = true;
+            return sell_launch(b);
+        }
+        return sell_launch(a);
+    }
+    NGSB_REQUIRE(!A->csr_released, "SpMV: the CSR kernels (spmv_algo 1/2) need the CSR arrays, which this matrix released");
     NGSB_REQUIRE(a.slice_list == nullptr, "SpMV: a slice list needs the SELL kernel (spmv_algo 0 or 3)");
     const bool stream = ctx->spmv_algo != 1;
     if (stream) {
@@ -646,8 +659,12 @@ static int pick_subwarp(int kind, double mean_row)
     return 32;
 }
 
-static int finish_create(ngsb_csr *A, const uint64_t *h_rowptr)
+static uint64_t g_uid = 0;
+uint64_t next_uid() { return __atomic_add_fetch(&g_uid, 1, __ATOMIC_RELAXED); }
+
+static int finish_create(ngsb_csr *A, const uint64_t *h_rowptr, bool allow_reorder = true)
 {
+    A->uid = next_uid();
     ngsb_ctx *ctx = A->ctx;
     A->mean_row = A->h ? (double)A->nnz / (double)A->h : 0.0;
     size_t mx = 0;
@@ -680,6 +697,12 @@ static int finish_create(ngsb_csr *A, const uint64_t *h_rowptr)
     if (!rowoff.empty()) NGSB_CUDA(cudaMemcpyAsync(A->d_rowoff, rowoff.data(), rowoff.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream));
     if (!longrows.empty()) NGSB_CUDA(cudaMemcpyAsync(A->d_longrows, longrows.data(), longrows.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
     NGSB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (allow_reorder) {
+        // netgen-style numberings: multiply P A P^T instead (reorder.cu); the SELL copy then belongs to the inner matrix
+        bool made = false;
+        NGSB_TRY(csr_maybe_reorder(A, &made));
+        if (made) return NGSB_OK;
+    }
     return sell_build(A, h_rowptr);
 }
 
@@ -710,7 +733,7 @@ static int validate_host_csr(size_t h, size_t w, size_t nnz, const uint64_t *row
 
 // take ownership of device CSR arrays (allocated with >= 16 entries of zeroed slack behind nnz)
 int csr_adopt_device(ngsb_ctx *ctx, size_t h, size_t w, size_t nnz, uint64_t *d_rowptr, int32_t *d_col, double *d_val, int kind,
-                     ngsb_csr **out)
+                     ngsb_csr **out, bool allow_reorder)
 {
     NGSB_REQUIRE(ctx && d_rowptr && d_col && d_val && out, "csr_adopt_device: NULL argument");
     NGSB_REQUIRE(w < (1ull << 31) && h < (1ull << 32) - 1024, "csr_adopt_device: dimensions exceed 32-bit indices");
@@ -721,7 +744,7 @@ int csr_adopt_device(ngsb_ctx *ctx, size_t h, size_t w, size_t nnz, uint64_t *d_
     ngsb_csr *A = new ngsb_csr();
     A->ctx = ctx; A->h = h; A->w = w; A->nnz = nnz; A->kind = kind;
     A->d_rowptr = d_rowptr; A->d_col = d_col; A->d_val = d_val;
-    int rc = finish_create(A, h_rowptr.data());
+    int rc = finish_create(A, h_rowptr.data(), allow_reorder);
     if (rc != NGSB_OK) { A->d_rowptr = nullptr; A->d_col = nullptr; A->d_val = nullptr; ngsb_csr_destroy(A); return rc; }
     *out = A;
     return NGSB_OK;
@@ -807,6 +830,8 @@ extern "C" int ngsb_csr_destroy(ngsb_csr *A)
     cudaFree(A->d_longrows);
     sell_free(A);
     if (A->transposed) ngsb_csr_destroy(A->transposed);
+    if (A->inner) ngsb_csr_destroy(A->inner);
+    cudaFree(A->d_perm); cudaFree(A->d_iperm); cudaFree(A->d_row_user); cudaFree(A->d_xperm);
     delete A;
     return NGSB_OK;
 }
@@ -874,7 +899,7 @@ extern "C" int ngsb_csr_multadd_multi(const ngsb_csr *A, size_t nvec, const doub
     }
     NGSB_CUDA(cudaSetDevice(A->ctx->device));
     size_t k = 0;
-    const bool grouped = A->kind == NGSB_REAL && A->novf == 0 && A->ctx->spmv_algo == 0;
+    const bool grouped = A->kind == NGSB_REAL && A->novf == 0 && A->ctx->spmv_algo == 0 && A->inner == nullptr;
     if (grouped)
         for (; k + 4 <= nvec; k += 4) {
             const double *xs[4] = {x[k]->d, x[k + 1]->d, x[k + 2]->d, x[k + 3]->d};
@@ -893,6 +918,7 @@ extern "C" int ngsb_csr_multadd_multi(const ngsb_csr *A, size_t nvec, const doub
 extern "C" int ngsb_csr_download(const ngsb_csr *A, uint64_t *rowptr, int32_t *col, void *val)
 {
     NGSB_REQUIRE(A, "ngsb_csr_download: A is NULL");
+    NGSB_REQUIRE(!A->csr_released, "ngsb_csr_download: the CSR arrays of this matrix were released");
     ngsb_ctx *ctx = A->ctx;
     NGSB_CUDA(cudaSetDevice(ctx->device));
     const size_t ms = kind_matscalars(A->kind);
@@ -906,6 +932,7 @@ extern "C" int ngsb_csr_download(const ngsb_csr *A, uint64_t *rowptr, int32_t *c
 extern "C" int ngsb_csr_layout(const ngsb_csr *A, uint64_t *sell_entries, uint32_t *overflow_rows, uint32_t *cap)
 {
     NGSB_REQUIRE(A, "ngsb_csr_layout: A is NULL");
+    if (A->inner) A = A->inner;
     if (sell_entries) *sell_entries = A->sell_entries;
     if (overflow_rows) *overflow_rows = A->novf;
     if (cap) *cap = A->sell_cap;
@@ -917,11 +944,13 @@ extern "C" int ngsb_csr_layout(const ngsb_csr *A, uint64_t *sell_entries, uint32
 extern "C" int ngsb_csr_stream_bytes(const ngsb_csr *A, double *bytes, uint64_t *c16_entries)
 {
     NGSB_REQUIRE(A && bytes, "ngsb_csr_stream_bytes: NULL argument");
+    const double gather = A->inner ? (double)A->w * (A->kind == NGSB_COMPLEX ? 16.0 : (A->kind == NGSB_BLOCK3 ? 24.0 : 8.0)) * 2.0 : 0.0;   // x' = x[perm]
+    if (A->inner) A = A->inner;
     const double S = A->kind == NGSB_COMPLEX ? 16.0 : 8.0;
     const double b = A->kind == NGSB_BLOCK3 ? 3.0 : 1.0;
     const double per_entry = b * b * S + 4.0;
     const double c16 = (double)A->sell_c16_entries, rest = (double)A->sell_entries - c16;
-    *bytes = c16 * (b * b * S + 2.0 + 4.0 / 32.0) + rest * per_entry + 4.0 * (double)A->h + (double)(A->w + A->h) * b * S;
+    *bytes = c16 * (b * b * S + 2.0 + 4.0 / 32.0) + rest * per_entry + 4.0 * (double)A->h + (double)(A->w + A->h) * b * S + gather;
     if (c16_entries) *c16_entries = A->sell_c16_entries;
     return NGSB_OK;
 }
@@ -933,37 +962,4 @@ extern "C" int ngsb_csr_mult_bytes(const ngsb_csr *A, double *bytes)
     const double b = A->kind == NGSB_BLOCK3 ? 3.0 : 1.0;
     *bytes = (double)A->nnz * (b * b * S + 4.0) + 4.0 * (double)A->h + (double)(A->h + A->w) * b * S;
     return NGSB_OK;
-}
-
-// SparseMatrix::Reorder (linalg/sparsematrix_impl.hpp:762-783): integer/byte work only, done on
-// the host from the downloaded arrays, then uploaded as a new matrix.
-extern "C" int ngsb_csr_reorder(const ngsb_csr *A, const uint64_t *perm, ngsb_csr **out)
-{
-    NGSB_REQUIRE(A && perm && out, "ngsb_csr_reorder: NULL argument");
-    NGSB_REQUIRE(A->h == A->w, "ngsb_csr_reorder: matrix must be square");
-    const size_t n = A->h, ms = kind_matscalars(A->kind);
-    std::vector<uint8_t> seen(n, 0);
-    for (size_t i = 0; i < n; i++) {
-        NGSB_REQUIRE(perm[i] < n && !seen[perm[i]], "ngsb_csr_reorder: perm is not a permutation (entry %zu)", i);
-        seen[perm[i]] = 1;
-    }
-    std::vector<uint64_t> rp(n + 1), nrp(n + 1), inv(n);
-    std::vector<int32_t> col(A->nnz), ncol(A->nnz);
-    std::vector<double> val(A->nnz * ms), nval(A->nnz * ms);
-    NGSB_TRY(ngsb_csr_download(A, rp.data(), col.data(), val.data()));
-    for (size_t i = 0; i < n; i++) inv[perm[i]] = i;
-    nrp[0] = 0;
-    for (size_t i = 0; i < n; i++) nrp[i + 1] = nrp[i] + (rp[perm[i] + 1] - rp[perm[i]]);
-    std::vector<std::pair<int32_t, uint64_t>> tmp;
-    for (size_t i = 0; i < n; i++) {
-        const size_t old = perm[i];
-        tmp.clear();
-        for (uint64_t j = rp[old]; j < rp[old + 1]; j++) tmp.emplace_back((int32_t)inv[col[j]], j);
-        std::sort(tmp.begin(), tmp.end());
-        for (size_t k = 0; k < tmp.size(); k++) {
-            ncol[nrp[i] + k] = tmp[k].first;
-            memcpy(&nval[(nrp[i] + k) * ms], &val[tmp[k].second * ms], ms * sizeof(double));
-        }
-    }
-    return ngsb_csr_create(A->ctx, n, n, A->nnz, nrp.data(), ncol.data(), nval.data(), A->kind, out);
 }

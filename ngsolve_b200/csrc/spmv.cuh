@@ -57,6 +57,15 @@ struct ngsb_csr {
     double mean_row = 0.0;
     size_t max_row = 0;
     ngsb_csr *transposed = nullptr;    // A^T, built by the first MultTransAdd (transpose.cu), owned
+    // internal dof reordering (reorder.cu): products and fused solvers run on inner = P A P^T, which holds only its SELL copy
+    ngsb_csr *inner = nullptr;         // owned; NULL: this matrix is multiplied as numbered by the caller
+    uint32_t *d_perm = nullptr;        // new -> old: row i of inner = row d_perm[i] of this matrix
+    uint32_t *d_iperm = nullptr;       // old -> new
+    uint32_t *d_row_user = nullptr;    // (inner matrices) slot -> row in the CALLER's numbering, for y / the fused dot
+    double *d_xperm = nullptr;         // (inner matrices) x gathered into the permuted numbering for one product
+    bool csr_released = false;         // d_col / d_val were freed (inner matrices)
+    double natural_c16_share = -1.0;   // share of natural slices fit for 16-bit column offsets (automatic reorder criterion)
+    uint64_t uid = 0;                  // unique per created matrix (key of cached CUDA graphs)
 };
 
 namespace ngsb {
@@ -86,6 +95,8 @@ struct SpmvArgs {
     uint32_t nlist;
     const double *dot_add;
     bool skip_overflow;
+    // (inner matrices) y and dotvec are in the caller's numbering: index them through d_row_user instead of d_row_of
+    bool user_rows;
 };
 
 int spmv_launch(const SpmvArgs &a);
@@ -93,6 +104,13 @@ int sell_build(ngsb_csr *A, const uint64_t *h_rowptr);
 void sell_free(ngsb_csr *A);
 int sell_launch(const SpmvArgs &a);
 // y_k += alpha_k * A * x_k for four real vectors in one sweep over the matrix (MultiVector MultAdd)
+// reorder.cu
+int csr_maybe_reorder(ngsb_csr *A, bool *made);
+int launch_perm_gather(ngsb_ctx *ctx, const double *in, const uint32_t *perm, size_t n, int es, double *out);
+// the same for entries of `es` doubles that lie `stride` doubles apart (in and out)
+int launch_perm_gather_strided(ngsb_ctx *ctx, const double *in, const uint32_t *perm, size_t n, int es, int stride, double *out);
+int launch_perm_bits(ngsb_ctx *ctx, const uint8_t *in, const uint32_t *perm, size_t n, uint8_t *out);
+uint64_t next_uid();
 int sell_launch_multi4(const ngsb_csr *A, const double *const x[4], double *const y[4], const double alpha[4]);
 
 } // namespace ngsb

@@ -19,7 +19,7 @@ namespace ngsb {
 
 int device_scan_u64(ngsb_ctx *ctx, uint64_t *d_a, uint64_t n);
 int csr_adopt_device(ngsb_ctx *ctx, size_t h, size_t w, size_t nnz, uint64_t *d_rowptr, int32_t *d_col, double *d_val, int kind,
-                     ngsb_csr **out);
+                     ngsb_csr **out, bool allow_reorder = true);
 
 __global__ void __launch_bounds__(256) iota_u32_kernel(uint32_t *a, uint64_t n)
 {

@@ -875,6 +875,19 @@ class DevSparseMatrix(BaseMatrix):
         check(_capi.lib().ngsb_csr_reorder(self.handle, _np_ptr(p), C.byref(h)))
         return DevSparseMatrix(None, ctx=self.ctx, _handle=h)
 
+    def RCM(self):
+        """the Cuthill-McKee permutation option "reorder" uses (ngsb_csr_rcm), in the form Reorder() takes"""
+        p = np.empty(self.height, dtype=np.uint64)
+        check(_capi.lib().ngsb_csr_rcm(self.handle, _np_ptr(p)))
+        return p
+
+    def ReorderInfo(self, want_perm=False):
+        """(products run on an internally reordered copy?, natural 16-bit-offset share or -1[, permutation])"""
+        r, s = C.c_int(), C.c_double()
+        p = np.empty(self.height, dtype=np.uint64) if want_perm else None
+        check(_capi.lib().ngsb_csr_reorder_info(self.handle, C.byref(r), _np_ptr(p) if want_perm else None, C.byref(s)))
+        return (bool(r.value), s.value, p) if want_perm else (bool(r.value), s.value)
+
     def CSR(self):
         ms = 9 if self.kind == BLOCK3 else 1
         rowptr = np.empty(self.height + 1, dtype=np.uint64)

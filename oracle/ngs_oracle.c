@@ -746,3 +746,117 @@ void orc_csrsym_multadd_d(size_t n, const uint64_t *firsti, const int32_t *colnr
         for (uint64_t j = firsti[i]; j < last; j++) y[colnr[j]] += data[j] * el;
     }
 }
+
+/* ===== Cuthill-McKee dof ordering (own specification, no reference counterpart) =========================
+ * The reference has SparseMatrix::Reorder(perm) (linalg/sparsematrix_impl.hpp:762-783) but computes no bandwidth-reducing
+ * permutation itself; the device library computes one (csrc/reorder.cu) and this is its serial statement, so that the
+ * permutation -- integer work -- can be checked bit for bit.  Graph = the rows' column lists (diagonal ignored).
+ *   degree(i) = min(row length, 2^20 - 1)
+ *   components in the order of their lowest-numbered dof; after `max_components` components the remaining dofs are
+ *     appended in ascending order
+ *   root of a component (George-Liu): r = lowest dof; repeat at most 8 times: x = dof of the last BFS level of r with the
+ *     smallest (degree, index); if the BFS from x has more levels than the one from r, r = x, else stop
+ *   Cuthill-McKee from r: parents in order, the unvisited neighbours of a parent appended sorted by (degree, index)
+ *   perm = the whole sequence reversed; new row k = old row perm[k]  (the argument SparseMatrix::Reorder takes) */
+#define ORC_RCM_DEGCAP ((1u << 20) - 1u)
+static uint32_t rcm_deg(const uint64_t *firsti, size_t i)
+{
+    uint64_t l = firsti[i + 1] - firsti[i];
+    return l > ORC_RCM_DEGCAP ? ORC_RCM_DEGCAP : (uint32_t)l;
+}
+
+/* plain BFS over dofs with tag != placed; returns the number of levels - 1 (eccentricity), fills queue, the last level
+ * is queue[*last_a .. *total) */
+static size_t rcm_bfs(size_t n, const uint64_t *firsti, const int32_t *colnr, const uint8_t *placed, uint32_t *seen, uint32_t stamp,
+                      uint32_t root, uint32_t *queue, size_t *last_a, size_t *total)
+{
+    size_t a = 0, b = 1, ecc = 0;
+    (void)n;
+    queue[0] = root;
+    seen[root] = stamp;
+    for (;;) {
+        size_t e = b;
+        for (size_t q = a; q < b; q++) {
+            uint32_t v = queue[q];
+            for (uint64_t j = firsti[v]; j < firsti[v + 1]; j++) {
+                uint32_t c = (uint32_t)colnr[j];
+                if (c == v || placed[c] || seen[c] == stamp) continue;
+                seen[c] = stamp;
+                queue[e++] = c;
+            }
+        }
+        if (e == b) break;
+        a = b; b = e; ecc++;
+    }
+    *last_a = a; *total = b;
+    return ecc;
+}
+
+typedef struct { uint32_t deg, id; } rcm_child;
+static int rcm_cmp_child(const void *x, const void *y)
+{
+    const rcm_child *a = (const rcm_child *)x, *b = (const rcm_child *)y;
+    if (a->deg != b->deg) return a->deg < b->deg ? -1 : 1;
+    return (a->id > b->id) - (a->id < b->id);
+}
+
+void orc_rcm(size_t n, const uint64_t *firsti, const int32_t *colnr, int max_components, uint64_t *perm)
+{
+    uint8_t *placed = (uint8_t *)calloc(n ? n : 1, 1);
+    uint32_t *seen = (uint32_t *)calloc(n ? n : 1, sizeof(uint32_t));
+    uint32_t *queue = (uint32_t *)malloc((n ? n : 1) * sizeof(uint32_t));
+    uint32_t *order = (uint32_t *)malloc((n ? n : 1) * sizeof(uint32_t));
+    size_t maxdeg = 1;
+    for (size_t i = 0; i < n; i++) if (firsti[i + 1] - firsti[i] > maxdeg) maxdeg = firsti[i + 1] - firsti[i];
+    rcm_child *ch = (rcm_child *)malloc(maxdeg * sizeof(rcm_child));
+    size_t done = 0, scan = 0;
+    uint32_t stamp = 0;
+    int comps = 0;
+    while (done < n) {
+        while (placed[scan]) scan++;
+        if (comps == max_components) {
+            for (size_t i = scan; i < n; i++) if (!placed[i]) order[done++] = (uint32_t)i;
+            break;
+        }
+        uint32_t r = (uint32_t)scan;
+        size_t la, tot;
+        size_t ecc = rcm_bfs(n, firsti, colnr, placed, seen, ++stamp, r, queue, &la, &tot);
+        for (int it = 0; it < 8; it++) {
+            uint32_t x = queue[la];
+            for (size_t q = la; q < tot; q++) {
+                uint32_t c = queue[q], dc = rcm_deg(firsti, c), dx = rcm_deg(firsti, x);
+                if (dc < dx || (dc == dx && c < x)) x = c;
+            }
+            if (x == r) break;
+            uint32_t *q2 = order + done;     /* scratch: the not yet used tail of order */
+            size_t la2, tot2;
+            size_t ecc2 = rcm_bfs(n, firsti, colnr, placed, seen, ++stamp, x, q2, &la2, &tot2);
+            if (ecc2 <= ecc) break;
+            r = x; ecc = ecc2;
+            memcpy(queue, q2, tot2 * sizeof(uint32_t));
+            la = la2; tot = tot2;
+        }
+        /* Cuthill-McKee from r */
+        size_t head = done, tail = done;
+        order[tail++] = r;
+        placed[r] = 1;
+        while (head < tail) {
+            uint32_t v = order[head++];
+            size_t k = 0;
+            for (uint64_t j = firsti[v]; j < firsti[v + 1]; j++) {
+                uint32_t c = (uint32_t)colnr[j];
+                if (c == v || placed[c]) continue;
+                placed[c] = 1;
+                ch[k].deg = rcm_deg(firsti, c);
+                ch[k].id = c;
+                k++;
+            }
+            qsort(ch, k, sizeof(rcm_child), rcm_cmp_child);
+            for (size_t q = 0; q < k; q++) order[tail++] = ch[q].id;
+        }
+        done = tail;
+        comps++;
+    }
+    for (size_t k = 0; k < n; k++) perm[k] = order[n - 1 - k];
+    free(placed); free(seen); free(queue); free(order); free(ch);
+}

@@ -96,6 +96,8 @@ int orc_gmres_solve(int kind, size_t n, const uint64_t *firsti, const int32_t *c
 /* new(i, inv[col]) = old(reorder[i], col); new rows sorted ascending.  kind 0/1/3. */
 void orc_csr_reorder(int kind, size_t n, const uint64_t *firsti, const int32_t *colnr, const void *data,
                      const uint64_t *reorder, uint64_t *nfirsti, int32_t *ncolnr, void *ndata);
+/* Cuthill-McKee ordering of the pattern (own specification, see ngs_oracle.c); perm is Reorder's argument */
+void orc_rcm(size_t n, const uint64_t *firsti, const int32_t *colnr, int max_components, uint64_t *perm);
 
 /* ---- ParallelDofs tables (restated; no MPI here) -------------------------------------- */
 /* dist_procs as CSR table (dp_first[ndof+1], dp_data).  Output: exchangedofs as CSR table

@@ -97,6 +97,12 @@ class Csr:
                               _p(nrp), _p(ncol), _p(nval))
         return Csr(nrp, ncol, nval, self.kind)
 
+    def rcm(self, max_components=64):
+        """the serial Cuthill-McKee specification the device ordering (csrc/reorder.cu) is checked against"""
+        perm = np.empty(self.n, dtype=np.uint64)
+        lib().orc_rcm(C.c_size_t(self.n), _p(self.rowptr), _p(self.col), C.c_int(max_components), _p(perm))
+        return perm
+
 
 def inner(x, y, conjugate=False):
     if np.iscomplexobj(x):

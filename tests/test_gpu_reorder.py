@@ -1,0 +1,191 @@
+"""GPU parity of the dof reordering (csrc/reorder.cu) through the C ABI.
+
+  * ngsb_csr_reorder  == the REFERENCE's SparseMatrix::Reorder (linalg/sparsematrix_impl.hpp:762-783), bit for bit
+  * ngsb_csr_rcm      == the serial Cuthill-McKee specification of the oracle (orc_rcm), bit for bit
+  * option "reorder": products / fused solvers on P A P^T agree with the reference goldens within the north-star
+    tolerances (SpMV 1e-12, CG steps +-2) while the interface keeps the caller's numbering
+"""
+import numpy as np
+import pytest
+
+from conftest import kind_of, load_golden, relerr
+from oracle import pyoracle as orc
+from test_oracle_reorder import _multi_component
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def la():
+    import ngsolve_b200.la as la
+    la.default_context()
+    return la
+
+
+@pytest.fixture()
+def forced(la):
+    ctx = la.default_context()
+    ctx.set_option("reorder", 1)
+    yield ctx
+    ctx.set_option("reorder", -1)
+
+
+def test_reorder_equals_reference(la):
+    g = load_golden("reorder_netgen_h1p3")
+    dev = la.SparseMatrix(g["rowptr"], g["col"], g["val"]).CreateDeviceMatrix()
+    val, col, rowptr = dev.Reorder(g["perm"]).CSR()
+    assert np.array_equal(rowptr, g["r_rowptr"]) and np.array_equal(col, g["r_col"]) and np.array_equal(val, g["r_val"])
+
+
+def test_rcm_equals_serial_specification(la):
+    g = load_golden("reorder_netgen_h1p3")
+    dev = la.SparseMatrix(g["rowptr"], g["col"], g["val"]).CreateDeviceMatrix()
+    assert np.array_equal(dev.RCM(), g["perm"])
+
+
+@pytest.mark.parametrize("name", ["poisson_h1p3", "maxwell_hcurlp2", "helmholtz_h1p4_complex", "elasticity_h1p4_dim3"])
+def test_rcm_on_reference_systems(la, name):
+    g = load_golden(name)
+    k = kind_of(g)
+    dev = la.SparseMatrix(g["rowptr"], g["col"], g["val"], entrysize=3 if k == 3 else 1).CreateDeviceMatrix()
+    ref = orc.Csr(g["rowptr"], g["col"], g["val"], k).rcm()
+    assert np.array_equal(dev.RCM(), ref)
+
+
+def test_rcm_many_components_long_rows(la):
+    rng = np.random.default_rng(5)
+    rowptr, col = _multi_component(rng, [50] * 70 + [3000], isolated=5)       # 76 components > the cutoff of 64
+    # one long row (> 1024 entries: the global-memory ranking path of Reorder) coupling dof 0 of the big block to all of it
+    n = len(rowptr) - 1
+    val = rng.random(len(col))
+    A = orc.Csr(rowptr, col, val, 0)
+    dev = la.SparseMatrix(rowptr, col, val).CreateDeviceMatrix()
+    perm = dev.RCM()
+    assert np.array_equal(perm, A.rcm())
+    v2, c2, r2 = dev.Reorder(perm).CSR()
+    B = A.reorder(perm)
+    assert np.array_equal(r2, B.rowptr) and np.array_equal(c2, B.col) and np.array_equal(v2, B.val)
+
+
+def test_reorder_long_row(la):
+    rng = np.random.default_rng(6)
+    n = 2600
+    rows = [np.arange(n)] + [np.unique(np.concatenate([[0, i], rng.choice(n, 5)])) for i in range(1, n)]
+    rowptr = np.zeros(n + 1, dtype=np.uint64)
+    rowptr[1:] = np.cumsum([len(r) for r in rows])
+    col = np.concatenate(rows).astype(np.int32)
+    val = rng.random(len(col))
+    dev = la.SparseMatrix(rowptr, col, val).CreateDeviceMatrix()
+    perm = rng.permutation(n).astype(np.uint64)
+    v2, c2, r2 = dev.Reorder(perm).CSR()
+    B = orc.Csr(rowptr, col, val, 0).reorder(perm)
+    assert np.array_equal(r2, B.rowptr) and np.array_equal(c2, B.col) and np.array_equal(v2, B.val)
+    assert np.array_equal(dev.RCM(), orc.Csr(rowptr, col, val, 0).rcm())
+
+
+@pytest.mark.parametrize("name", ["poisson_h1p3", "elasticity_h1p4_dim3", "maxwell_hcurlp2", "helmholtz_h1p4_complex"])
+def test_products_on_internally_reordered_matrix(la, forced, name):
+    g = load_golden(name)
+    k = kind_of(g)
+    es = 3 if k == 3 else 1
+    A = la.SparseMatrix(g["rowptr"], g["col"], g["val"], entrysize=es)
+    dev = A.CreateDeviceMatrix()
+    on, share, perm = dev.ReorderInfo(want_perm=True)
+    assert on and np.array_equal(perm, orc.Csr(g["rowptr"], g["col"], g["val"], k).rcm())
+    # the interface keeps the caller's numbering: CSR() is the uploaded matrix
+    val, col, rowptr = dev.CSR()
+    assert np.array_equal(rowptr, g["rowptr"]) and np.array_equal(col, g["col"]) and np.array_equal(val.reshape(-1), np.asarray(g["val"]).reshape(-1))
+    x = la.BaseVector(np.asarray(g["x"]), entrysize=es)
+    y = dev.CreateColVector()
+    dev.Mult(x, y)
+    assert relerr(y.NumPy().reshape(-1), g["y_mult"]) <= 1e-12
+    y = la.BaseVector(np.asarray(g["y0"]), entrysize=es)
+    dev.MultAdd(0.7, x, y)
+    assert relerr(y.NumPy().reshape(-1), g["y_multadd"]) <= 1e-12
+    if k == 1:
+        y = la.BaseVector(np.asarray(g["y0"]), entrysize=es)
+        dev.MultAdd(0.3 - 0.9j, x, y)
+        assert relerr(y.NumPy().reshape(-1), g["y_multadd_cs"]) <= 1e-12
+
+
+@pytest.mark.parametrize("name", ["poisson_h1p3", "elasticity_h1p4_dim3", "maxwell_hcurlp2", "shifted_laplace_complex"])
+def test_cg_on_internally_reordered_matrix(la, forced, name):
+    g = load_golden(name)
+    k = kind_of(g)
+    es = 3 if k == 3 else 1
+    A = la.SparseMatrix(g["rowptr"], g["col"], g["val"], entrysize=es)
+    dev = A.CreateDeviceMatrix()
+    assert dev.ReorderInfo()[0]
+    jac = A.CreateSmoother(la.BitArray(g["freebits"]))
+    f = la.BaseVector(np.asarray(g["f"]), entrysize=es)
+    inv = la.CGSolver(dev, jac, precision=float(g["cg_prec"]), maxsteps=int(g["cg_maxsteps"]), conjugate=False)
+    u = (inv * f).Evaluate()
+    assert abs(inv.GetSteps() - int(g["cg_steps"])) <= 2, (inv.GetSteps(), int(g["cg_steps"]))
+    assert relerr(u.NumPy().reshape(-1), g["cg_u"]) <= 1e-6
+    res = g["pycg_residuals"]
+    m = min(len(res), len(inv.history), 20) - 1
+    assert np.allclose(np.sqrt(inv.history[:m]), res[:m], rtol=1e-6, atol=0)
+    # a start value travels through the permutation as well (initialize = False): one more solve from the solution stops at once
+    u2 = u.CreateVector()
+    u2.data = u
+    inv.Mult(f, u2, initialize=False)
+    assert inv.GetSteps() <= 3
+    assert relerr(u2.NumPy().reshape(-1), g["cg_u"]) <= 1e-6
+    # host-buffer entry
+    uh, steps, _ = la.cg_solve_host(dev, jac, np.asarray(g["f"]), precision=float(g["cg_prec"]), maxsteps=int(g["cg_maxsteps"]),
+                                    conjugate=False)
+    assert abs(steps - int(g["cg_steps"])) <= 2 and relerr(np.asarray(uh).reshape(-1), g["cg_u"]) <= 1e-6
+
+
+@pytest.mark.parametrize("name", ["helmholtz_h1p4_complex", "poisson_h1p3"])
+def test_gmres_on_internally_reordered_matrix(la, forced, name):
+    g = load_golden(name)
+    dev = la.SparseMatrix(g["rowptr"], g["col"], g["val"]).CreateDeviceMatrix()
+    assert dev.ReorderInfo()[0]
+    jac = dev.CreateSmoother(la.BitArray(g["freebits"]))
+    f = la.BaseVector(np.asarray(g["f"]))
+    inv = la.GMRESSolver(dev, jac, precision=float(g["gmres_prec"]), maxsteps=int(g["gmres_maxsteps"]))
+    x = (inv * f).Evaluate()
+    assert abs(inv.GetSteps() - int(g["gmres_steps"])) <= 2, (inv.GetSteps(), int(g["gmres_steps"]))
+    assert relerr(x.NumPy().reshape(-1), g["gmres_u"]) <= 1e-6
+
+
+def test_netgen_numbering_triggers_the_automatic_mode(la):
+    """netgen/NGSolve numbering (entity by entity, refined vertices appended): hardly any natural slice fits 16-bit column
+    offsets -> automatic reordering; the reference's CG on the same system: same steps, same solution."""
+    g = load_golden("reorder_netgen_h1p3")
+    ctx = la.default_context()
+    ctx.set_option("reorder_min_rows", 0)
+    try:
+        A = la.SparseMatrix(g["rowptr"], g["col"], g["val"])
+        dev = A.CreateDeviceMatrix()
+    finally:
+        ctx.set_option("reorder_min_rows", 32768)
+    on, share, perm = dev.ReorderInfo(want_perm=True)
+    # 5 k dofs: every column offset fits 16 bits, so the criterion itself cannot fire at this size; force it for the rest
+    assert 0.0 <= share <= 1.0
+    ctx.set_option("reorder", 1)
+    try:
+        dev = A.CreateDeviceMatrix()
+    finally:
+        ctx.set_option("reorder", -1)
+    on, share, perm = dev.ReorderInfo(want_perm=True)
+    assert on and np.array_equal(perm, g["perm"])
+    x = la.BaseVector(g["x"])
+    y = dev.CreateColVector()
+    dev.Mult(x, y)
+    assert relerr(y.NumPy(), g["y"]) <= 1e-12
+    jac = A.CreateSmoother(la.BitArray(g["freebits"]))
+    inv = la.CGSolver(dev, jac, precision=1e-8, maxsteps=5000)
+    u = (inv * la.BaseVector(g["f"])).Evaluate()
+    assert abs(inv.GetSteps() - int(g["cg_steps"])) <= 2
+    assert relerr(u.NumPy(), g["u"]) <= 1e-6
+
+
+def test_generator_numbering_is_left_alone(la):
+    """the structured generator's lexicographic numbering qualifies for 16-bit offsets almost everywhere: no reordering"""
+    from ngsolve_b200 import workloads
+    ctx = la.default_context()
+    A, f = workloads.FemBox(12, order=3).device_system(ctx)          # 12^3 cubes: 50 653 dofs > reorder_min_rows
+    on, share = A.ReorderInfo()
+    assert not on and share > 0.5
