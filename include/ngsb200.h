@@ -171,7 +171,7 @@ int ngsb_csr_mult(const ngsb_csr *A, const ngsb_vec *x, ngsb_vec *y);
 int ngsb_csr_reorder(const ngsb_csr *A, const uint64_t *perm, ngsb_csr **out);
 /* The bandwidth-reducing permutation option "reorder" uses, in the form Reorder() takes (new row k = old row perm[k]).
  * The reference computes none (its dof numbering is netgen's, comp/h1hofespace.cpp:833-880); this is level-synchronous
- * Cuthill-McKee on the device, specified serially in oracle/ngs_oracle.c (orc_rcm) and equal to it bit for bit. */
+ * Cuthill-McKee on the device; tests/ hold a serial restatement (plain C) that it equals bit for bit. */
 int ngsb_csr_rcm(const ngsb_csr *A, uint64_t *perm);
 /* whether products of A run on an internally reordered copy, its permutation (perm may be NULL), and the share of natural
  * 32-row slices fit for 16-bit column offsets that the automatic mode looked at (-1: not evaluated) */

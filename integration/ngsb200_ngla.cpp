@@ -10,9 +10,12 @@
 //   fdev = f.vec.CreateDeviceVector(); adev = a.mat.CreateDeviceMatrix(); jdev = jac.CreateDeviceMatrix()
 //   inv = CGSolver(adev, jdev, maxsteps=2000); res = (inv * fdev).Evaluate()
 //
-// NOT compiled in this repository's CI: NGSolve itself is not available on the GPU box.
+// Compiled by integration/build_adapter.sh against the reference build (oracle/_ref/ngs, which travels to the GPU box) and
+// exercised by tests/test_gpu_dropin.py: an unchanged NGSolve script, the reference's own python/krylovspace.py solvers and the
+// C++ CGSolver / GMRESSolver factories all run on this layer.
 #include <la.hpp>
 #include <pybind11/pybind11.h>
+#include <pybind11/stl.h>
 
 #include "ngsb200.h"
 
@@ -66,6 +69,53 @@ namespace ngla
     mutable Array<SCAL> host;
     mutable bool host_uptodate = false, dev_uptodate = true;
     shared_ptr<BaseVector> parent;   // keeps the storage of a Range() view alive
+    // Range() views alias the parent's DEVICE storage but have a host mirror of their own (the reference's
+    // UnifiedVectorWrapper does the same and keeps the two coherent by UpdateDevice + InvalidateHost of the wrapped vector,
+    // ngscuda/unifiedvector.cpp:376-377).  Here a parent knows its live views and a view its parent, and every access
+    // keeps the aliases coherent in both directions:
+    //   before an object touches the device copy, pending host writes of its aliases are flushed (in program order);
+    //   a device write through one alias invalidates the host mirrors of the others.
+    mutable std::vector<const B200Vector*> views;
+    const B200Vector * vparent = nullptr;
+
+    void FlushOwn () const
+    {
+      if (dev_uptodate) return;
+      Check (ngsb_vec_h2d (dev, host.Data(), 0, this->size));
+      dev_uptodate = true;
+    }
+    template <typename F> void Ancestors (F f) const
+    {
+      std::vector<const B200Vector*> chain;
+      for (auto p = vparent; p; p = p->vparent) chain.push_back (p);
+      for (auto it = chain.rbegin(); it != chain.rend(); ++it) f (*it);          // root first
+    }
+    template <typename F> void Descendants (F f) const { for (auto v : views) { f (v); v->Descendants (f); } }
+    // pending host writes reach the device in program order: ancestors (older), this object, its views
+    void FlushAll (bool own) const
+    {
+      Ancestors ([] (auto p) { p->FlushOwn(); });
+      if (own) FlushOwn ();
+      Descendants ([] (auto v) { v->FlushOwn(); });
+    }
+    void InvalidateOthersHost () const
+    {
+      Ancestors ([] (auto p) { p->host_uptodate = false; });
+      Descendants ([] (auto v) { v->host_uptodate = false; });
+    }
+    // coherent host memory that the caller may write (FVDouble / FVComplex / Memory)
+    void HostAccess () const
+    {
+      if (host.Size() != this->size * size_t(EntryScalars())) host.SetSize (this->size * EntryScalars());
+      FlushAll (false);
+      if (!host_uptodate)
+        {
+          Check (ngsb_vec_d2h (dev, host.Data(), 0, this->size));
+          host_uptodate = true;
+        }
+      InvalidateOthersHost ();
+      dev_uptodate = false;
+    }
   public:
     B200Vector (size_t asize, int aes = 1)
     {
@@ -73,36 +123,33 @@ namespace ngla
       Check (ngsb_vec_create (TheCtx(), asize, KindOf<SCAL>(aes), &dev));
     }
     B200Vector (const BaseVector & v) : B200Vector (v.Size(), v.EntrySize() / (v.IsComplex() ? 2 : 1)) { *this = v; }
-    B200Vector (ngsb_vec * view, size_t asize, int aes, shared_ptr<BaseVector> aparent) : dev(view), parent(aparent)
-    { this->size = asize; this->entrysize = aes; }
-    ~B200Vector () { ngsb_vec_destroy (dev); }
+    B200Vector (ngsb_vec * view, size_t asize, int aes, shared_ptr<BaseVector> aparent, const B200Vector * avparent)
+      : dev(view), parent(aparent), vparent(avparent)
+    { this->size = asize; this->entrysize = aes; vparent->views.push_back (this); }
+    ~B200Vector ()
+    {
+      if (vparent)
+        {
+          try { FlushAll (true); } catch (...) { }       // a dying view must not lose its host writes
+          auto & l = vparent->views;
+          l.erase (std::remove (l.begin(), l.end(), this), l.end());
+        }
+      ngsb_vec_destroy (dev);
+    }
 
-    ngsb_vec * Dev () const { UpdateDevice(); return dev; }
-    ngsb_vec * DevW () { UpdateDevice(); host_uptodate = false; return dev; }
-    void UpdateDevice () const
-    {
-      if (dev_uptodate) return;
-      Check (ngsb_vec_h2d (dev, host.Data(), 0, this->size));
-      dev_uptodate = true;
-    }
-    void UpdateHost () const
-    {
-      if (host.Size() != this->size * size_t(EntryScalars())) host.SetSize (this->size * EntryScalars());
-      if (host_uptodate) return;
-      UpdateDevice ();
-      Check (ngsb_vec_d2h (dev, host.Data(), 0, this->size));
-      host_uptodate = true;
-    }
+    ngsb_vec * Dev () const { FlushAll (true); return dev; }
+    ngsb_vec * DevW () { FlushAll (true); host_uptodate = false; InvalidateOthersHost(); return dev; }
+    void UpdateDevice () const { FlushAll (true); }
     int EntryScalars () const { return this->entrysize / (std::is_same_v<SCAL,Complex> ? 2 : 1); }
 
     // host access: FVDouble()/FVComplex()/Memory() must hand out coherent host memory
-    void * Memory () const throw () override { UpdateHost(); dev_uptodate = false; return host.Data(); }
+    void * Memory () const throw () override { HostAccess(); return host.Data(); }
     FlatVector<double> FVDouble () const override
-    { UpdateHost(); dev_uptodate = false; return FlatVector<double> (this->size * this->entrysize, (double*)host.Data()); }
+    { HostAccess(); return FlatVector<double> (this->size * this->entrysize, (double*)host.Data()); }
     FlatVector<Complex> FVComplex () const override
     {
       if constexpr (!std::is_same_v<SCAL,Complex>) throw Exception ("FVComplex called for real B200Vector");
-      UpdateHost(); dev_uptodate = false; return FlatVector<Complex> (this->size * EntryScalars(), (Complex*)host.Data());
+      HostAccess(); return FlatVector<Complex> (this->size * EntryScalars(), (Complex*)host.Data());
     }
 
     // a read-only operand: a device vector as it is, a host vector through a temporary upload (what
@@ -132,7 +179,7 @@ namespace ngla
       return *p;
     }
 
-    BaseVector & SetScalar (double s) override { double z[2] = {s,0}; host_uptodate = false; dev_uptodate = true; Check (ngsb_vec_set_scalar (dev, z)); return *this; }
+    BaseVector & SetScalar (double s) override { double z[2] = {s,0}; dev_uptodate = true; Check (ngsb_vec_set_scalar (DevW(), z)); return *this; }
     BaseVector & Scale (double s) override { double z[2] = {s,0}; Check (ngsb_vec_scale (DevW(), z)); return *this; }
     BaseVector & Scale (Complex s) override { double z[2] = {s.real(),s.imag()}; Check (ngsb_vec_scale (DevW(), z)); return *this; }
     BaseVector & Set (double s, const BaseVector & v) override { double z[2] = {s,0}; Check (ngsb_vec_set (DevW(), z, Cast(v).Dev())); return *this; }
@@ -155,15 +202,15 @@ namespace ngla
     AutoVector CreateVector () const override { return make_unique<B200Vector<SCAL>> (this->size, EntryScalars()); }
     AutoVector Range (T_Range<size_t> r) const override
     {
-      ngsb_vec * view; Check (ngsb_vec_range (Dev(), r.First(), r.Next(), &view));
+      ngsb_vec * view; Check (ngsb_vec_range (Dev(), r.First(), r.Next(), &view));     // Dev(): the device copy is current
       return make_unique<B200Vector<SCAL>> (view, r.Size(), this->entrysize,
-                                            const_cast<B200Vector*>(this)->shared_from_this());
+                                            const_cast<B200Vector*>(this)->shared_from_this(), this);
     }
     BaseVector & operator= (const BaseVector & v)
     {
       if (auto p = dynamic_cast<const B200Vector*> (&v)) return Set (1.0, *p);
-      Check (ngsb_vec_h2d (dev, v.Memory(), 0, this->size));      // host vector -> device (H2D)
-      host_uptodate = false; dev_uptodate = true;
+      dev_uptodate = true;                                        // whatever the host mirror held is overwritten as a whole
+      Check (ngsb_vec_h2d (DevW(), v.Memory(), 0, this->size));   // host vector -> device (H2D)
       return *this;
     }
   };
@@ -276,29 +323,104 @@ namespace ngla
     { Check (ngsb_blockjacobi_mult (J, B200Vector<double>::Cast(x).Dev(), B200Vector<double>::CastW(y).DevW(), 0)); }
   };
 
-  // ---- fused device CG: same interface as DevCGSolver (ngscuda/cuda_linalg.hpp:289-310) ----------------
-  class B200CGSolver : public BaseMatrix
+  // ---- fused Krylov solvers behind the UNCHANGED factories ----------------------------------------------
+  // `CGSolver(mat, pre, ...)` / `GMRESSolver(mat, pre, ...)` (linalg/python_linalg.cpp:1773-1830) construct the C++ classes of
+  // linalg/cg.hpp, whose Mult drives the operands op by op through virtual calls -- on device operands that is 10+ kernel
+  // launches and two host round trips per iteration.  The classes below ARE those solvers (same base class, same accessors,
+  // same stopping rule) with Mult replaced by the device-resident loop of the library whenever both operands are objects of
+  // this layer the fused loop understands: SparseMatrix<double | Complex | Mat<3,3>> with a JacobiPrecond of the same entry
+  // type or no preconditioner.  Anything else (block Jacobi, composite operators, absolute tolerance) runs the inherited
+  // reference loop on the device vectors -- never a silently different preconditioner.
+  struct Fused { ngsb_csr * A = nullptr; ngsb_jacobi * C = nullptr; bool ok = false; };
+  template <typename TM> static bool TryFuse (const BaseMatrix * a, const BaseMatrix * c, Fused & f)
   {
-    shared_ptr<BaseMatrix> a, c;
-    int maxsteps; double prec; mutable int steps = 0;
+    auto A = dynamic_cast<const B200SparseMatrix<TM>*> (a);
+    if (!A) return false;
+    if (c)
+      {
+        auto C = dynamic_cast<const B200Jacobi<TM>*> (c);
+        if (!C) return false;
+        f.C = C->Handle();
+      }
+    f.A = A->Handle(); f.ok = true;
+    return true;
+  }
+  static Fused Fuse (const BaseMatrix * a, const BaseMatrix * c)
+  {
+    Fused f;
+    if (!a) return f;
+    if (!TryFuse<double> (a, c, f) && !TryFuse<Complex> (a, c, f)) TryFuse<Mat<3,3,double>> (a, c, f);
+    return f;
+  }
+  static bool IsB200Operator (const BaseMatrix * a)
+  {
+    return dynamic_cast<const B200SparseMatrix<double>*> (a) || dynamic_cast<const B200SparseMatrix<Complex>*> (a)
+      || dynamic_cast<const B200SparseMatrix<Mat<3,3,double>>*> (a);
+  }
+
+  template <class IPTYPE>
+  class B200CG : public CGSolver<IPTYPE>
+  {
+    using SCAL = typename SCAL_TRAIT<IPTYPE>::SCAL;
+    mutable bool last_fused = false;
   public:
-    B200CGSolver (shared_ptr<BaseMatrix> aa, shared_ptr<BaseMatrix> ac, int amaxsteps, double aprec)
-      : a(aa), c(ac), maxsteps(amaxsteps), prec(aprec) { }
-    int VHeight () const override { return a->VWidth(); }
-    int VWidth () const override { return a->VHeight(); }
-    int GetSteps () const { return steps; }
-    AutoVector CreateRowVector () const override { return a->CreateColVector(); }
-    AutoVector CreateColVector () const override { return a->CreateRowVector(); }
+    using CGSolver<IPTYPE>::CGSolver;
+    bool LastFused () const { return last_fused; }
     void Mult (const BaseVector & f, BaseVector & u) const override
     {
-      auto A = dynamic_cast<const B200SparseMatrix<double>*> (a.get());
-      auto C = dynamic_cast<const B200Jacobi<double>*> (c.get());
-      if (!A) throw Exception ("B200CGSolver: matrix is not a B200SparseMatrix<double>");
-      Check (ngsb_cg_solve (A->Handle(), C ? C->Handle() : nullptr, B200Vector<double>::Cast(f).Dev(),
-                            B200Vector<double>::CastW(u).DevW(), prec, maxsteps,
-                            NGSB_IP_REAL, 1, &steps, nullptr, 0, nullptr));
+      Fused fu = Fuse (this->a.get(), this->c.get());
+      last_fused = fu.ok && !this->stop_absolute && !this->useseed;
+      if (!last_fused) { CGSolver<IPTYPE>::Mult (f, u); return; }
+      constexpr int ip = std::is_same_v<IPTYPE,double> ? NGSB_IP_REAL : (std::is_same_v<IPTYPE,ComplexConjugate> ? NGSB_IP_COMPLEX_CONJ : NGSB_IP_COMPLEX);
+      std::vector<double> hist (this->printrates ? this->maxsteps + 2 : 0);
+      int nh = 0;
+      Check (ngsb_cg_solve (fu.A, fu.C, B200Vector<SCAL>::Cast(f).Dev(), B200Vector<SCAL>::CastW(u).DevW(), this->prec, this->maxsteps,
+                            ip, this->initialize, &this->steps, hist.data(), int(hist.size()), &nh));
+      if (this->printrates)      // the reference prints every step as it goes (linalg/cg.cpp:619-620); here after the fact
+        for (int k = 0; k < std::min<int> (nh, hist.size()); k++)
+          cout << IM(1) << k << " " << sqrt (hist[k]) << endl;
     }
   };
+
+  template <class IPTYPE>
+  class B200GMRES : public GMRESSolver<IPTYPE>
+  {
+    using SCAL = typename SCAL_TRAIT<IPTYPE>::SCAL;
+    mutable bool last_fused = false;
+  public:
+    using GMRESSolver<IPTYPE>::GMRESSolver;
+    bool LastFused () const { return last_fused; }
+    void Mult (const BaseVector & f, BaseVector & u) const override
+    {
+      Fused fu = Fuse (this->a.get(), this->c.get());
+      last_fused = fu.ok && !this->stop_absolute;
+      if (!last_fused) { GMRESSolver<IPTYPE>::Mult (f, u); return; }
+      Check (ngsb_gmres_solve (fu.A, fu.C, B200Vector<SCAL>::Cast(f).Dev(), B200Vector<SCAL>::CastW(u).DevW(), this->prec, this->maxsteps,
+                               this->initialize, &this->steps, nullptr, 0, nullptr));
+    }
+  };
+
+  static shared_ptr<KrylovSpaceSolver> MakeCG (shared_ptr<BaseMatrix> mat, shared_ptr<BaseMatrix> pre, bool iscomplex, bool conjugate)
+  {
+    if (mat->IsComplex()) iscomplex = true;
+    if (!iscomplex) return make_shared<B200CG<double>> (mat, pre);
+    if (conjugate) return make_shared<B200CG<ComplexConjugate>> (mat, pre);
+    return make_shared<B200CG<Complex>> (mat, pre);
+  }
+  static shared_ptr<KrylovSpaceSolver> MakeGMRES (shared_ptr<BaseMatrix> mat, shared_ptr<BaseMatrix> pre)
+  {
+    if (!mat->IsComplex()) return make_shared<B200GMRES<double>> (mat, pre);
+    return make_shared<B200GMRES<Complex>> (mat, pre);
+  }
+  static bool WasFused (const KrylovSpaceSolver & s)
+  {
+    if (auto p = dynamic_cast<const B200CG<double>*> (&s)) return p->LastFused();
+    if (auto p = dynamic_cast<const B200CG<Complex>*> (&s)) return p->LastFused();
+    if (auto p = dynamic_cast<const B200CG<ComplexConjugate>*> (&s)) return p->LastFused();
+    if (auto p = dynamic_cast<const B200GMRES<double>*> (&s)) return p->LastFused();
+    if (auto p = dynamic_cast<const B200GMRES<Complex>*> (&s)) return p->LastFused();
+    return false;
+  }
 
   template <typename TM> static void RegisterFor ()
   {
@@ -333,9 +455,61 @@ namespace ngla
 PYBIND11_MODULE(_ngsb200, m)
 {
   namespace py = pybind11;
-  ngla::InitNgsB200 ();        // registration at import, like _ngscuda
-  py::class_<ngla::B200CGSolver, std::shared_ptr<ngla::B200CGSolver>, ngla::BaseMatrix> (m, "DevCGSolver")
-    .def (py::init<std::shared_ptr<ngla::BaseMatrix>, std::shared_ptr<ngla::BaseMatrix>, int, double> (),
-          py::arg("mat"), py::arg("pre"), py::arg("maxsteps") = 200, py::arg("precision") = 1e-8)
-    .def ("GetSteps", &ngla::B200CGSolver::GetSteps);
+  using namespace ngla;
+  py::module_ la = py::module_::import ("ngsolve.la");    // BaseMatrix / KrylovSpaceSolver are registered there
+  InitNgsB200 ();                                         // registration at import, like _ngscuda (ngscuda/python_ngscuda.cpp:20-25)
+
+  // The factories scripts already call.  An overload PREPENDED to the existing function object: every name bound to it
+  // (`ngsolve.CGSolver`, `ngsolve.la.CGSolver`, a script's `from ngsolve import *`) dispatches here first; for operands that
+  // are not device matrices of this layer the overload steps aside (reference_cast_error = "try the next overload") and
+  // the reference's own factory runs, unchanged.
+  la.def ("CGSolver", [] (shared_ptr<BaseMatrix> mat, shared_ptr<BaseMatrix> pre, bool iscomplex, bool printrates, double precision,
+                          int maxsteps, bool conjugate, std::optional<int> maxiter) -> shared_ptr<KrylovSpaceSolver>
+          {
+            if (!mat || !IsB200Operator (mat.get())) throw py::reference_cast_error ();
+            if (maxiter) maxsteps = *maxiter;
+            auto solver = MakeCG (mat, pre, iscomplex, conjugate);
+            solver->SetPrecision (precision);
+            solver->SetMaxSteps (maxsteps);
+            solver->SetPrintRates (printrates);
+            return solver;
+          },
+          py::arg("mat"), py::arg("pre"), py::arg("complex") = false, py::arg("printrates") = true, py::arg("precision") = 1e-8,
+          py::arg("maxsteps") = 200, py::arg("conjugate") = false, py::arg("maxiter") = py::none(), py::prepend ());
+  la.def ("GMRESSolver", [] (shared_ptr<BaseMatrix> mat, shared_ptr<BaseMatrix> pre, bool printrates, double precision, int maxsteps)
+          -> shared_ptr<KrylovSpaceSolver>
+          {
+            if (!mat || !IsB200Operator (mat.get())) throw py::reference_cast_error ();
+            auto solver = MakeGMRES (mat, pre);
+            solver->SetPrecision (precision);
+            solver->SetMaxSteps (maxsteps);
+            solver->SetPrintRates (printrates);
+            return solver;
+          },
+          py::arg("mat"), py::arg("pre"), py::arg("printrates") = true, py::arg("precision") = 1e-8, py::arg("maxsteps") = 200,
+          py::prepend ());
+  // same call as ngscuda.DevCGSolver(mat, pre, ..., precision, maxsteps) (ngscuda/python_ngscuda.cpp:243-266)
+  m.def ("DevCGSolver", [] (shared_ptr<BaseMatrix> mat, shared_ptr<BaseMatrix> pre, int maxsteps, double precision, bool printrates)
+         {
+           auto solver = MakeCG (mat, pre, false, false);
+           solver->SetPrecision (precision);
+           solver->SetMaxSteps (maxsteps);
+           solver->SetPrintRates (printrates);
+           return solver;
+         }, py::arg("mat"), py::arg("pre"), py::arg("maxsteps") = 200, py::arg("precision") = 1e-8, py::arg("printrates") = false);
+  // did the last Mult of this solver run the fused device loop (diagnostics for tests)
+  m.def ("WasFused", [] (shared_ptr<KrylovSpaceSolver> s) { return WasFused (*s); });
+  m.def ("SetOption", [] (std::string name, long value) { Check (ngsb_ctx_set_option (TheCtx(), name.c_str(), value)); });
+  m.def ("LaunchCount", [] () { uint64_t n = 0; Check (ngsb_ctx_launch_count (TheCtx(), &n)); return n; });
+  m.def ("ReorderInfo", [] (shared_ptr<BaseMatrix> mat)
+         {
+           int on = 0; double share = -1;
+           ngsb_csr * h = nullptr;
+           if (auto p = dynamic_cast<B200SparseMatrix<double>*> (mat.get())) h = p->Handle();
+           else if (auto p = dynamic_cast<B200SparseMatrix<Complex>*> (mat.get())) h = p->Handle();
+           else if (auto p = dynamic_cast<B200SparseMatrix<Mat<3,3,double>>*> (mat.get())) h = p->Handle();
+           if (!h) throw Exception ("ReorderInfo: not a device sparse matrix of this layer");
+           Check (ngsb_csr_reorder_info (h, &on, nullptr, &share));
+           return py::make_tuple (bool(on), share);
+         });
 }

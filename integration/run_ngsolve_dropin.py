@@ -25,11 +25,14 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--maxh", type=float, default=0.05)
 ap.add_argument("--order", type=int, default=3)
 ap.add_argument("--threads", type=int, default=0)
+ap.add_argument("--reorder", type=int, default=None, help="library option reorder (-1 automatic, 0 off, 1 always)")
 args = ap.parse_args()
 ngsolve.ngsglobals.msg_level = 0
 SetNumThreads(args.threads or os.cpu_count())
 
 import _ngsb200               # registers the device creators (BaseMatrix::RegisterDeviceMatrixCreator, ...)
+if args.reorder is not None:
+    _ngsb200.SetOption("reorder", args.reorder)
 
 out = {"ngsolve": ngsolve.__version__, "maxh": args.maxh, "order": args.order, "threads": args.threads or os.cpu_count()}
 with TaskManager():
@@ -56,16 +59,61 @@ with TaskManager():
     fdev = f.vec.CreateDeviceVector()
     out.update(upload_s=time.perf_counter() - t0, types=[type(adev).__name__, type(jdev).__name__, type(fdev).__name__],
                is_host_object=[adev is a.mat, jdev is jac])
-    invdev = CGSolver(adev, jdev, precision=1e-8, maxsteps=20000, printrates=False)        # NGSolve's C++ CG loop, every op a virtual call into libngsb200
+    # the unchanged script line.  With `_ngsb200` imported the factory hands back the same KrylovSpaceSolver interface whose
+    # Mult is the library's device-resident loop (integration/ngsb200_ngla.cpp, B200CG)
+    invdev = CGSolver(adev, jdev, precision=1e-8, maxsteps=20000, printrates=False)
     res = (invdev * fdev).Evaluate()
     t0 = time.perf_counter()
     res = (invdev * fdev).Evaluate()
-    out.update(dev_steps=invdev.GetSteps(), dev_solve_s=time.perf_counter() - t0)
+    out.update(dev_steps=invdev.GetSteps(), dev_solve_s=time.perf_counter() - t0, dev_fused=_ngsb200.WasFused(invdev),
+               dev_solver_type=type(invdev).__name__, reorder_info=list(_ngsb200.ReorderInfo(adev)))
+    # a host matrix still gets the reference's own solver from the same factory
+    out.update(host_factory_type=type(inv).__name__, host_factory_fused=_ngsb200.WasFused(inv))
     gfu2 = GridFunction(fes)
     gfu2.vec.data = res
     diff = gfu.vec.CreateVector()
     diff.data = gfu.vec - gfu2.vec
     out.update(rel_diff=Norm(diff) / Norm(gfu.vec))
+
+    # ---- the reference's OWN python solvers (python/krylovspace.py:263-290, 988-1095), unmodified, on the device objects:
+    # every `vec.data = expr`, InnerProduct and Norm goes through the adapter's BaseVector / BaseMatrix virtuals
+    from ngsolve.krylovspace import CGSolver as PyCGSolver, GMResSolver as PyGMResSolver
+    pinv = PyCGSolver(mat=adev, pre=jdev, tol=1e-8, maxiter=20000, printrates=False)
+    t0 = time.perf_counter()
+    pres = pinv.Solve(rhs=fdev)
+    out.update(pycg_iterations=pinv.iterations, pycg_solve_s=time.perf_counter() - t0)
+    gfu2 = GridFunction(fes)
+    gfu2.vec.data = pres
+    diff = gfu.vec.CreateVector()
+    diff.data = gfu.vec - gfu2.vec
+    out.update(pycg_rel_diff=Norm(diff) / Norm(gfu.vec))
+    pinv_host = PyCGSolver(mat=a.mat, pre=jac, tol=1e-8, maxiter=20000, printrates=False)
+    pinv_host.Solve(rhs=f.vec)
+    out.update(pycg_host_iterations=pinv_host.iterations)
+    pg = PyGMResSolver(mat=adev, pre=jdev, tol=1e-8, maxiter=400, printrates=False)
+    gres = pg.Solve(rhs=fdev)
+    pgh = PyGMResSolver(mat=a.mat, pre=jac, tol=1e-8, maxiter=400, printrates=False)
+    gres_h = pgh.Solve(rhs=f.vec)
+    gfu2.vec.data = gres
+    diff.data = gres_h - gfu2.vec
+    out.update(pygmres_iterations=pg.iterations, pygmres_host_iterations=pgh.iterations, pygmres_rel_diff=Norm(diff) / Norm(gres_h))
+
+    # ---- host/device coherence of Range() views in both directions (ngscuda/unifiedvector.cpp:363-405)
+    vv = fdev.CreateVector()
+    vv.data = fdev
+    half = fes.ndof // 2
+    view = vv.Range(0, half)
+    view.data = 2.0 * view                               # device write through the view ...
+    h = vv.FV().NumPy()
+    ref = f.vec.FV().NumPy()
+    ok1 = bool(abs(h[:half] - 2 * ref[:half]).max() == 0 and abs(h[half:] - ref[half:]).max() == 0)   # ... seen by the parent's host side
+    vv.FV().NumPy()[:] = 1.0                             # host write to the parent ...
+    ok2 = bool(abs(Norm(view) ** 2 - half) < 1e-9 * half)   # ... seen by a device read through the view
+    view.FV().NumPy()[:] = 3.0                           # host write through the view ...
+    ok3 = bool(abs(InnerProduct(vv, vv) - (9.0 * half + (fes.ndof - half))) < 1e-9 * fes.ndof)   # ... seen by the parent on the device
+    vv.data = 5.0 * vv                                   # device write to the parent ...
+    ok4 = bool(abs(view.FV().NumPy() - 15.0).max() == 0)    # ... seen by the view's host side
+    out.update(range_coherence=[ok1, ok2, ok3, ok4])
 
     # ---- fused device solver (same interface as ngscuda.DevCGSolver)
     fused = _ngsb200.DevCGSolver(adev, jdev, maxsteps=20000, precision=1e-8)
@@ -88,7 +136,8 @@ with TaskManager():
     res4 = (invbd * fdev).Evaluate()
     t0 = time.perf_counter()
     res4 = (invbd * fdev).Evaluate()
-    out.update(bj_dev_steps=invbd.GetSteps(), bj_dev_solve_s=time.perf_counter() - t0, bj_type=type(bjdev).__name__)
+    out.update(bj_dev_steps=invbd.GetSteps(), bj_dev_solve_s=time.perf_counter() - t0, bj_type=type(bjdev).__name__,
+               bj_fused=_ngsb200.WasFused(invbd))     # False: block Jacobi runs the inherited reference loop, op by op on the device
     gfu2.vec.data = res4
     diff.data = gfu.vec - gfu2.vec
     out.update(bj_rel_diff=Norm(diff) / Norm(gfu.vec))
@@ -136,6 +185,7 @@ with TaskManager():
         ad, jd, fd = aa.mat.CreateDeviceMatrix(), jj.CreateDeviceMatrix(), ff.vec.CreateDeviceVector()
         idv = CGSolver(ad, jd, precision=1e-8, maxsteps=20000, printrates=False)
         r = (idv * fd).Evaluate()
+        out.update(b3_fused=_ngsb200.WasFused(idv))
         g2 = GridFunction(fe)
         g2.vec.data = r
         dd = g1.vec.CreateVector()
@@ -157,6 +207,7 @@ with TaskManager():
         ad, jd, fd = aa.mat.CreateDeviceMatrix(), jj.CreateDeviceMatrix(), ff.vec.CreateDeviceVector()
         idv = GMRESSolver(ad, jd, printrates=False, precision=1e-8, maxsteps=400)
         r = (idv * fd).Evaluate()
+        out.update(z_fused=_ngsb200.WasFused(idv))
         g2 = GridFunction(fe)
         g2.vec.data = r
         dd = g1.vec.CreateVector()

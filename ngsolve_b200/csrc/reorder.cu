@@ -8,7 +8,7 @@
 //    so a row's columns are spread over the whole vector: mean |i-j| = 0.29 n.  The SpMV then fetches x
 //    lines from HBM many times and the 16-bit column compression never applies.  After Cuthill-McKee the gathers of the
 //    resident slices fall into a window of O(n^(2/3)) entries that lives in L2.
-//    The ordering is specified serially in oracle/ngs_oracle.c (orc_rcm) and reproduced here bit for bit:
+//    The ordering has a serial specification (the test suite holds it in plain C) that is reproduced here bit for bit:
 //      degree(i) = min(row length, 2^20-1); components by lowest dof, at most `max_components`, the rest appended ascending;
 //      root by George-Liu (<= 8 trial BFS); level k+1 sorted by (position of the first parent, degree, index); reversed.
 //    One BFS level = one expand kernel (warp per frontier dof, atomicMax stamps, atomicMin of the parent position) + two

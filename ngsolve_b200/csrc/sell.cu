@@ -767,44 +767,27 @@ int sell_build(ngsb_csr *A, const uint64_t *h_rowptr)
     const uint64_t nslots = (uint64_t)ns * 32;
     A->nslices = ns;
     // rows longer than cap keep their tail in the overflow CSR
-    uint32_t cap = (uint32_t)std::max<double>(64.0, 4.0 * A->mean_row + 0.5);
-    if (ctx->sell_cap > 0) cap = (uint32_t)ctx->sell_cap;
-    cap = (cap + 1u) & ~1u;
-    if (ctx->sell_cap <= 0) {
-        // Rows of one slice have similar lengths in an FE numbering (entity by entity), so long rows sit in slices of long
-        // rows and cost no padding: when the slices padded to their own longest row stay within 5 % of nnz, no row needs the
-        // overflow path at all (order-4 systems have 1-2 % vertex rows above 4 x mean: 439 k single-row CTAs per product)
-        uint64_t full = 0;
-        for (size_t r0 = 0; r0 < A->h; r0 += 32) {
-            uint64_t w = 0;
-            for (size_t r = r0; r < std::min<size_t>(A->h, r0 + 32); r++) w = std::max<uint64_t>(w, h_rowptr[r + 1] - h_rowptr[r]);
-            full += 32 * ((w + 1) & ~(uint64_t)1);
-        }
-        if ((double)full <= 1.05 * (double)std::max<size_t>(1, A->nnz) && A->max_row < (1u << 20))
-            cap = std::max<uint32_t>(cap, (uint32_t)((A->max_row + 1) & ~(size_t)1));
-    }
-    A->sell_cap = cap;
-    uint32_t novf = 0;
-    uint64_t natural_entries = 0;      // padded size of the natural (unsorted) slices
+    uint32_t cap0 = (uint32_t)std::max<double>(64.0, 4.0 * A->mean_row + 0.5);
+    if (ctx->sell_cap > 0) cap0 = (uint32_t)ctx->sell_cap;
+    cap0 = (cap0 + 1u) & ~1u;
+    const uint32_t cap_full = (uint32_t)((std::min<size_t>(A->max_row, (1u << 20)) + 1) & ~(size_t)1);
+    // padded size of the natural (unsorted) slices when no row is cut: rows of one slice have similar lengths in an FE
+    // numbering (entity by entity), so long rows sit in slices of long rows and cost no padding.  Where that holds
+    // (structured numberings) the slices stay in natural order and no row needs the overflow path.
+    uint64_t full = 0;
     for (size_t r0 = 0; r0 < A->h; r0 += 32) {
         uint64_t w = 0;
-        for (size_t r = r0; r < std::min<size_t>(A->h, r0 + 32); r++) {
-            const uint64_t len = h_rowptr[r + 1] - h_rowptr[r];
-            if (len > cap) novf++;
-            w = std::max<uint64_t>(w, std::min<uint64_t>(len, cap));
-        }
-        natural_entries += 32 * w;
+        for (size_t r = r0; r < std::min<size_t>(A->h, r0 + 32); r++) w = std::max<uint64_t>(w, h_rowptr[r + 1] - h_rowptr[r]);
+        full += 32 * ((w + 1) & ~(uint64_t)1);
     }
-    A->novf = novf;
-    // sigma-sorting pays when neighbouring rows differ in length (unstructured meshes: 30-60 % padding);
-    // where the natural slices are already tight (structured numberings) it only scatters the y writes (-5 %)
-    const bool tight = (double)natural_entries <= 1.05 * (double)std::max<size_t>(1, A->nnz);
+    const bool tight = ctx->sell_cap <= 0 && (double)full <= 1.05 * (double)std::max<size_t>(1, A->nnz) && A->max_row < (1u << 20);
     NGSB_CUDA(cudaMalloc(&A->d_slice_off, ((size_t)ns + 1) * sizeof(uint64_t)));
     NGSB_CUDA(cudaMalloc(&A->d_slice_src, std::max<size_t>(1, ns) * sizeof(uint32_t)));
     NGSB_CUDA(cudaMalloc(&A->d_row_of, std::max<uint64_t>(32, nslots) * sizeof(uint32_t)));
     if (ns == 0) {
         NGSB_CUDA(cudaMemsetAsync(A->d_slice_off, 0, sizeof(uint64_t), ctx->stream));
         A->sell_entries = 0;
+        A->sell_cap = cap0;
         NGSB_CUDA(cudaMalloc(&A->d_scol, 16));
         NGSB_CUDA(cudaMalloc(&A->d_sval, 16));
         NGSB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -816,6 +799,15 @@ int sell_build(ngsb_csr *A, const uint64_t *h_rowptr)
     auto cleanup = [&]() { for (void *p : temps) cudaFree(p); temps.clear(); };
     cudaError_t e1 = cudaSuccess;
     int rc = NGSB_OK;
+    // Unstructured numberings (netgen, or any numbering after the Cuthill-McKee reordering): neighbouring rows differ in
+    // length (vertex rows of an order-3 space are 5x the mean), so rows are sorted by length inside windows of sigma rows
+    // (SELL-C-sigma).  Sorted windows group the long rows, so they can usually stay whole as well: first try without a
+    // cap and keep that layout when it pads less than 8 %; otherwise cut rows at cap0 and reduce the tails in the overflow
+    // kernel (145 k single-row CTAs per product on the 13.6 M-dof netgen system: 15 % of the product time).
+    uint32_t cap = tight ? std::max(cap0, cap_full) : cap0;
+    const int attempts = (!tight && ctx->sell_cap <= 0 && ctx->sell_sigma != 0 && ctx->sell_sigma != 1 && cap_full > cap0 && A->max_row < (1u << 20)) ? 2 : 1;
+    for (int attempt = 0; attempt < attempts; attempt++) {
+        if (attempts == 2) cap = attempt == 0 ? cap_full : cap0;
     // ---- 1. row order: sigma-sort by length inside windows (SELL-C-sigma), identity when sigma <= 1
     const uint32_t sigma = ctx->sell_sigma >= 0 ? (uint32_t)ctx->sell_sigma : (tight ? 0u : 4096u);
     fill_u32_kernel<<<grid_slots, 256, 0, ctx->stream>>>(A->d_row_of, A->h, nslots, 0xffffffffu, 0);
@@ -874,6 +866,12 @@ int sell_build(ngsb_csr *A, const uint64_t *h_rowptr)
         if (e1 != cudaSuccess) { set_error("SELL build (schedule): %s", cudaGetErrorString(e1)); return NGSB_ERR_CUDA; }
         if (rc != NGSB_OK) return rc;
     }
+        if (attempts == 2 && attempt == 0 && (double)A->sell_entries <= 1.08 * (double)A->nnz) break;      // whole rows: accepted
+    }
+    A->sell_cap = cap;
+    uint32_t novf = 0;
+    for (size_t r = 0; r < A->h; r++) novf += (h_rowptr[r + 1] - h_rowptr[r]) > cap;
+    A->novf = novf;
     // ---- 3. fill
     e1 = cudaMalloc(&A->d_scol, std::max<size_t>(16, A->sell_entries * sizeof(int32_t)));
     if (e1 == cudaSuccess) e1 = cudaMalloc(&A->d_sval, std::max<size_t>(16, A->sell_entries * ms * sizeof(double)));

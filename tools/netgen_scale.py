@@ -41,7 +41,7 @@ def generate(args):
     if env is None:
         raise SystemExit("netgen_scale: the reference build oracle/_ref/ngs is not here")
     cmd = [sys.executable, os.path.join(ROOT, "tools", "netgen_system.py"), "--maxh", str(args.maxh), "--nref", str(args.nref), "--order", str(args.order),
-           "--cpu-iters", str(args.cpu_iters), "--out", args.cache] + (["--cpu-full"] if args.cpu_full else []) + (["--threads", str(args.threads)] if args.threads else [])
+           "--cpu-iters", str(args.cpu_iters), "--out", args.cache] + (["--cpu-full"] if args.cpu_full else []) + (["--gpu-reference"] if args.gpu_reference else []) + (["--threads", str(args.threads)] if args.threads else [])
     r = subprocess.run(cmd, env=env, capture_output=True, text=True)
     if r.returncode != 0:
         raise SystemExit("netgen_system failed:\n" + r.stdout[-2000:] + r.stderr[-4000:])
@@ -136,6 +136,7 @@ def main():
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--cpu-iters", type=int, default=20)
     ap.add_argument("--cpu-full", action="store_true")
+    ap.add_argument("--gpu-reference", action="store_true")
     ap.add_argument("--cache", default="/dev/shm/ngsys")
     ap.add_argument("--modes", type=int, nargs="+", default=[0, 1])
     ap.add_argument("--reps", type=int, default=20)

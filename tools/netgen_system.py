@@ -24,6 +24,10 @@ ap.add_argument("--order", type=int, default=3)
 ap.add_argument("--threads", type=int, default=0)
 ap.add_argument("--cpu-iters", type=int, default=20)
 ap.add_argument("--cpu-full", action="store_true")
+ap.add_argument("--gpu-reference", action="store_true", help="also time the reference's OWN device path (ngscuda: cuSPARSE DevSparseMatrix, "
+                "cuBLAS UnifiedVector, DevCGSolver; built by oracle/build_reference_cuda.sh) on this GPU")
+ap.add_argument("--gpu-iters", type=int, default=100)
+ap.add_argument("--no-save", action="store_true")
 ap.add_argument("--out", required=True)
 args = ap.parse_args()
 ngsolve.ngsglobals.msg_level = 0
@@ -51,11 +55,12 @@ with TaskManager():
     res.data = Projector(fd, True) * ones
     free = res.FV().NumPy() > 0.5
     bits = np.packbits(free, bitorder="little")
-    np.save(os.path.join(args.out, "rowptr.npy"), rowptr)
-    np.save(os.path.join(args.out, "col.npy"), col)
-    np.save(os.path.join(args.out, "val.npy"), val)
-    np.save(os.path.join(args.out, "f.npy"), f.vec.FV().NumPy())
-    np.save(os.path.join(args.out, "freebits.npy"), bits)
+    if not args.no_save:
+        np.save(os.path.join(args.out, "rowptr.npy"), rowptr)
+        np.save(os.path.join(args.out, "col.npy"), col)
+        np.save(os.path.join(args.out, "val.npy"), val)
+        np.save(os.path.join(args.out, "f.npy"), f.vec.FV().NumPy())
+        np.save(os.path.join(args.out, "freebits.npy"), bits)
     meta["sha256_rowptr"] = hashlib.sha256(rowptr.tobytes()).hexdigest()
     meta["sha256_col"] = hashlib.sha256(col.tobytes()).hexdigest()
     meta["saved_s"] = time.perf_counter() - t0
@@ -83,5 +88,56 @@ with TaskManager():
         gfu.vec.data = inv * f.vec
         meta.update(cpu_full_steps=inv.GetSteps(), cpu_full_s=time.perf_counter() - t1)
         np.save(os.path.join(args.out, "u_ref.npy"), gfu.vec.FV().NumPy())
+    if args.gpu_reference:
+        # the stock reference device layer (ngscuda/cuda_linalg.cpp:187-316 DevSparseMatrix = cuSPARSE SpMV with a generic-API
+        # descriptor per call, ngscuda/unifiedvector.cpp cuBLAS vectors, ngscuda/cuda_krylov.cpp:19-203 DevCGSolver).  The
+        # python wrapper ngsolve/ngscuda.py refuses to load when the core library was configured without CUDA, the
+        # compiled module itself is complete: import it directly.
+        gr = {}
+        try:
+            from ngsolve._ngscuda import DevCGSolver as RefDevCGSolver      # registers the device creators at import
+            adev = a.mat.CreateDeviceMatrix()
+            jdev = jac.CreateDeviceMatrix()
+            fdev = f.vec.CreateDeviceVector()
+            gr["types"] = [type(adev).__name__, type(jdev).__name__, type(fdev).__name__]
+            xd = fdev.CreateVector(); yd = fdev.CreateVector()
+            xd.data = fdev
+            for _ in range(3):
+                yd.data = adev * xd
+            InnerProduct(yd, yd)                       # cublasDdot returns to the host: a device synchronisation
+            reps = 20
+            t1 = time.perf_counter()
+            for _ in range(reps):
+                yd.data = adev * xd
+            InnerProduct(yd, yd)
+            dt = (time.perf_counter() - t1) / reps
+            b_alg = a.mat.nze * 12 + fes.ndof * 20
+            gr.update(spmv_ms=dt * 1e3, spmv_gbs_algorithmic=b_alg / dt / 1e9)
+            # NGSolve's C++ CGSolver loop driving the device objects op by op (docs/i-tutorials/unit-5.5-cuda/poisson_cuda.ipynb)
+            K = args.gpu_iters
+            inv = CGSolver(adev, jdev, precision=1e-30, maxsteps=K, printrates=False)
+            res = (inv * fdev).Evaluate()
+            t1 = time.perf_counter()
+            res = (inv * fdev).Evaluate()
+            InnerProduct(res, res)
+            dt = time.perf_counter() - t1
+            gr.update(cg_hostloop_it_per_s=(inv.GetSteps() - 1) / dt, cg_hostloop_steps=inv.GetSteps())
+            # DevCGSolver: the graph-captured device CG
+            dinv = RefDevCGSolver(adev, jdev, precision=1e-30, maxsteps=K)
+            res = (dinv * fdev).Evaluate()
+            t1 = time.perf_counter()
+            res = (dinv * fdev).Evaluate()
+            InnerProduct(res, res)
+            dt = time.perf_counter() - t1
+            gr.update(devcg_it_per_s=(dinv.GetSteps() - 1) / dt if dinv.GetSteps() > 1 else K / dt, devcg_steps=dinv.GetSteps())
+            if args.cpu_full:
+                dinv = RefDevCGSolver(adev, jdev, precision=1e-8, maxsteps=20000)
+                t1 = time.perf_counter()
+                res = (dinv * fdev).Evaluate()
+                InnerProduct(res, res)
+                gr.update(devcg_full_steps=dinv.GetSteps(), devcg_full_s=time.perf_counter() - t1)
+        except Exception as e:                  # noqa: BLE001 -- report what the reference device path did
+            gr["error"] = repr(e)[:500]
+        meta["gpu_reference"] = gr
 json.dump(meta, open(os.path.join(args.out, "meta.json"), "w"))
 print(json.dumps(meta))
