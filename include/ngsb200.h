@@ -79,6 +79,7 @@ int ngsb_ctx_launch_count(const ngsb_ctx *ctx, uint64_t *count);
  *     "spmv_algo"        0 auto (= 3), 1 sub-warp CSR, 2 TMA-streamed CSR, 3 SELL-32
  *     "spmv_ctas_per_sm" grid of the SpMV kernels in CTAs per SM, 0 = default (96 for SELL)
  *     "cg_batch"         CG iterations per CUDA graph / between two polls of the device stop flag (default 16)
+ *     "cg_chunked"       0/1: the CG update kernel works on one contiguous chunk per CTA instead of grid-stride (default 0; A/B)
  *     "cg_fold_u"        0/1: the CG direction kernel also does u += al s (10 instead of 11 vector passes per iteration)
  *     "sell_variant"     inner-loop variant of the real SELL kernel (0 default; 1-6 kept for A/B, all bit-identical)
  *     "sell_pf_steps", "sell_pf_next"   L2 prefetch distances of the compressed loop (0 = off, default)
@@ -92,7 +93,7 @@ int ngsb_ctx_launch_count(const ngsb_ctx *ctx, uint64_t *count);
  *                        16-bit column offsets -- the signature of netgen's entity-by-entity numbering
  *     "sell_c16_all"     0/1: 16-bit column offsets for Complex and Mat<3,3> matrices too (default 0; must still be on at launch)
  *     "sell_cap"         longest row part kept in a slice, 0 = max(64, 4 x mean row length) or the longest row when cheap
- *     "sell_sigma"       rows sorted by length inside windows of this many rows, -1 = automatic, 0/1 = off
+ *     "sell_sigma"       rows sorted by length inside windows of this many rows, -1 = automatic (65536 where natural slices would pad > 5 %), 0/1 = off
  *     "sell_schedule"    slices ordered by their smallest first column: 0 off, 1 automatic, 2 on
  *     "spmv_tile", "spmv_ncw", "spmv_stages", "spmv_subwarp"   CSR kernels, 0 = default
  *   read by ngsb_parmat_create:

@@ -151,7 +151,7 @@ with TaskManager():
         host_ip = InnerProduct(fdev, w)
         t = fdev.CreateVector()
         t.data = fdev
-        t.Add(sc, w)                                   # t = f + <f, C f> * C f with the device scalar
+        t.data += sc * w                               # t = f + <f, C f> * C f with the device scalar (BaseScalar * vector expression)
         t2 = fdev.CreateVector()
         t2.data = fdev + host_ip * w
         dd = t.CreateVector()

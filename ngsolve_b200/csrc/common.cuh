@@ -75,6 +75,7 @@ struct ngsb_ctx {
     long sell_c16 = 1;           // 16-bit column offsets where a slice allows it (read at matrix creation and at launch)
     long sell_c16_all = 0;       // the same for complex and 3x3-block matrices (18.1 instead of 20, 74.1 instead of 76 bytes per entry)
     long spmv_tile = 0, spmv_ncw = 0, spmv_stages = 0, spmv_subwarp = 0;   // 0 = default; read when a matrix is created
+    long cg_chunked = 0;         // CG update kernel: contiguous chunk per CTA instead of the grid-stride split (A/B)
     long cg_fold_u = 0;          // CG: `u += al s` in the direction kernel instead of the update kernel (10 vector passes, not 11)
     long dist_overlap = 0;       // distributed CG: interface slices first, push, interior slices while the values travel
                                  // (read when a parallel matrix is created; peer-memory data path only)

@@ -58,6 +58,7 @@ struct ngsb_parmat {
     int32_t *d_if_dof = nullptr;
     uint32_t *d_if_first = nullptr;
     uint32_t *d_if_pos = nullptr;
+    uint32_t *d_if_nlow = nullptr;    // per interface dof: how many of its sharers have a lower rank than this one
     uint8_t *d_master = nullptr;  // n bytes
     std::vector<uint8_t> h_master;
     // peer-memory mode
@@ -234,18 +235,31 @@ __global__ void __launch_bounds__(256) pack_kernel(const double *__restrict__ v,
 }
 
 // ... and AddRecvValues for all neighbours at once, one thread per interface dof, copies added in ascending rank order
+// The copies of one dof are summed in ascending rank order WITH this rank's own value at its place in that order, so that
+// every sharer computes the bit-identical sum (the reference gets the same guarantee for its Jacobi diagonal by reducing at
+// the master, own value first, then the distant procs ascending, and scattering the result: linalg/paralleldofs.hpp:213-334).
+__device__ __forceinline__ double sum_copies(double own, const double *__restrict__ recv, const uint32_t *__restrict__ if_pos, uint32_t a, uint32_t m,
+                                             uint32_t b, int es, int c)
+{
+    double acc;
+    if (m > a) {
+        acc = __ldcg(recv + (size_t)es * if_pos[a] + c);
+        for (uint32_t q = a + 1; q < m; q++) acc += __ldcg(recv + (size_t)es * if_pos[q] + c);
+        acc += own;
+    } else acc = own;
+    for (uint32_t q = m; q < b; q++) acc += __ldcg(recv + (size_t)es * if_pos[q] + c);
+    return acc;
+}
+
 __global__ void __launch_bounds__(256) unpack_add_kernel(double *__restrict__ v, const int32_t *__restrict__ if_dof,
                                                         const uint32_t *__restrict__ if_first, const uint32_t *__restrict__ if_pos,
-                                                        const double *__restrict__ recv, size_t nif, int es)
+                                                        const uint32_t *__restrict__ if_nlow, const double *__restrict__ recv, size_t nif, int es)
 {
     size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= nif) return;
     const size_t dof = (size_t)if_dof[k];
-    for (int c = 0; c < es; c++) {
-        double acc = v[es * dof + c];
-        for (uint32_t q = if_first[k]; q < if_first[k + 1]; q++) acc += recv[es * (size_t)if_pos[q] + c];
-        v[es * dof + c] = acc;
-    }
+    const uint32_t a = if_first[k], b = if_first[k + 1], m = a + if_nlow[k];
+    for (int c = 0; c < es; c++) v[es * dof + c] = sum_copies(v[es * dof + c], recv, if_pos, a, m, b, es, c);
 }
 
 // Peer-memory mode, first half of Cumulate: store my interface values into the neighbours' receive areas (P2P stores
@@ -285,8 +299,8 @@ __global__ void __launch_bounds__(256) halo_push_kernel(const PeerHalo *__restri
 // so this kernel publishes the partial (`red`) itself before it waits.
 __global__ void __launch_bounds__(256) halo_unpack_kernel(const PeerHalo *__restrict__ H, double *__restrict__ v,
                                                          const int32_t *__restrict__ if_dof, const uint32_t *__restrict__ if_first,
-                                                         const uint32_t *__restrict__ if_pos, size_t nif, int es, CgState *st,
-                                                         const PeerReduce *R, int fin, const double *red)
+                                                         const uint32_t *__restrict__ if_pos, const uint32_t *__restrict__ if_nlow, size_t nif, int es,
+                                                         CgState *st, const PeerReduce *R, int fin, const double *red)
 {
     if (st && st->done) return;
     const unsigned long long s = *(volatile unsigned long long *)H->seq + 1;
@@ -298,11 +312,8 @@ __global__ void __launch_bounds__(256) halo_unpack_kernel(const PeerHalo *__rest
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < nif; k += stride) {
         const size_t dof = (size_t)if_dof[k];
-        for (int c = 0; c < es; c++) {
-            double acc = v[es * dof + c];
-            for (uint32_t q = if_first[k]; q < if_first[k + 1]; q++) acc += __ldcg(recv + (size_t)es * if_pos[q] + c);
-            v[es * dof + c] = acc;
-        }
+        const uint32_t a = if_first[k], b = if_first[k + 1], m = a + if_nlow[k];
+        for (int c = 0; c < es; c++) v[es * dof + c] = sum_copies(v[es * dof + c], recv, if_pos, a, m, b, es, c);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -353,7 +364,7 @@ static int cumulate_es(const ngsb_parmat *P, double *v, int es, CgState *st = nu
         SpanGuard g(ctx, KC_OTHER);
         const PeerReduce *R = fin ? comm->d_R : nullptr;
         halo_push_kernel<<<halo_grid(ctx, P->nex), 256, 0, ctx->stream>>>(P->d_H, v, P->d_exdofs, P->nex, es, st, R, red);
-        halo_unpack_kernel<<<halo_grid(ctx, P->nif), 256, 0, ctx->stream>>>(P->d_H, v, P->d_if_dof, P->d_if_first, P->d_if_pos, P->nif, es, st, R, fin, red);
+        halo_unpack_kernel<<<halo_grid(ctx, P->nif), 256, 0, ctx->stream>>>(P->d_H, v, P->d_if_dof, P->d_if_first, P->d_if_pos, P->d_if_nlow, P->nif, es, st, R, fin, red);
         ctx->launches += 1;          // two kernels, one counted by the SpanGuard
         NGSB_CUDA(cudaGetLastError());
         return NGSB_OK;
@@ -385,7 +396,7 @@ static int cumulate_es(const ngsb_parmat *P, double *v, int es, CgState *st = nu
     }
     if (rc == NGSB_OK) {
         SpanGuard g(ctx, KC_OTHER);
-        unpack_add_kernel<<<(unsigned)((P->nif + 255) / 256), 256, 0, ctx->stream>>>(v, P->d_if_dof, P->d_if_first, P->d_if_pos, recv, P->nif, es);
+        unpack_add_kernel<<<(unsigned)((P->nif + 255) / 256), 256, 0, ctx->stream>>>(v, P->d_if_dof, P->d_if_first, P->d_if_pos, P->d_if_nlow, recv, P->nif, es);
         if (cudaGetLastError() != cudaSuccess) rc = NGSB_ERR_CUDA;
     }
     if (own) {
@@ -412,7 +423,7 @@ static int halo_unpack_fin(const ngsb_parmat *P, double *v, CgState *st, const d
 {
     ngsb_ctx *ctx = P->comm->ctx;
     SpanGuard g(ctx, KC_OTHER);
-    halo_unpack_kernel<<<halo_grid(ctx, P->nif), 256, 0, ctx->stream>>>(P->d_H, v, P->d_if_dof, P->d_if_first, P->d_if_pos, P->nif, P->es, st,
+    halo_unpack_kernel<<<halo_grid(ctx, P->nif), 256, 0, ctx->stream>>>(P->d_H, v, P->d_if_dof, P->d_if_first, P->d_if_pos, P->d_if_nlow, P->nif, P->es, st,
                                                                         P->comm->d_R, 2, red);
     NGSB_CUDA(cudaGetLastError());
     return NGSB_OK;
@@ -740,10 +751,11 @@ extern "C" int ngsb_parmat_create_ex(ngsb_comm *comm, const ngsb_csr *local, con
     for (size_t k = 0; k < nex; k++) pairs[k] = std::make_pair(ex_dofs[k], (uint32_t)k);
     std::sort(pairs.begin(), pairs.end());   // by dof, then by position == by rank
     std::vector<int32_t> if_dof;
-    std::vector<uint32_t> if_first, if_pos(nex);
+    std::vector<uint32_t> if_first, if_pos(nex), if_nlow;
     for (size_t k = 0; k < nex; k++) {
-        if (k == 0 || pairs[k].first != pairs[k - 1].first) { if_dof.push_back(pairs[k].first); if_first.push_back((uint32_t)k); }
+        if (k == 0 || pairs[k].first != pairs[k - 1].first) { if_dof.push_back(pairs[k].first); if_first.push_back((uint32_t)k); if_nlow.push_back(0); }
         if_pos[k] = pairs[k].second;
+        if (pairs[k].second < ex_first[comm->rank]) if_nlow.back()++;        // ex_dofs is rank-major: a position below my own range = a lower rank
     }
     if_first.push_back((uint32_t)nex);
     P->nif = if_dof.size();
@@ -757,6 +769,7 @@ extern "C" int ngsb_parmat_create_ex(ngsb_comm *comm, const ngsb_csr *local, con
     if (rc == NGSB_OK) rc = up((void **)&P->d_if_dof, if_dof.data(), if_dof.size() * sizeof(int32_t));
     if (rc == NGSB_OK) rc = up((void **)&P->d_if_first, if_first.data(), if_first.size() * sizeof(uint32_t));
     if (rc == NGSB_OK) rc = up((void **)&P->d_if_pos, if_pos.data(), if_pos.size() * sizeof(uint32_t));
+    if (rc == NGSB_OK) rc = up((void **)&P->d_if_nlow, if_nlow.data(), if_nlow.size() * sizeof(uint32_t));
     if (rc == NGSB_OK) rc = up((void **)&P->d_master, P->h_master.data(), n);
     cudaStreamSynchronize(ctx->stream);
     if (rc == NGSB_OK && comm->p2p) {
@@ -796,7 +809,7 @@ extern "C" int ngsb_parmat_destroy(ngsb_parmat *P)
         if (P->peer_halo[q]) cudaIpcCloseMemHandle(P->peer_halo[q]);
     cudaFree(P->d_H); cudaFree(P->d_local); cudaFree(P->halo_mem);
     cudaFree(P->d_exdofs); cudaFree(P->d_send); cudaFree(P->d_recv);
-    cudaFree(P->d_if_dof); cudaFree(P->d_if_first); cudaFree(P->d_if_pos); cudaFree(P->d_master);
+    cudaFree(P->d_if_dof); cudaFree(P->d_if_first); cudaFree(P->d_if_pos); cudaFree(P->d_if_nlow); cudaFree(P->d_master);
     cudaFree(P->d_list_bnd); cudaFree(P->d_list_int); cudaFree(P->d_red_b);
     delete P;
     return NGSB_OK;
@@ -970,6 +983,7 @@ extern "C" int ngsb_parmat_cg_solve(const ngsb_parmat *P, const ngsb_jacobi *C, 
     v.counter = ctx->d_counter;
     v.ip_mode = ip_mode;
     v.fold_u = ctx->cg_fold_u ? 1 : 0;
+    v.chunked = ctx->cg_chunked ? 1 : 0;
 
     // u = 0; d = f, cumulated by the Jacobi application (linalg/jacobi.cpp:78)
     cu(cudaMemsetAsync(u->d, 0, nscal * sizeof(double), ctx->stream));
@@ -987,7 +1001,7 @@ extern "C" int ngsb_parmat_cg_solve(const ngsb_parmat *P, const ngsb_jacobi *C, 
     if (rc == NGSB_OK && use_graph) {
         // the preconditioner enters by its unique id, never by its address (a re-created object may get the same one back)
         const void *key[9] = {u->d, d, w, s, as, (const void *)(uintptr_t)(C ? C->uid : 0), (const void *)(intptr_t)ip_mode, d_hist,
-                              (const void *)(intptr_t)(ctx->cg_fold_u | (ctx->sell_variant << 4) | (ctx->sell_c16 << 12) | (ctx->spmv_ctas_per_sm << 16))};
+                              (const void *)(intptr_t)(ctx->cg_fold_u | (ctx->cg_chunked << 1) | (ctx->sell_variant << 4) | (ctx->sell_c16 << 12) | (ctx->spmv_ctas_per_sm << 16))};
         const bool hit = Pm->graph_exec && Pm->g_batch == batch && memcmp(key, Pm->g_key, sizeof(key)) == 0;
         if (!hit) {
             cudaGraph_t graph = nullptr;

@@ -34,7 +34,7 @@ struct Workspace {
     // re-created object may get the same address back), the vectors, and every option the captured launches read
     uint64_t g_A = 0, g_C = 0;
     double *g_ptrs[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    long g_opts[10] = {-1, -1, -1, -1, -1, -1, -1, -1, -1, -1};
+    long g_opts[11] = {-1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1};
 };
 
 // buffers taken from the workspace go back on every exit path
@@ -231,11 +231,21 @@ __global__ void __launch_bounds__(256) cg_fused_kernel(const CgVecs v, int sub)
     const double alr = MODE == 1 ? st->al[0] : 0.0;
     const double ali = MODE == 1 ? st->al[1] : 0.0;
     const bool conj = v.ip_mode == NGSB_IP_COMPLEX_CONJ;
-    // contiguous chunk per block (fixed -> deterministic), even length so that pairs never straddle chunks
-    uint64_t per = ((v.n + gridDim.x - 1) / gridDim.x + 1) & ~(uint64_t)1;
-    uint64_t lo = (uint64_t)blockIdx.x * per;
-    uint64_t hi = lo + per < v.n ? lo + per : v.n;
-    if (lo > hi) lo = hi;
+    // Work split (fixed for a given n and grid -> deterministic sums).  Default: grid-stride, i.e. at any moment all CTAs
+    // read neighbouring addresses of each of the eight vectors -- eight DRAM streams instead of eight per CTA (the chunked
+    // split ran at 0.82 of the copy rate, the grid-stride direction kernel at 0.95; profiles/r1_ncu_launches_bench_n1_summary.txt).
+    // v.chunked: one contiguous chunk per block, even length so that pairs never straddle chunks (kept for A/B).
+    uint64_t lo, hi, first, step;
+    if (v.chunked) {
+        uint64_t per = ((v.n + gridDim.x - 1) / gridDim.x + 1) & ~(uint64_t)1;
+        lo = (uint64_t)blockIdx.x * per;
+        hi = lo + per < v.n ? lo + per : v.n;
+        if (lo > hi) lo = hi;
+        first = threadIdx.x; step = blockDim.x;
+    } else {
+        lo = 0; hi = v.n;
+        first = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; step = (uint64_t)gridDim.x * blockDim.x;
+    }
     double accr = 0.0, acci = 0.0;
     if (KIND == NGSB_REAL && MODE == 1 && v.invdiag != nullptr &&
         ((reinterpret_cast<uintptr_t>(v.u) | reinterpret_cast<uintptr_t>(v.d) | reinterpret_cast<uintptr_t>(v.w) |
@@ -244,7 +254,8 @@ __global__ void __launch_bounds__(256) cg_fused_kernel(const CgVecs v, int sub)
         // three out; identical arithmetic to the scalar loop below
         double acc1 = 0.0;
         const uint64_t hi2 = lo + ((hi - lo) & ~(uint64_t)1);
-        for (uint64_t i = lo + 2 * (uint64_t)threadIdx.x; i < hi2; i += 2 * (uint64_t)blockDim.x) {
+#pragma unroll 2
+        for (uint64_t i = lo + 2 * first; i < hi2; i += 2 * step) {
             const double2 a2 = *reinterpret_cast<const double2 *>(v.as + i);
             const double2 m2 = *reinterpret_cast<const double2 *>(v.invdiag + i);
             double2 d2 = *reinterpret_cast<double2 *>(v.d + i);
@@ -264,7 +275,7 @@ __global__ void __launch_bounds__(256) cg_fused_kernel(const CgVecs v, int sub)
             if (v.master == nullptr || v.master[i]) accr = fma(d2.x, w2.x, accr);
             if (v.master == nullptr || v.master[i + 1]) acc1 = fma(d2.y, w2.y, acc1);
         }
-        if (hi2 < hi && threadIdx.x == 0) {      // odd tail of the last chunk
+        if (hi2 < hi && first == 0) {            // odd tail (of the last chunk / of the vector)
             const uint64_t i = hi2;
             if (!FOLD) v.u[i] += alr * v.s[i];
             const double dn = v.d[i] - alr * v.as[i];
@@ -276,7 +287,7 @@ __global__ void __launch_bounds__(256) cg_fused_kernel(const CgVecs v, int sub)
         accr += acc1;
         lo = hi;                                  // skip the generic loop
     }
-    for (uint64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    for (uint64_t i = lo + first; i < hi; i += step) {
         double dn[3], wn[3];
         if (MODE == 0) {
 #pragma unroll
@@ -521,6 +532,7 @@ int cg_solve_device(const ngsb_csr *A, const ngsb_jacobi *C, const double *f, do
     v.counter = ctx->d_counter;
     v.ip_mode = ip_mode;
     v.fold_u = ctx->cg_fold_u ? 1 : 0;
+    v.chunked = ctx->cg_chunked ? 1 : 0;
 
     int sub = 0;
     if (initialize) {
@@ -539,8 +551,8 @@ int cg_solve_device(const ngsb_csr *A, const ngsb_jacobi *C, const double *f, do
     const bool use_graph = !ctx->timing && getenv("NGSB_NO_CUDA_GRAPH") == nullptr && batch > 1;
     if (use_graph) {
         double *key[6] = {u, d, w, s, as, (double *)f};
-        const long opts[10] = {batch, (long)ip_mode, ctx->spmv_algo, ctx->spmv_ctas_per_sm, ctx->cg_fold_u, ctx->sell_variant, ctx->sell_c16,
-                               ctx->sell_c16_all, ctx->sell_pf_steps, ctx->sell_pf_next};
+        const long opts[11] = {batch, (long)ip_mode, ctx->spmv_algo, ctx->spmv_ctas_per_sm, ctx->cg_fold_u, ctx->sell_variant, ctx->sell_c16,
+                               ctx->sell_c16_all, ctx->sell_pf_steps, ctx->sell_pf_next, ctx->cg_chunked};
         bool hit = ws->graph_exec && ws->g_A == A->uid && ws->g_C == (C ? C->uid : 0) && memcmp(opts, ws->g_opts, sizeof(opts)) == 0 &&
                    memcmp(key, ws->g_ptrs, sizeof(key)) == 0;
         if (!hit) {

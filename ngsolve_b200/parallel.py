@@ -75,6 +75,19 @@ class ParallelDofs:
         self.ndof, self.nranks, self.rank = ndof, nranks, rank
         assert len(self.ex_first) == nranks + 1
 
+    @classmethod
+    def from_dist_procs(cls, dp_first, dp, nranks, rank):
+        """the reference constructor's input: per local dof the other ranks that hold it (ParallelDofs(comm, Table<int>
+        dist_procs), linalg/paralleldofs.cpp:20-59): exchangedofs[p] = the local dofs listing p, ascending"""
+        dp_first = np.asarray(dp_first, dtype=np.int64)
+        dp = np.asarray(dp, dtype=np.int64)
+        ndof = len(dp_first) - 1
+        dof_of = np.repeat(np.arange(ndof, dtype=np.int64), np.diff(dp_first))
+        order = np.lexsort((dof_of, dp))                      # by rank, then by local dof
+        cnt = np.bincount(dp, minlength=nranks) if len(dp) else np.zeros(nranks, dtype=np.int64)
+        ex_first = np.concatenate([[0], np.cumsum(cnt)]).astype(np.uint64)
+        return cls(ex_first, dof_of[order].astype(np.int32), ndof, nranks, rank)
+
     def GetExchangeDofs(self, proc):
         return self.ex_dofs[int(self.ex_first[proc]):int(self.ex_first[proc + 1])]
 

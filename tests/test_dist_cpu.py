@@ -122,3 +122,32 @@ def test_masterdofs_partition_global_dofs():
         pd = ParallelDofs(*W.exchange_tables(boxes, r), ndof=b.ndof, nranks=4, rank=r)
         seen[b.dof_info()[0][pd.MasterDofs()].astype(np.int64)] += 1
     assert np.all(seen == 1)          # every global dof has exactly one master (global_ndof = sum of master counts)
+
+
+# ---- pinned against the REFERENCE's ParallelDofs (tests/golden/pardofs_reference.npz, produced by running
+# linalg/paralleldofs.cpp on in-process ranks: tests/golden/make_golden_pardofs.py) --------------------------------------
+@pytest.mark.parametrize("name", ["grid4", "rand3"])
+def test_exchange_tables_equal_the_reference_paralleldofs(name):
+    from conftest import load_golden
+    from oracle import pyoracle as orc
+    from ngsolve_b200.parallel import ParallelDofs
+    g = load_golden("pardofs_reference")
+    nr = int(g[name + "_nranks"])
+    masters = 0
+    for r in range(nr):
+        pre = "%s_r%d_" % (name, r)
+        first, dp = g[pre + "dp_first"], g[pre + "dp"]
+        # the oracle's restatement of the constructor ...
+        dist_procs = [dp[first[i]:first[i + 1]] for i in range(len(first) - 1)]
+        exch, ismaster = orc.pardofs_build(nr, r, dist_procs)
+        gf = g[pre + "ex_first"]
+        for p in range(nr):                                                   # bit-exact halo maps
+            assert np.array_equal(exch[p], g[pre + "ex_dofs"][gf[p]:gf[p + 1]])
+        assert np.array_equal(ismaster.astype(np.uint8), g[pre + "master"])
+        # ... and the host side of the product
+        pd = ParallelDofs.from_dist_procs(first, dp, nr, r)
+        assert np.array_equal(pd.ex_first.astype(np.int64), g[pre + "ex_first"]) and np.array_equal(pd.ex_dofs, g[pre + "ex_dofs"])
+        assert np.array_equal(pd.MasterDofs().astype(np.uint8), g[pre + "master"])
+        masters += int(g[pre + "master"].sum())
+        assert int(g[pre + "global_ndof"]) == int(g[name + "_nglobal"])
+    assert masters == int(g[name + "_nglobal"])        # global_ndof = all-reduced master count (paralleldofs.cpp:104-107)

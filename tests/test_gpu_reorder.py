@@ -142,7 +142,7 @@ def test_cg_on_internally_reordered_matrix(la, forced, name):
     s0, v0 = two_stage(plain)
     assert abs(s1 - s0) <= 2 and relerr(v1, v0) <= 1e-5, (s1, s0)
     # host-buffer entry
-    uh, steps, _ = la.cg_solve_host(dev, jac, np.asarray(g["f"]), precision=float(g["cg_prec"]), maxsteps=int(g["cg_maxsteps"]),
+    uh, steps, _ = la.cg_solve_host(dev, dev.CreateSmoother(la.BitArray(g["freebits"])), np.asarray(g["f"]), precision=float(g["cg_prec"]), maxsteps=int(g["cg_maxsteps"]),
                                     conjugate=False)
     assert abs(steps - int(g["cg_steps"])) <= 2 and relerr(np.asarray(uh).reshape(-1), g["cg_u"]) <= 1e-6
 

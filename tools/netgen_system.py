@@ -123,7 +123,7 @@ with TaskManager():
             dt = time.perf_counter() - t1
             gr.update(cg_hostloop_it_per_s=(inv.GetSteps() - 1) / dt, cg_hostloop_steps=inv.GetSteps())
             # DevCGSolver: the graph-captured device CG
-            dinv = RefDevCGSolver(adev, jdev, precision=1e-30, maxsteps=K)
+            dinv = RefDevCGSolver(adev, jdev, adev, jdev, precision=1e-30, maxsteps=K)
             res = (dinv * fdev).Evaluate()
             t1 = time.perf_counter()
             res = (dinv * fdev).Evaluate()
@@ -131,7 +131,7 @@ with TaskManager():
             dt = time.perf_counter() - t1
             gr.update(devcg_it_per_s=(dinv.GetSteps() - 1) / dt if dinv.GetSteps() > 1 else K / dt, devcg_steps=dinv.GetSteps())
             if args.cpu_full:
-                dinv = RefDevCGSolver(adev, jdev, precision=1e-8, maxsteps=20000)
+                dinv = RefDevCGSolver(adev, jdev, adev, jdev, precision=1e-8, maxsteps=20000)
                 t1 = time.perf_counter()
                 res = (dinv * fdev).Evaluate()
                 InnerProduct(res, res)
