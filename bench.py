@@ -11,9 +11,14 @@ the reference's ParallelDofs / ParallelMatrix split; interface values move by NC
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--size M] [--impl reference]
 
---impl reference times the CPU restatement of the reference path (oracle/, OpenMP on all host
-cores; NGSolve itself needs cmake + netgen and cannot be built on the box) on a bounded sample
-of the same workload, scaled to the full size by the nnz ratio.
+--impl reference times the reference itself -- NGSolve's C++ CGSolver + JacobiPrecond under its TaskManager on all host
+cores (oracle/ref_cpu_cg.py, the build of oracle/build_reference.sh travels to the GPU box in oracle/_ref/ngs) -- on a
+bounded sample of the same workload family, scaled to the full size by the nnz ratio; only when that build is absent
+the oracle port of the same path (oracle/ngs_oracle.c, OpenMP) stands in (cpu_baseline.kind says which).
+
+config.netgen_check (N = 1, when the reference build is on the box): the same library on a netgen-meshed system in
+NGSolve's own dof numbering -- unit_cube maxh=0.05 + 2x Refine, H1 order 3, 13.6 M dofs (the C3 fallback) --
+with the automatic Cuthill-McKee reordering, SpMV and CG against the same roofline, the reference's CPU CG beside it.
 """
 import argparse
 import json
@@ -37,7 +42,7 @@ SAMPLE_M = 50            # CPU sample: (3*50+1)^3 = 3.4 M dofs, 163 M non-zeros 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--size", type=int, default=160, help="cubes per axis of the global grid; dofs = (3*size+1)^3 "
                     "(160 -> 111 M dofs; divisible by 8 so that the z-slabs of the multi-GPU runs are equal)")
@@ -46,6 +51,8 @@ def parse():
                     "is created (e.g. dist_overlap=1, spmv_ctas_per_sm=64); repeatable; recorded in config.options")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-full-solve", action="store_true")
+    ap.add_argument("--no-netgen-check", action="store_true")
+    ap.add_argument("--netgen-nref", type=int, default=2, help="Refine() steps of the netgen check (2 -> 13.6 M dofs, 1 -> 1.7 M)")
     ap.add_argument("--cpu-iters", type=int, default=150)
     ap.add_argument("--cpu-sample", type=int, default=SAMPLE_M, help="cubes per axis of the CPU arm's sample system")
     ap.add_argument("--cpu-sample-t1", type=int, default=SAMPLE_M_T1, help="the same for the single-thread run")
@@ -189,6 +196,33 @@ def run_reference(args):
     emit(line)
 
 
+def netgen_check(nref):
+    """tools/netgen_scale.py in a subprocess (its own CUDA context, before the big system is built): the library on a
+    netgen-numbered system with the automatic reordering.  None when the reference build is not on the box."""
+    if _reference_env() is None:
+        return None
+    import tempfile
+    cache = tempfile.mkdtemp(prefix="ngsys_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    try:
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "netgen_scale.py"), "--nref", str(nref), "--cache", cache, "--modes", "-1",
+                            "--full", "--cpu-iters", "10"], capture_output=True, text=True, timeout=600)
+        d = json.loads(r.stdout.strip().splitlines()[-1])
+    except Exception as e:                    # noqa: BLE001 -- the check is reported, never fatal for the bench line
+        return {"error": repr(e)[:300]}
+    finally:
+        import shutil
+        shutil.rmtree(cache, ignore_errors=True)
+    s, m = d["system"], d["reorder=-1"]
+    return {"mesh": "netgen unit_cube maxh=%g + %dx Refine, H1 order %d, NGSolve dof numbering" % (s["maxh"], s["nref"], s["order"]),
+            "ne": s["ne"], "nv": s["nv"], "ndof": s["ndof"], "nnz": s["nnz"], "sha256_rowptr": s["sha256_rowptr"][:16], "sha256_col": s["sha256_col"][:16],
+            "reordered": m["reordered"], "natural_c16_share": m["natural_c16_share"], "c16_share_of_entries": m["c16_share_of_entries"],
+            "sell_padding": m["sell_padding"], "create_s": m["create_s"],
+            "spmv_kernel_ms": m["spmv_kernel_ms"], "spmv_gbs_algorithmic": m["spmv_gbs_algorithmic"], "spmv_frac_of_peak": m["spmv_frac_algorithmic"],
+            "spmv_gbs_stored": m["spmv_gbs_stored"], "spmv_call_ms_incl_gather": m["spmv_call_ms"],
+            "cg_it_per_s": m["cg_it_per_s"], "cg_frac_of_peak": m["cg_frac"], "full_solve_steps": m.get("full_steps"), "full_solve_s": m.get("full_s"),
+            "cpu_reference_it_per_s": s.get("cpu_it_per_s"), "cpu_reference_threads": s.get("threads"), "cpu_reference_spmv_ms": s.get("cpu_spmv_ms")}
+
+
 # ---------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------
@@ -248,6 +282,9 @@ def run_b200(args):
     if world != args.gpus:
         raise SystemExit("bench.py: --gpus %d but WORLD_SIZE=%d (launch with torch.distributed.run)" % (args.gpus, world))
     torch.cuda.set_device(local_rank)
+    ng_check = None
+    if world == 1 and not args.no_netgen_check:
+        ng_check = netgen_check(args.netgen_nref)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = la.Context(local_rank)
@@ -432,7 +469,7 @@ def run_b200(args):
                                     + ("; interface slices first, pushed while the interior slices are multiplied (%d + %d slices)" % pmat.overlap[1:] if pmat.overlap[0] else ""),
                        "options": list(args.opt),
                        "l2": "inputs (%.1f GB per GPU) far larger than the 126 MB L2" % (b_spmv / 1e9),
-                       "setup_s": setup_s, "full_solve": full,
+                       "setup_s": setup_s, "full_solve": full, "netgen_check": ng_check,
                        "cg_gbs_per_gpu": b_cg * value / 1e9, "cg_bytes_per_iteration_per_gpu": b_cg,
                        "spmv_pct_of_8TBs": achieved / 8000.0 * 100.0,
                        "sell_padding": sell_entries / max(1, nnz_local) - 1.0, "sell_overflow_rows": sell_ovf},

@@ -97,6 +97,7 @@ int ngsb_ctx_launch_count(const ngsb_ctx *ctx, uint64_t *count);
  *     "sell_schedule"    slices ordered by their smallest first column: 0 off, 1 automatic, 2 on
  *     "spmv_tile", "spmv_ncw", "spmv_stages", "spmv_subwarp"   CSR kernels, 0 = default
  *   read by ngsb_parmat_create:
+ *     "dist_fused_push"  0/1: product + halo push in one kernel (default 1, see ngsb_parmat_create)
  *     "dist_overlap"     0/1: interface slices first, pushed while the interior slices are multiplied (default 0) */
 int ngsb_ctx_set_option(ngsb_ctx *ctx, const char *name, long value);
 /* device time in ms of the kernels recorded since the last reset for a class
@@ -302,7 +303,11 @@ int ngsb_parmat_create_ex(ngsb_comm *comm, const ngsb_csr *local, const uint64_t
 int ngsb_parmat_destroy(ngsb_parmat *P);
 int ngsb_parmat_info(const ngsb_parmat *P, int *peer_memory, int *n_neighbours, size_t *n_exchange,
                      size_t *n_interface);
-/* option "dist_overlap" (set on the context before ngsb_parmat_create, peer-memory data path): the CG product runs the
+/* option "dist_fused_push" (default 1; read by ngsb_parmat_create, peer-memory data path): the product kernel of the distributed
+ * CG stores every interface row straight into the neighbours' receive areas (P2P stores over NVLink) as soon as its slice is
+ * done, and its last block publishes the sequence flags and the rank's partial of <s, A s> -- product and halo push are ONE
+ * kernel, the exchange overlaps the rest of the product; 0 = separate halo_push_kernel after the product.
+ * option "dist_overlap" (set on the context before ngsb_parmat_create, peer-memory data path): the CG product runs the
  * SELL slices holding interface rows first, pushes them, and runs the interior slices while the values travel -- the
  * overlap the reference gets from MPI_Isend/Irecv around its local MultAdd (parallel/parallelvvector.cpp:452-475).
  * Reports whether the split is active and the two slice counts. */

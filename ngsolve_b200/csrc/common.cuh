@@ -11,6 +11,8 @@
 #include <memory>
 #include <algorithm>
 
+#include <nvtx3/nvToolsExt.h>     // header-only NVTX v3: ranges cost nothing unless a profiler is attached
+
 #include "../../include/ngsb200.h"
 
 namespace ngsb {
@@ -40,6 +42,13 @@ void set_error(const char *fmt, ...);
         int rc__ = (call);             \
         if (rc__ != NGSB_OK) return rc__; \
     } while (0)
+
+// NVTX range named after the reference's Timer of the same region ("SparseMatrix::MultAdd", "CG solver", ...),
+// so that a timeline of the library reads like the reference's own profile
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 // kernel classes for the optional per-class device timing (option "timing")
 enum KClass { KC_SPMV = 0, KC_CGUPDATE = 1, KC_VEC = 2, KC_OTHER = 3, KC_COUNT = 4 };
@@ -77,6 +86,8 @@ struct ngsb_ctx {
     long spmv_tile = 0, spmv_ncw = 0, spmv_stages = 0, spmv_subwarp = 0;   // 0 = default; read when a matrix is created
     long cg_chunked = 0;         // CG update kernel: contiguous chunk per CTA instead of the grid-stride split (A/B)
     long cg_fold_u = 0;          // CG: `u += al s` in the direction kernel instead of the update kernel (10 vector passes, not 11)
+    long dist_fused_push = 1;    // distributed CG, peer-memory path: interface rows are stored into the neighbours' receive areas by
+                                 // the product kernel itself (no separate push kernel); read when a parallel matrix is created
     long dist_overlap = 0;       // distributed CG: interface slices first, push, interior slices while the values travel
                                  // (read when a parallel matrix is created; peer-memory data path only)
     long reorder = -1;           // internal Cuthill-McKee reordering of square matrices: 0 off, 1 always, -1 automatic

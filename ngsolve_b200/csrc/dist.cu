@@ -73,6 +73,12 @@ struct ngsb_parmat {
     uint32_t *d_list_bnd = nullptr, *d_list_int = nullptr;
     uint32_t n_bnd = 0, n_int = 0;
     double *d_red_b = nullptr;                    // <s, A s> over the interface slices (2 doubles)
+    // product + exchange in one kernel (option "dist_fused_push", default on in peer-memory mode): per scheduled slice the
+    // record of its interface rows (sell.cu, SellPush)
+    bool fused_push = false;
+    uint32_t *d_slice_if = nullptr;
+    int32_t *d_lane_if = nullptr;
+    ngsb::SellPush *d_push_desc = nullptr;        // device copy of the descriptor
     // cached CUDA graph of one batch of CG iterations (peer-memory mode)
     cudaGraphExec_t graph_exec = nullptr;
     const void *g_key[9] = {};
@@ -666,6 +672,47 @@ __global__ void __launch_bounds__(256) mark_interface_slices_kernel(const uint32
     if (lane == 0) flag[t] = m ? 1 : 0;
 }
 
+// tables for the product + exchange kernel: which scheduled slices hold interface rows, and which interface dof sits in which lane
+static int parmat_setup_fused_push(ngsb_parmat *P, const std::vector<int32_t> &if_dof)
+{
+    const ngsb_csr *A = P->local;
+    ngsb_ctx *ctx = P->comm->ctx;
+    const uint32_t ns = A->nslices;
+    std::vector<uint32_t> slice_src(ns), row_of((size_t)ns * 32);
+    NGSB_CUDA(cudaMemcpyAsync(slice_src.data(), A->d_slice_src, (size_t)ns * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    NGSB_CUDA(cudaMemcpyAsync(row_of.data(), A->d_row_of, (size_t)ns * 32 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    NGSB_CUDA(cudaStreamSynchronize(ctx->stream));
+    std::vector<int32_t> ifidx(P->n, -1);
+    for (size_t k = 0; k < if_dof.size(); k++) ifidx[if_dof[k]] = (int32_t)k;
+    std::vector<uint32_t> slice_if(ns, 0xffffffffu);
+    std::vector<int32_t> lane_if;
+    for (uint32_t t = 0; t < ns; t++) {
+        const size_t base = (size_t)slice_src[t] * 32;
+        bool any = false;
+        for (int l = 0; l < 32 && !any; l++) any = row_of[base + l] != 0xffffffffu && ifidx[row_of[base + l]] >= 0;
+        if (!any) continue;
+        slice_if[t] = (uint32_t)(lane_if.size() / 32);
+        for (int l = 0; l < 32; l++) lane_if.push_back(row_of[base + l] != 0xffffffffu ? ifidx[row_of[base + l]] : -1);
+    }
+    NGSB_CUDA(cudaMalloc(&P->d_slice_if, std::max<size_t>(1, ns) * sizeof(uint32_t)));
+    NGSB_CUDA(cudaMalloc(&P->d_lane_if, std::max<size_t>(32, lane_if.size()) * sizeof(int32_t)));
+    NGSB_CUDA(cudaMemcpyAsync(P->d_slice_if, slice_if.data(), (size_t)ns * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    if (!lane_if.empty()) NGSB_CUDA(cudaMemcpyAsync(P->d_lane_if, lane_if.data(), lane_if.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    NGSB_CUDA(cudaStreamSynchronize(ctx->stream));
+    SellPush desc;
+    desc.H = P->d_H;
+    desc.R = P->comm->d_R;
+    desc.slice_if = P->d_slice_if;
+    desc.lane_if = P->d_lane_if;
+    desc.if_first = P->d_if_first;
+    desc.if_pos = P->d_if_pos;
+    desc.es = P->es;
+    NGSB_CUDA(cudaMalloc(&P->d_push_desc, sizeof(SellPush)));
+    NGSB_CUDA(cudaMemcpy(P->d_push_desc, &desc, sizeof(SellPush), cudaMemcpyHostToDevice));
+    P->fused_push = true;
+    return NGSB_OK;
+}
+
 static int parmat_setup_overlap(ngsb_parmat *P, const std::vector<int32_t> &if_dof)
 {
     const ngsb_csr *A = P->local;
@@ -783,6 +830,8 @@ extern "C" int ngsb_parmat_create_ex(ngsb_comm *comm, const ngsb_csr *local, con
     if (rc == NGSB_OK && P->p2p && np > 1 && ctx->dist_overlap && local->nslices > 0 && !if_dof.empty() &&
         (ctx->spmv_algo == 0 || ctx->spmv_algo == 3))
         rc = parmat_setup_overlap(P, if_dof);
+    if (rc == NGSB_OK && P->p2p && np > 1 && !P->overlap && ctx->dist_fused_push && local->nslices > 0 && (ctx->spmv_algo == 0 || ctx->spmv_algo == 3))
+        rc = parmat_setup_fused_push(P, if_dof);
     if (rc == NGSB_OK && !P->p2p && np > 1) {
         if (cudaMalloc(&P->d_send, std::max<size_t>(16, nex * P->es * sizeof(double))) != cudaSuccess) rc = NGSB_ERR_NOMEM;
         if (rc == NGSB_OK && cudaMalloc(&P->d_recv, std::max<size_t>(16, nex * P->es * sizeof(double))) != cudaSuccess) rc = NGSB_ERR_NOMEM;
@@ -809,7 +858,7 @@ extern "C" int ngsb_parmat_destroy(ngsb_parmat *P)
         if (P->peer_halo[q]) cudaIpcCloseMemHandle(P->peer_halo[q]);
     cudaFree(P->d_H); cudaFree(P->d_local); cudaFree(P->halo_mem);
     cudaFree(P->d_exdofs); cudaFree(P->d_send); cudaFree(P->d_recv);
-    cudaFree(P->d_if_dof); cudaFree(P->d_if_first); cudaFree(P->d_if_pos); cudaFree(P->d_if_nlow); cudaFree(P->d_master);
+    cudaFree(P->d_if_dof); cudaFree(P->d_if_first); cudaFree(P->d_if_pos); cudaFree(P->d_if_nlow); cudaFree(P->d_master); cudaFree(P->d_slice_if); cudaFree(P->d_lane_if); cudaFree(P->d_push_desc);
     cudaFree(P->d_list_bnd); cudaFree(P->d_list_int); cudaFree(P->d_red_b);
     delete P;
     return NGSB_OK;
@@ -910,15 +959,23 @@ static int enqueue_par_iteration(const ngsb_parmat *P, const CgVecs &v, double *
         NGSB_TRY(spmv_launch(a));                                               // as(interior slices), local <s,as> complete
         NGSB_TRY(halo_unpack_fin(P, as, v.state, comm->d_red));                 // as -> CUMULATED; kss all-reduced, al = wd/kss
         NGSB_TRY(cg_launch_fused(ctx, A->kind, 1, v, 0));
-        NGSB_TRY(cg_launch_finalize(ctx, 2, v.state, comm->d_red, v.hist, comm->d_R));
+        if (!v.R) NGSB_TRY(cg_launch_finalize(ctx, 2, v.state, comm->d_red, v.hist, comm->d_R));
         NGSB_TRY(cg_launch_dir(ctx, A->kind, v));
         return NGSB_OK;
     }
+    if (P->fused_push) a.push = P->d_push_desc;                                  // interface rows leave for the neighbours from inside the product
     NGSB_TRY(spmv_launch(a));                                                   // as = A s (DISTRIBUTED), local <s,as>
     if (P->p2p) {
+        if (P->fused_push) {
+            // the product pushed the rows, the flags and the <s,As> partial itself: only the unpack half of Cumulate is left
+            SpanGuard g(ctx, KC_OTHER);
+            halo_unpack_kernel<<<halo_grid(ctx, P->nif), 256, 0, ctx->stream>>>(P->d_H, as, P->d_if_dof, P->d_if_first, P->d_if_pos, P->d_if_nlow, P->nif, P->es,
+                                                                                v.state, comm->d_R, 1, comm->d_red);
+            NGSB_CUDA(cudaGetLastError());
+        } else
         NGSB_TRY(cumulate_es(P, as, P->es, v.state, comm->d_red, 1));           // as -> CUMULATED; kss all-reduced, al = wd/kss
-        NGSB_TRY(cg_launch_fused(ctx, A->kind, 1, v, 0));                       // u, d, w, masked <d,w> -> d_red
-        NGSB_TRY(cg_launch_finalize(ctx, 2, v.state, comm->d_red, v.hist, comm->d_R));   // all-reduce, be, loop condition
+        NGSB_TRY(cg_launch_fused(ctx, A->kind, 1, v, 0));                       // u, d, w, masked <d,w> (-> d_red, or all-reduced in place)
+        if (!v.R) NGSB_TRY(cg_launch_finalize(ctx, 2, v.state, comm->d_red, v.hist, comm->d_R));   // all-reduce, be, loop condition
     } else {
         NGSB_TRY(all_reduce2(comm, comm->d_red));
         NGSB_TRY(cg_launch_finalize(ctx, 1, v.state, comm->d_red, v.hist));
@@ -976,6 +1033,7 @@ extern "C" int ngsb_parmat_cg_solve(const ngsb_parmat *P, const ngsb_jacobi *C, 
     v.bits = C ? C->d_bits : nullptr;
     v.master = P->d_master;
     v.dot_out = comm->d_red;
+    v.R = (P->p2p && ctx->dist_fused_push) ? comm->d_R : nullptr;      // the update kernel all-reduces <d,w> itself (krylov.cu)
     v.n = A->h;
     v.state = d_state;
     v.hist = d_hist;
@@ -992,7 +1050,7 @@ extern "C" int ngsb_parmat_cg_solve(const ngsb_parmat *P, const ngsb_jacobi *C, 
     v.f = d;                       // init kernel reads f, writes d: same values
     if (rc == NGSB_OK) rc = cg_launch_fused(ctx, A->kind, 0, v, 0);
     if (rc == NGSB_OK && !P->p2p) rc = all_reduce2(comm, comm->d_red);
-    if (rc == NGSB_OK) rc = cg_launch_finalize(ctx, 0, d_state, comm->d_red, d_hist, P->p2p ? comm->d_R : nullptr);
+    if (rc == NGSB_OK && !v.R) rc = cg_launch_finalize(ctx, 0, d_state, comm->d_red, d_hist, P->p2p ? comm->d_R : nullptr);
 
     const long batch = ctx->cg_batch;
     // peer-memory mode has no library call inside the iteration: one CUDA graph per batch

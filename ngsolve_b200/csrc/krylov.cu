@@ -335,7 +335,11 @@ __global__ void __launch_bounds__(256) cg_fused_kernel(const CgVecs v, int sub)
     }
     double2 total;
     if (grid_finish(accr, acci, v.partials, v.counter, &total)) {
-        if (v.dot_out != nullptr) { v.dot_out[0] = total.x; v.dot_out[1] = total.y; }
+        if (v.R != nullptr) {
+            pr_push(*v.R, total.x, total.y);
+            total = pr_wait_sum(*v.R);
+        }
+        if (v.R == nullptr && v.dot_out != nullptr) { v.dot_out[0] = total.x; v.dot_out[1] = total.y; }
         else if (MODE == 0) cg_finalize_init(st, total, v.hist);
         else cg_finalize_wdn(st, total, v.hist);
     }
@@ -856,6 +860,7 @@ static int check_solver_args(const ngsb_csr *A, const ngsb_jacobi *C, const ngsb
 extern "C" int ngsb_cg_solve(const ngsb_csr *A, const ngsb_jacobi *C, const ngsb_vec *f, ngsb_vec *u, double prec, int maxsteps,
                              int ip_mode, int initialize, int *steps, double *history, int hist_cap, int *nhist)
 {
+    NvtxRange nv("CG solver");                      // the reference's Timer name, linalg/cg.cpp:511
     NGSB_TRY(check_solver_args(A, C, f, u, "CGSolver::Mult"));
     NGSB_REQUIRE(ip_mode >= 0 && ip_mode <= 2, "CGSolver::Mult: bad ip_mode %d", ip_mode);
     NGSB_REQUIRE((A->kind == NGSB_COMPLEX) == (ip_mode != NGSB_IP_REAL), "CGSolver::Mult: ip_mode %d does not fit matrix kind %d", ip_mode, A->kind);
@@ -897,6 +902,7 @@ extern "C" int ngsb_gmres_solve(const ngsb_csr *A, const ngsb_jacobi *C, const n
 int ngsb::gmres_solve_impl(const ngsb_csr *A, const ngsb_jacobi *C, const ngsb_vec *fvec, ngsb_vec *xvec, double prec,
                            int maxsteps, int initialize, int *steps, double *history, int hist_cap, int *nhist, const GmresDist *dist)
 {
+    NvtxRange nv("GMRES solver");
     NGSB_TRY(check_solver_args(A, C, fvec, xvec, "GMRESSolver::Mult"));
     NGSB_REQUIRE(maxsteps >= 1, "GMRESSolver::Mult: maxsteps < 1");
     ngsb_ctx *ctx = A->ctx;

@@ -15,6 +15,9 @@ struct CgVecs {
                                // (masked inner product, parallel/parallelvvector.cpp:305-314); NULL: all
     double *dot_out;           // distributed: the local dot goes here (2 doubles) and the scalar
                                // step runs after the all-reduce; NULL: last block finalises
+    const PeerReduce *R;       // distributed, peer-memory mode: the finishing thread all-reduces the dot over the ranks itself
+                               // (partials into the peers' mailboxes, rank-ordered sum) and does the scalar step -- no
+                               // separate finalize launch; takes precedence over dot_out
     uint64_t n;                // entries
     CgState *state;
     double *hist;

@@ -188,6 +188,7 @@ static int rcm_bfs(RcmWork &W, uint32_t root, uint32_t *queue, uint32_t *ecc, ui
 // new -> old permutation (d_perm) and its inverse (d_iperm), n entries each (device, caller-allocated)
 int rcm_device(ngsb_ctx *ctx, size_t n_, const uint64_t *d_rowptr, const int32_t *d_col, int max_components, uint32_t *d_perm, uint32_t *d_iperm)
 {
+    NvtxRange nv("Cuthill-McKee ordering");
     NGSB_REQUIRE(n_ < 0xf0000000ull / 2, "rcm: too many rows");
     const uint32_t n = (uint32_t)n_;
     if (n == 0) return NGSB_OK;

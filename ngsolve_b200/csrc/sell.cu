@@ -21,6 +21,7 @@
 // stripe of the schedule as one moving window and x lines are shared through L1/L2); it fuses
 // y = s A x (+ y), the dot <dotvec, result> and the CG scalar step (deterministic last-block finish).
 #include "spmv.cuh"
+#include "peer.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
 
@@ -59,6 +60,7 @@ struct SellParams {
     const uint32_t *slice_list;   // LIST kernels: scheduled positions to process (ascending), nlist of them
     uint32_t nlist;
     const double *dot_add;        // (re,im) added to the fused dot by the finishing thread, or NULL
+    const SellPush *push;         // PUSH kernels: interface rows go straight to the neighbours (descriptor in device memory)
 };
 
 __device__ __forceinline__ double2 ldg_stream_d2(const double2 *p)
@@ -145,16 +147,41 @@ __device__ __forceinline__ double warp_sum_s(double v)
     return v;
 }
 
+// interface row of a PUSH product: its result (already stored at y) goes to every sharer's receive area now (P2P stores over
+// NVLink), at the place that rank's exchange table expects it -- what halo_push_kernel did in a launch of its own after the
+// product.  Out of line: about 3 % of the slices come here, the streaming loops keep their 64 registers.
+__device__ __noinline__ void sell_push_row(const SellPush *Pp, uint32_t s, int lane, const double *y, uint32_t row)
+{
+    const SellPush &P = *Pp;
+    const uint32_t rec = P.slice_if[s];
+    if (rec == 0xffffffffu) return;
+    const int k = P.lane_if[(size_t)rec * 32 + lane];
+    if (k < 0) return;
+    const PeerHalo *H = P.H;
+    const int es = P.es;
+    const double *yy = y + (size_t)es * row;
+    // sequence number / parity of the exchange this product feeds (the previous one was completed by its unpack kernel)
+    const unsigned long long xseq = *(volatile const unsigned long long *)H->seq + 1;
+    for (uint32_t q = P.if_first[k]; q < P.if_first[k + 1]; q++) {
+        const uint32_t kk = P.if_pos[q];
+        int pq = 0;
+        while (kk >= H->peer_off[pq + 1]) pq++;
+        double *dst = H->peer_recv[pq] + (xseq & 1) * H->peer_stride[pq] + (H->peer_my_off[pq] + (kk - H->peer_off[pq])) * (size_t)es;
+        for (int c = 0; c < es; c++) dst[c] = yy[c];
+    }
+}
+
 // VAR (tuning variants of the real-valued inner loop): 0 = 4 packets per step; 1 = 2 packets per step;
 // 2 = 4 packets per step with the next step's values/columns prefetched before the gathers of this one
 // LIST: walk p.slice_list instead of the whole schedule (interface-first split of the distributed product)
-template <int KIND, int VAR, int MINB, bool POL = false, bool LIST = false>
+template <int KIND, int VAR, int MINB, bool POL = false, bool LIST = false, bool PUSH = false>
 __global__ void __launch_bounds__(256, MINB) sell_spmv_kernel(const SellParams p)
 {
     __shared__ double red[64];
     __shared__ int s_last;
     if (p.state != nullptr && p.state->done) return;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+
     double dr = 0.0, di = 0.0;
     const uint64_t nwalk = LIST ? (uint64_t)p.nlist : (uint64_t)p.nslices;
     for (uint64_t it = (uint64_t)blockIdx.x * 8 + wid; it < nwalk; it += (uint64_t)gridDim.x * 8) {
@@ -451,9 +478,11 @@ __global__ void __launch_bounds__(256, MINB) sell_spmv_kernel(const SellParams p
                     dr += v[0] * r0 + v[1] * r1 + v[2] * r2;
                 }
             }
+            if (PUSH) sell_push_row(p.push, (uint32_t)s, lane, p.y, row);
         }
     }
     if (!p.epi) return;
+    if (PUSH) __threadfence_system();        // this thread's peer stores are visible system-wide before the block takes its ticket
     // deterministic grid-wide finish of the fused dot (+ scalar step of CG)
     dr = warp_sum_s(dr);
     di = warp_sum_s(di);
@@ -487,6 +516,15 @@ __global__ void __launch_bounds__(256, MINB) sell_spmv_kernel(const SellParams p
         if (p.dot_add != nullptr) { a += p.dot_add[0]; b += p.dot_add[1]; }
         if (p.epi == EPI_DOT_OUT) { p.dot_out[0] = a; p.dot_out[1] = b; }
         else if (p.epi == EPI_CG_KSS) cg_finalize_kss(p.state, make_double2(a, b));
+        if (PUSH) {
+            // every block's stores are out (each fenced before its ticket): tell the neighbours, and send this rank's partial
+            // of <s, A s> on its way to all ranks (the unpack kernel sums the partials and does al = wd / kss)
+            const PeerHalo *H = p.push->H;
+            const unsigned long long xseq = *(volatile const unsigned long long *)H->seq + 1;
+            __threadfence_system();
+            for (int q = 0; q < H->npeers; q++) st_release_sys(H->peer_flags[q] + (xseq & 1) * NGSB_MAX_RANKS + H->rank, xseq);
+            if (p.push->R) pr_push(*p.push->R, a, b);
+        }
     }
 }
 
@@ -761,6 +799,7 @@ __global__ void __launch_bounds__(256) sell_c16_count_kernel(const uint64_t *__r
 
 int sell_build(ngsb_csr *A, const uint64_t *h_rowptr)
 {
+    NvtxRange nv("SELL-32 build");
     ngsb_ctx *ctx = A->ctx;
     const size_t ms = kind_matscalars(A->kind);
     const uint32_t ns = (uint32_t)((A->h + 31) / 32);
@@ -975,6 +1014,11 @@ int sell_launch(const SpmvArgs &a)
     p.partials = ctx->d_partials; p.counter = ctx->d_counter;
     p.slice_list = a.slice_list; p.nlist = a.nlist; p.dot_add = a.dot_add;
     const bool list = a.slice_list != nullptr;
+    const bool push = a.push != nullptr;
+    if (push) {
+        NGSB_REQUIRE(a.epi != EPI_NONE && !list && !a.user_rows, "SpMV: the fused neighbour exchange needs the fused dot and the whole schedule");
+        p.push = a.push;
+    }
     if (A->novf && !a.skip_overflow) {
         SpanGuard g(ctx, KC_SPMV);
         if (A->kind == NGSB_REAL) sell_overflow_kernel<NGSB_REAL><<<A->novf, 256, 0, ctx->stream>>>(A->d_ovf_ptr, A->d_ovf_col, A->d_ovf_val, a.x, A->d_ovf_sum, a.state);
@@ -986,7 +1030,11 @@ int sell_launch(const SpmvArgs &a)
     typedef void (*kern_t)(const SellParams);
     kern_t kern;
     const long var = ctx->sell_variant;
-    if (list) {
+    if (push) {
+        if (A->kind == NGSB_REAL) kern = sell_spmv_kernel<NGSB_REAL, 2, 4, false, false, true>;
+        else if (A->kind == NGSB_COMPLEX) kern = sell_spmv_kernel<NGSB_COMPLEX, 2, 4, false, false, true>;
+        else kern = sell_spmv_kernel<NGSB_BLOCK3, 0, 5, false, false, true>;
+    } else if (list) {
         // interface-first split: the default loops only
         if (A->kind == NGSB_REAL) kern = sell_spmv_kernel<NGSB_REAL, 2, 4, false, true>;
         else if (A->kind == NGSB_COMPLEX) kern = sell_spmv_kernel<NGSB_COMPLEX, 2, 4, false, true>;

@@ -759,6 +759,7 @@ extern "C" int ngsb_csr_create(ngsb_ctx *ctx, size_t height, size_t width, size_
 {
     NGSB_REQUIRE(ctx && rowptr && out && (nnz == 0 || (col && val)), "ngsb_csr_create: NULL argument");
     NGSB_REQUIRE(kind_valid(kind), "ngsb_csr_create: bad kind %d", kind);
+    NvtxRange nv("CreateDeviceMatrix (upload, reorder, SELL build)");
     NGSB_TRY(validate_host_csr(height, width, nnz, rowptr, col));
     NGSB_CUDA(cudaSetDevice(ctx->device));
     ngsb_csr *A = new ngsb_csr();
@@ -861,6 +862,7 @@ static int check_mult_args(const ngsb_csr *A, const ngsb_vec *x, const ngsb_vec 
 
 extern "C" int ngsb_csr_multadd(const ngsb_csr *A, const double s[2], const ngsb_vec *x, ngsb_vec *y)
 {
+    NvtxRange nv("SparseMatrix::MultAdd");
     NGSB_TRY(check_mult_args(A, x, y, "SparseMatrix::MultAdd"));
     NGSB_REQUIRE(s, "ngsb_csr_multadd: s is NULL");
     NGSB_REQUIRE(A->kind == NGSB_COMPLEX || s[1] == 0.0, "MultAdd(complex) called for real matrix");   // sparsematrix_impl.hpp:394
@@ -873,6 +875,7 @@ extern "C" int ngsb_csr_multadd(const ngsb_csr *A, const double s[2], const ngsb
 
 extern "C" int ngsb_csr_mult(const ngsb_csr *A, const ngsb_vec *x, ngsb_vec *y)
 {
+    NvtxRange nv("SparseMatrix::Mult");
     NGSB_TRY(check_mult_args(A, x, y, "BaseMatrix::Mult"));
     NGSB_CUDA(cudaSetDevice(A->ctx->device));
     SpmvArgs a;

@@ -68,7 +68,25 @@ struct ngsb_csr {
     uint64_t uid = 0;                  // unique per created matrix (key of cached CUDA graphs)
 };
 
+struct PeerHalo;
+struct PeerReduce;
+
 namespace ngsb {
+
+// Product + neighbour exchange in ONE kernel (distributed CG, peer-memory data path): a warp that has finished a slice
+// holding interface rows stores those rows' results straight into the neighbours' receive areas over NVLink, while the
+// other warps keep multiplying; the kernel's last block publishes the sequence flags and this rank's partial of <s, A s>.
+// Replaces the separate halo_push_kernel of ParallelBaseVector::Cumulate (parallel/parallelvvector.cpp:247-272: ISend of
+// the interface values after the local MultAdd).
+struct SellPush {
+    const PeerHalo *H;
+    const PeerReduce *R;
+    const uint32_t *slice_if;     // per scheduled slice position: index of its interface record, 0xffffffff = no interface row
+    const int32_t *lane_if;       // [records * 32]: interface dof index of the lane's row, -1 = interior row
+    const uint32_t *if_first;     // per interface dof: its copies' positions if_pos[if_first[k] .. if_first[k+1]) in the packed
+    const uint32_t *if_pos;       //   neighbour-major exchange list (the tables the unpack kernel adds by)
+    int es;
+};
 
 // epilogue selector for the fused dot
 enum SpmvEpi { EPI_NONE = 0, EPI_DOT_OUT = 1, EPI_CG_KSS = 2 };
@@ -97,6 +115,8 @@ struct SpmvArgs {
     bool skip_overflow;
     // (inner matrices) y and dotvec are in the caller's numbering: index them through d_row_user instead of d_row_of
     bool user_rows;
+    // fused neighbour exchange (see SellPush; DEVICE pointer); needs epi != EPI_NONE (the last-block finish publishes the flags)
+    const SellPush *push;
 };
 
 int spmv_launch(const SpmvArgs &a);

@@ -557,6 +557,7 @@ extern "C" int ngsb_ctx_set_option(ngsb_ctx *ctx, const char *name, long value)
     else if (!strcmp(name, "reorder_min_rows")) { NGSB_REQUIRE(value >= 0, "reorder_min_rows must be >= 0"); ctx->reorder_min_rows = value; }
     else if (!strcmp(name, "cg_chunked")) { NGSB_REQUIRE(value == 0 || value == 1, "cg_chunked must be 0 or 1"); ctx->cg_chunked = value; }
     else if (!strcmp(name, "cg_fold_u")) { NGSB_REQUIRE(value == 0 || value == 1, "cg_fold_u must be 0 or 1"); ctx->cg_fold_u = value; }
+    else if (!strcmp(name, "dist_fused_push")) { NGSB_REQUIRE(value == 0 || value == 1, "dist_fused_push must be 0 or 1"); ctx->dist_fused_push = value; }
     else if (!strcmp(name, "dist_overlap")) { NGSB_REQUIRE(value == 0 || value == 1, "dist_overlap must be 0 or 1"); ctx->dist_overlap = value; }
     else if (!strcmp(name, "sell_variant")) { NGSB_REQUIRE(value >= 0 && value <= 8, "sell_variant out of range"); ctx->sell_variant = value; }
     else if (!strcmp(name, "sell_schedule")) { NGSB_REQUIRE(value >= 0 && value <= 2, "sell_schedule must be 0 (off), 1 (auto), 2 (on)"); ctx->sell_schedule = value; }

@@ -1,4 +1,7 @@
-"""Pure-Python Krylov solvers in the style of ngsolve.krylovspace (python/krylovspace.py):
+"""TEST HELPER (not part of the product package): pure-Python Krylov solvers in the style of ngsolve.krylovspace
+(python/krylovspace.py), so that the op-by-op device path of the ctypes mirror ngsolve_b200.la can be driven on a box
+without NGSolve.  The reference's OWN file runs on the real adapter in tests/test_gpu_dropin.py.
+
 they only use the BaseMatrix / BaseVector interface (`w.data = A * s`, `InnerProduct`,
 `+=`), so they exercise the op-by-op device path -- the way an unchanged NGSolve script
 reaches the library through the generic virtual calls.
@@ -11,7 +14,7 @@ from math import sqrt
 
 import numpy as np
 
-from .la import BaseMatrix, BaseVector, Norm, Projector  # noqa: F401
+from ngsolve_b200.la import BaseMatrix, BaseVector, Norm, Projector  # noqa: F401
 
 
 class LinearSolver(BaseMatrix):

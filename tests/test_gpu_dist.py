@@ -49,6 +49,8 @@ def _worker(rank, world, port, cfg, out):
         ctx.set_option("dist_overlap", 1)
     if cfg.get("fold"):
         ctx.set_option("cg_fold_u", 1)
+    if "fused_push" in cfg:
+        ctx.set_option("dist_fused_push", cfg["fused_push"])
     G = tuple(cfg.get("G", G_DEFAULT))
     boxes = [W.FemBox(n, offset=o, global_n=G, **_box_kw(cfg)) for n, o in W.slab_partition(G, world)]
     box = boxes[rank]
@@ -157,6 +159,18 @@ def test_four_ranks_interface_first_overlap():
 
 def test_two_ranks_cg_fold_u():
     _run(dict(CASES[1], devices="same", p2p=1, fold=True))
+
+
+@pytest.mark.parametrize("case", CASES[:3], ids=IDS[:3])
+def test_two_ranks_separate_push_kernel(case):
+    """option dist_fused_push = 0: product, then halo_push_kernel, then unpack, then a finalize launch per reduction (the round-1
+    sequence); the default since round 2 pushes the interface rows from inside the product kernel and all-reduces <d,w> in the
+    update kernel (4 launches per iteration instead of 6) -- both must reproduce the one-GPU solve"""
+    _run(dict(case, devices="same", p2p=1, fused_push=0))
+
+
+def test_four_ranks_separate_push_kernel():
+    _run(dict(order=2, kind=REAL, solver="cg", devices="same", p2p=1, G=(4, 4, 8), fused_push=0), world=4)
 
 
 def test_four_ranks_on_one_gpu_peer_memory():

@@ -174,7 +174,7 @@ def test_cg_fused_matches_reference(la, sysm, graph, monkeypatch):
 def test_cg_op_by_op_paths(la, name):
     """The generic virtual-call path (what an unchanged script drives): the C++-style loop on
     arbitrary operators and the python krylovspace.CGSolver, both on device vectors."""
-    from ngsolve_b200 import krylovspace
+    import krylovspace_on_la as krylovspace
     g = load_golden(name)
     A = host_matrix(la, g)
     dev = A.CreateDeviceMatrix()
@@ -216,7 +216,7 @@ def test_gmres_matches_reference(la, name):
 
 def test_python_gmres_solver(la):
     """tests/pytest/test_solvers.py:59-79 flavour: python GMResSolver on the unit-square p4 problem."""
-    from ngsolve_b200 import krylovspace
+    import krylovspace_on_la as krylovspace
     g = load_golden("square_h1p4_testsolvers")
     dev = host_matrix(la, g).CreateDeviceMatrix()
     jac = dev.CreateSmoother(la.BitArray(g["freebits"]))
@@ -446,7 +446,7 @@ def test_device_scalars_drive_a_cg_iteration(la):
 def test_projector_and_diagonal_matrix(la):
     """Projector(freedofs, True) as the default 'preconditioner' of the python solvers and
     DiagonalMatrix, both as device operators."""
-    from ngsolve_b200 import krylovspace
+    import krylovspace_on_la as krylovspace
     g = load_golden("poisson_h1p3")
     n = int(g["n"])
     free = np.unpackbits(g["freebits"], bitorder="little")[:n].astype(bool)

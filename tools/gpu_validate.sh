@@ -9,6 +9,9 @@ nproc >> $O/${TAG}_gpu.txt; free -g | head -2 >> $O/${TAG}_gpu.txt
 ( time timeout 1200 python -m pytest tests -m gpu -q ) > $O/${TAG}_pytest_gpu.log 2>&1
 tail -3 $O/${TAG}_pytest_gpu.log
 timeout 300 python __graft_entry__.py smoke > $O/${TAG}_smoke.log 2>&1; tail -1 $O/${TAG}_smoke.log
+# memory checker over the smoke solve and the reorder tests (racecheck/initcheck are too slow for the suite; memcheck is the gate)
+timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python __graft_entry__.py smoke > $O/${TAG}_sanitizer_smoke.log 2>&1; echo "sanitizer smoke rc=$?"; tail -3 $O/${TAG}_sanitizer_smoke.log
+timeout 1200 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_reorder.py -m gpu -q -x -k "rcm or reorder_equals or reorder_long" > $O/${TAG}_sanitizer_reorder.log 2>&1; echo "sanitizer reorder rc=$?"; tail -3 $O/${TAG}_sanitizer_reorder.log
 timeout 600 python bench.py > $O/${TAG}_bench_n1.json 2> $O/${TAG}_bench_n1.err; cat $O/${TAG}_bench_n1.json
 timeout 300 python bench.py --impl reference > $O/${TAG}_bench_reference_arm.json 2> $O/${TAG}_bench_ref.err; cat $O/${TAG}_bench_reference_arm.json
 timeout 900 python tools/bench_configs.py c1 c2 c4 c5 --out $O/${TAG}_configs.jsonl > $O/${TAG}_configs.log 2>&1; tail -5 $O/${TAG}_configs.log
