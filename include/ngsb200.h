@@ -86,6 +86,9 @@ int ngsb_ctx_launch_count(const ngsb_ctx *ctx, uint64_t *count);
  *     "sell_c16"         0/1: use the 16-bit column offsets of real matrices (default 1; also read at creation)
  *     "timing"           0/1: record an event pair around every launch (ngsb_ctx_kernel_time)
  *   read when a matrix is created:
+ *     "csr_keep"         the uploaded column / value arrays after the SELL copy exists: 1 keep, 0 release (rebuilt from the SELL copy
+ *                        when CSR(), CreateTranspose, Reorder or the block-Jacobi constructor ask for them; the Jacobi
+ *                        constructor reads the diagonal out of the SELL copy), -1 automatic (default) = release above 4 GiB
  *     "reorder"          internal dof reordering of square matrices (csrc/reorder.cu): -1 automatic (default), 0 off, 1 always.
  *                        The matrix keeps the caller's numbering at the interface; products and the fused solvers run on
  *                        P A P^T with P = Cuthill-McKee of the pattern (ngsb_csr_rcm).  Automatic = at least
@@ -187,6 +190,9 @@ int ngsb_csr_layout(const ngsb_csr *A, uint64_t *sell_entries, uint32_t *overflo
  * store 16-bit column offsets per slice where the columns of one entry step lie within 65535 of each
  * other: 10.125 instead of 12 bytes per entry); *c16_entries = padded entries in such slices */
 int ngsb_csr_stream_bytes(const ngsb_csr *A, double *bytes, uint64_t *c16_entries);
+/* device memory the matrix holds right now: row pointers + (if resident) the uploaded CSR arrays [+ permutation tables];
+ * the SELL copy the products stream; whether the CSR arrays are resident (option csr_keep) */
+int ngsb_csr_memory(const ngsb_csr *A, uint64_t *csr_bytes, uint64_t *sell_bytes, int *csr_resident);
 /* algorithmic bytes of one Mult: nnz*(b*b*S+4) + 4*h + 2*N*S */
 int ngsb_csr_mult_bytes(const ngsb_csr *A, double *bytes);
 

@@ -64,6 +64,7 @@ PROTOTYPES = {
     "ngsb_csr_mult": [_vp, _vp, _vp],
     "ngsb_csr_reorder": [_vp, _vp, _pvp],
     "ngsb_csr_rcm": [_vp, _vp],
+    "ngsb_csr_memory": [_vp, _vp, _vp, _vp],
     "ngsb_csr_reorder_info": [_vp, _vp, _vp, _vp],
     "ngsb_csr_download": [_vp, _vp, _vp, _vp],
     "ngsb_csr_mult_bytes": [_vp, C.POINTER(_d)],

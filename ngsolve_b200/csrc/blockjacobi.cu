@@ -289,7 +289,7 @@ static int bj_build(ngsb_ctx *ctx, size_t ndof, const ngsb_csr *A, const double 
         }
         cu(cudaMemcpyAsync(J->d_inv, cm.data(), cm.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         cu(cudaStreamSynchronize(ctx->stream));
-    } else if (rc == NGSB_OK && total) {
+    } else if (rc == NGSB_OK && total && (rc = csr_ensure(A)) == NGSB_OK) {
         const size_t threads = total * 32;
         bj_extract_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, ctx->stream>>>(A->d_rowptr, A->d_col, A->d_val, J->d_first, J->d_moff,
                                                                                       J->d_dofs, d_slot_block, total, J->d_inv);

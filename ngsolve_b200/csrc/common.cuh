@@ -90,6 +90,8 @@ struct ngsb_ctx {
                                  // the product kernel itself (no separate push kernel); read when a parallel matrix is created
     long dist_overlap = 0;       // distributed CG: interface slices first, push, interior slices while the values travel
                                  // (read when a parallel matrix is created; peer-memory data path only)
+    long csr_keep = -1;          // CSR column/value arrays after the SELL copy exists: 1 keep, 0 release (rebuilt from the SELL copy on
+                                 // demand), -1 automatic = release above 4 GiB (read when a matrix is created)
     long reorder = -1;           // internal Cuthill-McKee reordering of square matrices: 0 off, 1 always, -1 automatic
                                  // (read when a matrix is created)
     long reorder_min_rows = 32768;   // automatic mode: smaller matrices keep their numbering

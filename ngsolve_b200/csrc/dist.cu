@@ -79,6 +79,7 @@ struct ngsb_parmat {
     uint32_t *d_slice_if = nullptr;
     int32_t *d_lane_if = nullptr;
     ngsb::SellPush *d_push_desc = nullptr;        // device copy of the descriptor
+    uint32_t *d_slice_src_flagged = nullptr;      // the local matrix' schedule, bit 31 = slice holds interface rows
     // cached CUDA graph of one batch of CG iterations (peer-memory mode)
     cudaGraphExec_t graph_exec = nullptr;
     const void *g_key[9] = {};
@@ -692,8 +693,12 @@ static int parmat_setup_fused_push(ngsb_parmat *P, const std::vector<int32_t> &i
         for (int l = 0; l < 32 && !any; l++) any = row_of[base + l] != 0xffffffffu && ifidx[row_of[base + l]] >= 0;
         if (!any) continue;
         slice_if[t] = (uint32_t)(lane_if.size() / 32);
+        slice_src[t] |= 0x80000000u;
         for (int l = 0; l < 32; l++) lane_if.push_back(row_of[base + l] != 0xffffffffu ? ifidx[row_of[base + l]] : -1);
     }
+    NGSB_REQUIRE(ns < 0x80000000u, "parallel matrix: too many slices");
+    NGSB_CUDA(cudaMalloc(&P->d_slice_src_flagged, std::max<size_t>(1, ns) * sizeof(uint32_t)));
+    NGSB_CUDA(cudaMemcpyAsync(P->d_slice_src_flagged, slice_src.data(), (size_t)ns * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
     NGSB_CUDA(cudaMalloc(&P->d_slice_if, std::max<size_t>(1, ns) * sizeof(uint32_t)));
     NGSB_CUDA(cudaMalloc(&P->d_lane_if, std::max<size_t>(32, lane_if.size()) * sizeof(int32_t)));
     NGSB_CUDA(cudaMemcpyAsync(P->d_slice_if, slice_if.data(), (size_t)ns * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
@@ -858,7 +863,7 @@ extern "C" int ngsb_parmat_destroy(ngsb_parmat *P)
         if (P->peer_halo[q]) cudaIpcCloseMemHandle(P->peer_halo[q]);
     cudaFree(P->d_H); cudaFree(P->d_local); cudaFree(P->halo_mem);
     cudaFree(P->d_exdofs); cudaFree(P->d_send); cudaFree(P->d_recv);
-    cudaFree(P->d_if_dof); cudaFree(P->d_if_first); cudaFree(P->d_if_pos); cudaFree(P->d_if_nlow); cudaFree(P->d_master); cudaFree(P->d_slice_if); cudaFree(P->d_lane_if); cudaFree(P->d_push_desc);
+    cudaFree(P->d_if_dof); cudaFree(P->d_if_first); cudaFree(P->d_if_pos); cudaFree(P->d_if_nlow); cudaFree(P->d_master); cudaFree(P->d_slice_if); cudaFree(P->d_lane_if); cudaFree(P->d_push_desc); cudaFree(P->d_slice_src_flagged);
     cudaFree(P->d_list_bnd); cudaFree(P->d_list_int); cudaFree(P->d_red_b);
     delete P;
     return NGSB_OK;
@@ -963,7 +968,7 @@ static int enqueue_par_iteration(const ngsb_parmat *P, const CgVecs &v, double *
         NGSB_TRY(cg_launch_dir(ctx, A->kind, v));
         return NGSB_OK;
     }
-    if (P->fused_push) a.push = P->d_push_desc;                                  // interface rows leave for the neighbours from inside the product
+    if (P->fused_push) { a.push = P->d_push_desc; a.push_slice_src = P->d_slice_src_flagged; }                                  // interface rows leave for the neighbours from inside the product
     NGSB_TRY(spmv_launch(a));                                                   // as = A s (DISTRIBUTED), local <s,as>
     if (P->p2p) {
         if (P->fused_push) {

@@ -213,6 +213,7 @@ int jacobi_extract(const ngsb_csr *A, ngsb_jacobi *J, int *d_status)
     ngsb_ctx *ctx = A->ctx;
     if (A->h == 0) return NGSB_OK;
     SpanGuard g(ctx, KC_OTHER);
+    if (A->csr_released) return sell_extract_diag(A, J->d_bits, J->d_invdiag, d_status);     // no rebuild for the diagonal (csrview.cu)
     int grid = grid_for_n(ctx, A->h);
     if (A->kind == NGSB_REAL) jacobi_extract_kernel<NGSB_REAL><<<grid, 256, 0, ctx->stream>>>(A->d_rowptr, A->d_col, A->d_val, J->d_bits, J->d_invdiag, A->h, d_status);
     else if (A->kind == NGSB_COMPLEX) jacobi_extract_kernel<NGSB_COMPLEX><<<grid, 256, 0, ctx->stream>>>(A->d_rowptr, A->d_col, A->d_val, J->d_bits, J->d_invdiag, A->h, d_status);

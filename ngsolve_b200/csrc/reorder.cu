@@ -335,7 +335,7 @@ int csr_permute_device(const ngsb_csr *A, const uint32_t *d_perm, const uint32_t
 {
     ngsb_ctx *ctx = A->ctx;
     const size_t n = A->h, ms = kind_matscalars(A->kind), slack = 16;
-    NGSB_REQUIRE(A->d_col != nullptr || A->nnz == 0, "Reorder: the CSR arrays of this matrix were released");
+    NGSB_TRY(csr_ensure(A));
     uint64_t *nrp = nullptr;
     int32_t *ncol = nullptr;
     double *nval = nullptr;
@@ -553,7 +553,7 @@ extern "C" int ngsb_csr_rcm(const ngsb_csr *A, uint64_t *perm)
 {
     NGSB_REQUIRE(A && perm, "ngsb_csr_rcm: NULL argument");
     NGSB_REQUIRE(A->h == A->w, "ngsb_csr_rcm: matrix must be square");
-    NGSB_REQUIRE(A->d_col != nullptr || A->nnz == 0, "ngsb_csr_rcm: the CSR arrays of this matrix were released");
+    NGSB_TRY(csr_ensure(A));
     ngsb_ctx *ctx = A->ctx;
     NGSB_CUDA(cudaSetDevice(ctx->device));
     const size_t n = A->h;

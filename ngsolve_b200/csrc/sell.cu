@@ -188,7 +188,11 @@ __global__ void __launch_bounds__(256, MINB) sell_spmv_kernel(const SellParams p
         const uint64_t s = LIST ? (uint64_t)p.slice_list[it] : it;
         const uint64_t off = p.slice_off[s];
         const uint32_t width = (uint32_t)((p.slice_off[s + 1] - off) >> 5);     // entries per lane
-        const uint64_t src = p.slice_src[s];
+        // PUSH launches get a copy of the schedule whose top bit marks the slices holding interface rows: no extra load, no
+        // extra register in the streaming loops
+        const uint32_t src_raw = p.slice_src[s];
+        const bool has_if = PUSH && (src_raw >> 31);
+        const uint64_t src = PUSH ? (src_raw & 0x7fffffffu) : src_raw;
         const uint32_t slot = (uint32_t)(src * 32 + lane);
         const uint32_t row = p.row_of[slot];
         double s0 = 0.0, s1 = 0.0, s2 = 0.0;
@@ -478,7 +482,7 @@ __global__ void __launch_bounds__(256, MINB) sell_spmv_kernel(const SellParams p
                     dr += v[0] * r0 + v[1] * r1 + v[2] * r2;
                 }
             }
-            if (PUSH) sell_push_row(p.push, (uint32_t)s, lane, p.y, row);
+            if (PUSH && has_if) sell_push_row(p.push, (uint32_t)s, lane, p.y, row);
         }
     }
     if (!p.epi) return;
@@ -942,6 +946,14 @@ int sell_build(ngsb_csr *A, const uint64_t *h_rowptr)
         NGSB_CUDA(cudaStreamSynchronize(ctx->stream));
         cudaFree(d_cnt);
         A->sell_c16_entries = cnt;
+        if ((double)cnt < 0.25 * (double)A->sell_entries) {
+            // hardly any slice qualifies (unstructured numberings at scale: 3 % on the 13.6 M-dof netgen system): the 2 bytes
+            // per entry of offset storage are better spent elsewhere, every slice keeps its 32-bit columns
+            cudaFree(A->d_scol16); A->d_scol16 = nullptr;
+            cudaFree(A->d_sbase); A->d_sbase = nullptr;
+            cudaFree(A->d_slice_c16); A->d_slice_c16 = nullptr;
+            A->sell_c16_entries = 0;
+        }
     }
     // ---- 4. overflow CSR of the rows longer than cap
     if (novf) {
@@ -1016,8 +1028,9 @@ int sell_launch(const SpmvArgs &a)
     const bool list = a.slice_list != nullptr;
     const bool push = a.push != nullptr;
     if (push) {
-        NGSB_REQUIRE(a.epi != EPI_NONE && !list && !a.user_rows, "SpMV: the fused neighbour exchange needs the fused dot and the whole schedule");
+        NGSB_REQUIRE(a.epi != EPI_NONE && !list && !a.user_rows && a.push_slice_src, "SpMV: the fused neighbour exchange needs the fused dot and the whole schedule");
         p.push = a.push;
+        p.slice_src = a.push_slice_src;
     }
     if (A->novf && !a.skip_overflow) {
         SpanGuard g(ctx, KC_SPMV);

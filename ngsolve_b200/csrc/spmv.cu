@@ -565,7 +565,7 @@ int spmv_launch(const SpmvArgs &a)
         }
         return sell_launch(a);
     }
-    NGSB_REQUIRE(!A->csr_released, "SpMV: the CSR kernels (spmv_algo 1/2) need the CSR arrays, which this matrix released");
+    NGSB_REQUIRE(!A->csr_released, "SpMV: the CSR kernels (spmv_algo 1/2) need the CSR arrays, which this matrix released (create it with option csr_keep = 1)");
     NGSB_REQUIRE(a.slice_list == nullptr, "SpMV: a slice list needs the SELL kernel (spmv_algo 0 or 3)");
     const bool stream = ctx->spmv_algo != 1;
     if (stream) {
@@ -701,9 +701,15 @@ static int finish_create(ngsb_csr *A, const uint64_t *h_rowptr, bool allow_reord
         // netgen-style numberings: multiply P A P^T instead (reorder.cu); the SELL copy then belongs to the inner matrix
         bool made = false;
         NGSB_TRY(csr_maybe_reorder(A, &made));
-        if (made) return NGSB_OK;
+        if (made) {
+            if (csr_release_wanted(A)) csr_release(A);
+            return NGSB_OK;
+        }
     }
-    return sell_build(A, h_rowptr);
+    NGSB_TRY(sell_build(A, h_rowptr));
+    // the products only stream the SELL copy: large matrices give the uploaded column / value arrays back (csrview.cu)
+    if (allow_reorder && (ctx->spmv_algo == 0 || ctx->spmv_algo == 3) && csr_release_wanted(A)) csr_release(A);
+    return NGSB_OK;
 }
 
 static int alloc_csr(ngsb_csr *A)
@@ -921,7 +927,7 @@ extern "C" int ngsb_csr_multadd_multi(const ngsb_csr *A, size_t nvec, const doub
 extern "C" int ngsb_csr_download(const ngsb_csr *A, uint64_t *rowptr, int32_t *col, void *val)
 {
     NGSB_REQUIRE(A, "ngsb_csr_download: A is NULL");
-    NGSB_REQUIRE(!A->csr_released, "ngsb_csr_download: the CSR arrays of this matrix were released");
+    if ((col || val) && A->nnz) NGSB_TRY(csr_ensure(A));
     ngsb_ctx *ctx = A->ctx;
     NGSB_CUDA(cudaSetDevice(ctx->device));
     const size_t ms = kind_matscalars(A->kind);

@@ -117,6 +117,7 @@ struct SpmvArgs {
     bool user_rows;
     // fused neighbour exchange (see SellPush; DEVICE pointer); needs epi != EPI_NONE (the last-block finish publishes the flags)
     const SellPush *push;
+    const uint32_t *push_slice_src;   // the matrix' slice schedule with bit 31 set on the slices that hold interface rows (device)
 };
 
 int spmv_launch(const SpmvArgs &a);
@@ -124,6 +125,11 @@ int sell_build(ngsb_csr *A, const uint64_t *h_rowptr);
 void sell_free(ngsb_csr *A);
 int sell_launch(const SpmvArgs &a);
 // y_k += alpha_k * A * x_k for four real vectors in one sweep over the matrix (MultiVector MultAdd)
+// csrview.cu: the CSR column / value arrays on demand (option csr_keep)
+void csr_release(ngsb_csr *A);
+bool csr_release_wanted(const ngsb_csr *A);
+int csr_ensure(const ngsb_csr *A);
+int sell_extract_diag(const ngsb_csr *A, const uint8_t *d_bits, double *d_diag, int *d_status);
 // reorder.cu
 int csr_maybe_reorder(ngsb_csr *A, bool *made);
 int launch_perm_gather(ngsb_ctx *ctx, const double *in, const uint32_t *perm, size_t n, int es, double *out);

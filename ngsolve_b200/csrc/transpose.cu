@@ -171,6 +171,7 @@ extern "C" int ngsb_csr_transpose(const ngsb_csr *A, ngsb_csr **out)
     uint64_t *t_rp = nullptr;
     int32_t *t_col = nullptr;
     double *t_val = nullptr;
+    NGSB_TRY(csr_ensure(A));
     NGSB_TRY(transpose_raw(ctx, A->h, A->w, A->nnz, A->kind, A->d_rowptr, A->d_col, A->d_val, &t_rp, &t_col, &t_val));
     int rc = csr_adopt_device(ctx, A->w, A->h, A->nnz, t_rp, t_col, t_val, A->kind, out);
     if (rc != NGSB_OK) { cudaFree(t_rp); cudaFree(t_col); cudaFree(t_val); }

@@ -875,6 +875,12 @@ class DevSparseMatrix(BaseMatrix):
         check(_capi.lib().ngsb_csr_reorder(self.handle, _np_ptr(p), C.byref(h)))
         return DevSparseMatrix(None, ctx=self.ctx, _handle=h)
 
+    def Memory(self):
+        """(bytes of CSR arrays + tables resident, bytes of the SELL copy, CSR column/value arrays resident?)"""
+        c, s, r = C.c_uint64(), C.c_uint64(), C.c_int()
+        check(_capi.lib().ngsb_csr_memory(self.handle, C.byref(c), C.byref(s), C.byref(r)))
+        return c.value, s.value, bool(r.value)
+
     def RCM(self):
         """the Cuthill-McKee permutation option "reorder" uses (ngsb_csr_rcm), in the form Reorder() takes"""
         p = np.empty(self.height, dtype=np.uint64)
