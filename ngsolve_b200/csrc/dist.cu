@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(256) halo_push_kernel(const PeerHalo *__restri
     if (st && st->done) return;
     const unsigned long long s = *(volatile unsigned long long *)H->seq + 1;
     const unsigned long long par = s & 1;
-    if (R && blockIdx.x == 0 && threadIdx.x == 0) pr_push(*R, red[0], red[1]);
+    if (R && blockIdx.x == 0 && threadIdx.x < 32) pr_push_warp(*R, red[0], red[1]);
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < nex; k += stride) {
         int q = 0;
@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(256) halo_unpack_kernel(const PeerHalo *__rest
     if (st && st->done) return;
     const unsigned long long s = *(volatile unsigned long long *)H->seq + 1;
     const unsigned long long par = s & 1;
-    if (fin == 2 && R && blockIdx.x == 0 && threadIdx.x == 0) pr_push(*R, red[0], red[1]);
+    if (fin == 2 && R && blockIdx.x == 0 && threadIdx.x < 32) pr_push_warp(*R, red[0], red[1]);
     if ((int)threadIdx.x < H->npeers) peer_wait(H->flags + par * NGSB_MAX_RANKS + H->peer_rank[threadIdx.x], s, H->err);
     __syncthreads();
     const double *recv = H->recv + par * H->stride;

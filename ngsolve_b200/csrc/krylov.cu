@@ -144,7 +144,9 @@ __device__ __forceinline__ double warp_sum_k(double v)
 }
 
 
-// grid-wide deterministic reduction finish; returns true on thread 0 of the last block
+// grid-wide deterministic reduction finish; returns true on thread 0 of the last block (WARP: on all 32 lanes of its first
+// warp, every lane holding the total -- for finishes that talk to the peers with one lane per rank)
+template <bool WARP = false>
 __device__ __forceinline__ bool grid_finish(double a, double b, double *partials, unsigned int *counter, double2 *total)
 {
     __shared__ double red[64];
@@ -179,8 +181,8 @@ __device__ __forceinline__ bool grid_finish(double a, double b, double *partials
     }
     a = warp_sum_k(a);
     b = warp_sum_k(b);
-    if (threadIdx.x == 0) {
-        *counter = 0;
+    if (threadIdx.x == 0) *counter = 0;
+    if (WARP || threadIdx.x == 0) {
         *total = make_double2(a, b);
         return true;
     }
@@ -334,14 +336,17 @@ __global__ void __launch_bounds__(256) cg_fused_kernel(const CgVecs v, int sub)
         }
     }
     double2 total;
-    if (grid_finish(accr, acci, v.partials, v.counter, &total)) {
+    if (grid_finish<true>(accr, acci, v.partials, v.counter, &total)) {
         if (v.R != nullptr) {
-            pr_push(*v.R, total.x, total.y);
-            total = pr_wait_sum(*v.R);
+            // distributed: the first warp of the last block all-reduces the dot over the ranks itself, one lane per rank
+            pr_push_warp(*v.R, total.x, total.y);
+            total = pr_wait_sum_warp(*v.R);
         }
-        if (v.R == nullptr && v.dot_out != nullptr) { v.dot_out[0] = total.x; v.dot_out[1] = total.y; }
-        else if (MODE == 0) cg_finalize_init(st, total, v.hist);
-        else cg_finalize_wdn(st, total, v.hist);
+        if (threadIdx.x == 0) {
+            if (v.R == nullptr && v.dot_out != nullptr) { v.dot_out[0] = total.x; v.dot_out[1] = total.y; }
+            else if (MODE == 0) cg_finalize_init(st, total, v.hist);
+            else cg_finalize_wdn(st, total, v.hist);
+        }
     }
 }
 

@@ -181,6 +181,7 @@ __global__ void __launch_bounds__(256, MINB) sell_spmv_kernel(const SellParams p
     __shared__ int s_last;
     if (p.state != nullptr && p.state->done) return;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    bool pushed = false;
 
     double dr = 0.0, di = 0.0;
     const uint64_t nwalk = LIST ? (uint64_t)p.nlist : (uint64_t)p.nslices;
@@ -482,11 +483,13 @@ __global__ void __launch_bounds__(256, MINB) sell_spmv_kernel(const SellParams p
                     dr += v[0] * r0 + v[1] * r1 + v[2] * r2;
                 }
             }
-            if (PUSH && has_if) sell_push_row(p.push, (uint32_t)s, lane, p.y, row);
+            if (PUSH && has_if) { sell_push_row(p.push, (uint32_t)s, lane, p.y, row); pushed = true; }
         }
     }
     if (!p.epi) return;
-    if (PUSH) __threadfence_system();        // this thread's peer stores are visible system-wide before the block takes its ticket
+    // this thread's peer stores are visible system-wide before the block takes its ticket.  Only the threads that stored pay
+    // for the system-scope fence (a fence by every thread of the grid cost 4 % of the product)
+    if (PUSH && pushed) __threadfence_system();
     // deterministic grid-wide finish of the fused dot (+ scalar step of CG)
     dr = warp_sum_s(dr);
     di = warp_sum_s(di);
@@ -520,15 +523,15 @@ __global__ void __launch_bounds__(256, MINB) sell_spmv_kernel(const SellParams p
         if (p.dot_add != nullptr) { a += p.dot_add[0]; b += p.dot_add[1]; }
         if (p.epi == EPI_DOT_OUT) { p.dot_out[0] = a; p.dot_out[1] = b; }
         else if (p.epi == EPI_CG_KSS) cg_finalize_kss(p.state, make_double2(a, b));
-        if (PUSH) {
-            // every block's stores are out (each fenced before its ticket): tell the neighbours, and send this rank's partial
-            // of <s, A s> on its way to all ranks (the unpack kernel sums the partials and does al = wd / kss)
-            const PeerHalo *H = p.push->H;
-            const unsigned long long xseq = *(volatile const unsigned long long *)H->seq + 1;
-            __threadfence_system();
-            for (int q = 0; q < H->npeers; q++) st_release_sys(H->peer_flags[q] + (xseq & 1) * NGSB_MAX_RANKS + H->rank, xseq);
-            if (p.push->R) pr_push(*p.push->R, a, b);
-        }
+    }
+    if (PUSH) {
+        // every block's stores are out (each fenced before its ticket): tell the neighbours, and send this rank's partial of
+        // <s, A s> on its way to all ranks (the unpack kernel sums the partials and does al = wd / kss).  One lane per peer.
+        const PeerHalo *H = p.push->H;
+        const unsigned long long xseq = *(volatile const unsigned long long *)H->seq + 1;
+        __threadfence_system();
+        if ((int)threadIdx.x < H->npeers) st_release_sys(H->peer_flags[threadIdx.x] + (xseq & 1) * NGSB_MAX_RANKS + H->rank, xseq);
+        if (p.push->R) pr_push_warp(*p.push->R, a, b);
     }
 }
 
