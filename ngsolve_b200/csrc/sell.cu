@@ -1074,9 +1074,14 @@ int sell_launch(const SpmvArgs &a)
     // wave of CTAs and x is fetched again each time; with ~96 CTAs per SM there are only a few dozen wide stripes, every
     // window slides through its stripe once and the x lines are re-used out of L2.  Measured at 111 M dofs: 10.66 ms with
     // 8 CTAs/SM, 9.31 ms with 96 (profiles/r1_sweep_c16_grid_size.txt); 3x3 blocks +18 %, complex +9 %.
-    long cps = ctx->spmv_ctas_per_sm > 0 ? ctx->spmv_ctas_per_sm : 96;
+    // ... and about eight slices per warp: below ~30 M rows a grid of 96 CTAs per SM leaves each CTA only 3-4 slices and the
+    // per-CTA cost (launch, prologue, ticket) shows in the CG loop (13.6 M-dof netgen system: 589.6 it/s at 96, 595.7 at 48;
+    // one rank's slab of the 8-GPU run: 1.490 -> 1.456 ms per iteration, 637 -> 653 it/s on eight GPUs)
+    const uint64_t nwork = (uint64_t)(list ? a.nlist : A->nslices);
+    long cps = ctx->spmv_ctas_per_sm > 0 ? ctx->spmv_ctas_per_sm
+                                         : (long)std::min<uint64_t>(96, std::max<uint64_t>(32, nwork / (64ull * (uint64_t)std::max(1, ctx->sm_count))));
     uint64_t grid = (uint64_t)ctx->sm_count * (uint64_t)cps;
-    const uint64_t need = ((uint64_t)(list ? a.nlist : A->nslices) + 7) / 8;
+    const uint64_t need = (nwork + 7) / 8;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
     if (grid > (uint64_t)MAX_PARTIALS - 8) grid = MAX_PARTIALS - 8;
