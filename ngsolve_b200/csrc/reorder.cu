@@ -494,6 +494,9 @@ int csr_attach_inner(ngsb_csr *A, uint32_t *d_perm, uint32_t *d_iperm)
     int32_t *ncol = nullptr;
     double *nval = nullptr;
     NGSB_TRY(csr_permute_device(A, d_perm, d_iperm, &nrp, &ncol, &nval));
+    // large matrices: the uploaded arrays go before the SELL copy of P A P^T is built (they come back from that copy on
+    // demand, csrview.cu) -- uploaded CSR + permuted CSR + SELL copy of a 100 M-dof system do not fit 180 GB together
+    if (csr_release_wanted(A)) csr_release(A);
     ngsb_csr *in = nullptr;
     int rc = csr_adopt_device(ctx, A->h, A->w, A->nnz, nrp, ncol, nval, A->kind, &in, false);
     if (rc != NGSB_OK) { cudaFree(nrp); cudaFree(ncol); cudaFree(nval); return rc; }

@@ -101,6 +101,55 @@ class ParallelDofs:
         return m
 
 
+def row_block_local_system(rowptr, col, val, perm, cuts, rank):
+    """Rank `rank`'s share of a globally assembled matrix split by rows: dofs renumbered by `perm`
+    (new -> old), rank r owns the new indices [cuts[r], cuts[r+1]).  Its local dofs are the owned ones plus the ghost dofs
+    its rows couple to, numbered ascending in the new global index; its local matrix holds the owned rows complete and
+    the ghost rows empty, so A_loc * x (x CUMULATED) is DISTRIBUTED in the reference's sense.  Index work only (host, numpy).
+    Returns (lrowptr uint64, lcol int32, lval, loc2glob (new global index per local dof), ghosts)."""
+    n = len(rowptr) - 1
+    perm = np.asarray(perm, dtype=np.int64)
+    iperm = np.empty(n, dtype=np.int64)
+    iperm[perm] = np.arange(n)
+    lo, hi = int(cuts[rank]), int(cuts[rank + 1])
+    rp = np.asarray(rowptr).astype(np.int64)
+    old_rows = perm[lo:hi]
+    lens = rp[old_rows + 1] - rp[old_rows]
+    nnz = int(lens.sum())
+    idx = np.repeat(rp[old_rows] - np.concatenate([[0], np.cumsum(lens)[:-1]]), lens) + np.arange(nnz)
+    gcol = iperm[np.asarray(col)[idx]]
+    gval = np.asarray(val)[idx]
+    grow = np.repeat(np.arange(lo, hi), lens)
+    ghosts = np.unique(gcol[(gcol < lo) | (gcol >= hi)])
+    loc2glob = np.concatenate([ghosts[ghosts < lo], np.arange(lo, hi), ghosts[ghosts >= hi]])
+    lcol = np.searchsorted(loc2glob, gcol)
+    lrow = np.searchsorted(loc2glob, grow)
+    order = np.lexsort((lcol, lrow))
+    cnt = np.bincount(lrow, minlength=len(loc2glob))
+    lrp = np.concatenate([[0], np.cumsum(cnt)]).astype(np.uint64)
+    return lrp, lcol[order].astype(np.int32), gval[order], loc2glob, ghosts
+
+
+def row_block_dist_procs(loc2glob, cuts, rank, all_ghosts):
+    """dist_procs of the row-block split: for every local dof the OTHER ranks that hold it -- the ranks that ghost it and,
+    for a ghost, its owner.  all_ghosts[q] = sorted ghost list (new global indices) of rank q.  Returns (dp_first, dp)."""
+    world = len(cuts) - 1
+    nloc = len(loc2glob)
+    owner = np.searchsorted(np.asarray(cuts[1:]), loc2glob, side="right")
+    pi, pp = [np.flatnonzero(owner != rank)], [owner[owner != rank]]
+    for q in range(world):
+        if q == rank:
+            continue
+        _, mine, _ = np.intersect1d(loc2glob, all_ghosts[q], assume_unique=True, return_indices=True)
+        pi.append(mine)
+        pp.append(np.full(len(mine), q))
+    pi, pp = np.concatenate(pi).astype(np.int64), np.concatenate(pp).astype(np.int64)
+    key = np.unique(pi * world + pp)               # by local dof, then rank; a ghost's owner may also appear as "ghosting" rank: once
+    pi, pp = key // world, key % world
+    dp_first = np.concatenate([[0], np.cumsum(np.bincount(pi, minlength=nloc))]).astype(np.int64)
+    return dp_first, pp
+
+
 class ParallelMatrix(la.BaseMatrix):
     """ParallelMatrix(local matrix, pardofs, C2D): cumulated in, distributed out."""
 

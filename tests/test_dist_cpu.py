@@ -151,3 +151,37 @@ def test_exchange_tables_equal_the_reference_paralleldofs(name):
         masters += int(g[pre + "master"].sum())
         assert int(g[pre + "global_ndof"]) == int(g[name + "_nglobal"])
     assert masters == int(g[name + "_nglobal"])        # global_ndof = all-reduced master count (paralleldofs.cpp:104-107)
+
+
+def test_row_block_split_reproduces_the_global_product():
+    """host logic of tools/netgen_multi.py: a globally assembled matrix split into row blocks of a permuted numbering.
+    Sum over the ranks of the DISTRIBUTED local products = the global product; exchange tables pair up; masters partition."""
+    from conftest import load_golden
+    from oracle import pyoracle as orc
+    from ngsolve_b200 import parallel as par
+    g = load_golden("reorder_netgen_h1p3")
+    rowptr, col, val, perm = g["rowptr"], g["col"], g["val"], g["perm"].astype(np.int64)
+    n = len(rowptr) - 1
+    world = 4
+    cuts = [(n * r) // world for r in range(world + 1)]
+    loc = [par.row_block_local_system(rowptr, col, val, perm, cuts, r) for r in range(world)]
+    all_ghosts = [l[4] for l in loc]
+    x = g["x"]
+    y = np.zeros(n)
+    masters = np.zeros(n, dtype=int)
+    pds = []
+    for r in range(world):
+        lrp, lcol, lval, l2g, ghosts = loc[r]
+        dp_first, dp = par.row_block_dist_procs(l2g, cuts, r, all_ghosts)
+        pd = par.ParallelDofs.from_dist_procs(dp_first, dp, world, r)
+        pds.append(pd)
+        yl = orc.Csr(lrp, lcol, lval, 0).mult(x[perm[l2g]])          # x CUMULATED: the global values at the local dofs
+        np.add.at(y, perm[l2g], yl)                                   # DISTRIBUTED results summed over the ranks
+        masters[perm[l2g][pd.MasterDofs()]] += 1
+    assert np.max(np.abs(y - g["y"])) <= 1e-12 * np.max(np.abs(g["y"]))
+    assert np.all(masters == 1)
+    for r in range(world):                     # both sides of every exchange list the same global dofs in the same order
+        for q in range(world):
+            a = loc[r][3][pds[r].GetExchangeDofs(q)]
+            b = loc[q][3][pds[q].GetExchangeDofs(r)]
+            assert np.array_equal(a, b)
