@@ -1085,6 +1085,12 @@ int sell_launch(const SpmvArgs &a)
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
     if (grid > (uint64_t)MAX_PARTIALS - 8) grid = MAX_PARTIALS - 8;
+    if (ctx->spmv_ctas_per_sm <= 0) {
+        // whole rounds: every CTA walks the same number of 8-slice steps (46 CTAs per SM on the 14 M-row slab meant 8.1
+        // rounds, i.e. a ninth, nearly empty one: 636 instead of 653 it/s on eight GPUs)
+        const uint64_t rounds = (need + grid - 1) / grid;
+        grid = std::max<uint64_t>(1, (need + rounds - 1) / rounds);
+    }
     SpanGuard g(ctx, KC_SPMV);
     kern<<<(unsigned)grid, 256, 0, ctx->stream>>>(p);
     NGSB_CUDA(cudaGetLastError());
