@@ -1047,6 +1047,7 @@ extern "C" int ngsb_parmat_cg_solve(const ngsb_parmat *P, const ngsb_jacobi *C, 
     v.ip_mode = ip_mode;
     v.fold_u = ctx->cg_fold_u ? 1 : 0;
     v.chunked = ctx->cg_chunked ? 1 : 0;
+    v.stream = ctx->cg_stream_hints ? 1 : 0;
 
     // u = 0; d = f, cumulated by the Jacobi application (linalg/jacobi.cpp:78)
     cu(cudaMemsetAsync(u->d, 0, nscal * sizeof(double), ctx->stream));

@@ -258,21 +258,26 @@ __global__ void __launch_bounds__(256) cg_fused_kernel(const CgVecs v, int sub)
         const uint64_t hi2 = lo + ((hi - lo) & ~(uint64_t)1);
 #pragma unroll 2
         for (uint64_t i = lo + 2 * first; i < hi2; i += 2 * step) {
-            const double2 a2 = *reinterpret_cast<const double2 *>(v.as + i);
-            const double2 m2 = *reinterpret_cast<const double2 *>(v.invdiag + i);
-            double2 d2 = *reinterpret_cast<double2 *>(v.d + i);
+            // v.stream (option cg_stream_hints): u, d, As and the diagonal are not touched again before the next iteration's
+            // update -- load them streaming and store u, d evict-first, so that the L2 keeps w (read by the direction kernel
+            // next) and s (gathered by the next product) instead of 2 x N dirty doubles nobody asks for
+            const double2 a2 = v.stream ? __ldcs(reinterpret_cast<const double2 *>(v.as + i)) : *reinterpret_cast<const double2 *>(v.as + i);
+            const double2 m2 = v.stream ? __ldcs(reinterpret_cast<const double2 *>(v.invdiag + i)) : *reinterpret_cast<const double2 *>(v.invdiag + i);
+            double2 d2 = v.stream ? __ldcs(reinterpret_cast<const double2 *>(v.d + i)) : *reinterpret_cast<double2 *>(v.d + i);
             if (!FOLD) {
                 const double2 s2 = *reinterpret_cast<const double2 *>(v.s + i);
-                double2 u2 = *reinterpret_cast<double2 *>(v.u + i);
+                double2 u2 = v.stream ? __ldcs(reinterpret_cast<const double2 *>(v.u + i)) : *reinterpret_cast<double2 *>(v.u + i);
                 u2.x += alr * s2.x; u2.y += alr * s2.y;
-                *reinterpret_cast<double2 *>(v.u + i) = u2;
+                if (v.stream) __stcs(reinterpret_cast<double2 *>(v.u + i), u2);
+                else *reinterpret_cast<double2 *>(v.u + i) = u2;
             }
             d2.x -= alr * a2.x; d2.y -= alr * a2.y;
             unsigned bits = v.bits ? (unsigned)(v.bits[i >> 3] >> (i & 7)) : 3u;
             double2 w2;
             w2.x = (bits & 1u) ? m2.x * d2.x : 0.0;
             w2.y = (bits & 2u) ? m2.y * d2.y : 0.0;
-            *reinterpret_cast<double2 *>(v.d + i) = d2;
+            if (v.stream) __stcs(reinterpret_cast<double2 *>(v.d + i), d2);
+            else *reinterpret_cast<double2 *>(v.d + i) = d2;
             *reinterpret_cast<double2 *>(v.w + i) = w2;
             if (v.master == nullptr || v.master[i]) accr = fma(d2.x, w2.x, accr);
             if (v.master == nullptr || v.master[i + 1]) acc1 = fma(d2.y, w2.y, acc1);
@@ -542,6 +547,7 @@ int cg_solve_device(const ngsb_csr *A, const ngsb_jacobi *C, const double *f, do
     v.ip_mode = ip_mode;
     v.fold_u = ctx->cg_fold_u ? 1 : 0;
     v.chunked = ctx->cg_chunked ? 1 : 0;
+    v.stream = ctx->cg_stream_hints ? 1 : 0;
 
     int sub = 0;
     if (initialize) {
@@ -561,7 +567,7 @@ int cg_solve_device(const ngsb_csr *A, const ngsb_jacobi *C, const double *f, do
     if (use_graph) {
         double *key[6] = {u, d, w, s, as, (double *)f};
         const long opts[11] = {batch, (long)ip_mode, ctx->spmv_algo, ctx->spmv_ctas_per_sm, ctx->cg_fold_u, ctx->sell_variant, ctx->sell_c16,
-                               ctx->sell_c16_all, ctx->sell_pf_steps, ctx->sell_pf_next, ctx->cg_chunked};
+                               ctx->sell_c16_all, ctx->sell_pf_steps, ctx->sell_pf_next, ctx->cg_chunked | (ctx->cg_stream_hints << 1)};
         bool hit = ws->graph_exec && ws->g_A == A->uid && ws->g_C == (C ? C->uid : 0) && memcmp(opts, ws->g_opts, sizeof(opts)) == 0 &&
                    memcmp(key, ws->g_ptrs, sizeof(key)) == 0;
         if (!hit) {

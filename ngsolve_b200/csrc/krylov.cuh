@@ -24,6 +24,7 @@ struct CgVecs {
     double *partials;
     unsigned int *counter;
     int ip_mode;
+    int stream;                // option cg_stream_hints: streaming loads / evict-first stores for the vectors nobody reads next
     int chunked;               // option cg_chunked: contiguous chunk per CTA instead of the grid-stride split (A/B)
     int fold_u;                // option cg_fold_u: `u += al s` moves from the update kernel into the direction kernel, which
                                // reads s anyway (10 instead of 11 vector passes per iteration, same arithmetic per entry)

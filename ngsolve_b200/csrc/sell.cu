@@ -509,15 +509,27 @@ __global__ void __launch_bounds__(256, MINB) sell_spmv_kernel(const SellParams p
         }
     }
     __syncthreads();
-    if (!s_last || threadIdx.x >= 32) return;
+    if (!s_last) return;
+    // the last block sums the per-CTA partials in a fixed order (thread t: partials t, t+256, ...; then lanes, then warps)
     __threadfence();
     double a = 0.0, b = 0.0;
-    for (unsigned int k = threadIdx.x; k < gridDim.x; k += 32) {
+    for (unsigned int k = threadIdx.x; k < gridDim.x; k += blockDim.x) {
         a += __ldcg(&p.partials[2 * k]);
         b += __ldcg(&p.partials[2 * k + 1]);
     }
     a = warp_sum_s(a);
     b = warp_sum_s(b);
+    __syncthreads();                       // red[] is free again
+    if (lane == 0) { red[wid] = a; red[32 + wid] = b; }
+    __syncthreads();
+    if (threadIdx.x >= 32) return;
+    {
+        const int nw = blockDim.x >> 5;
+        a = lane < nw ? red[lane] : 0.0;
+        b = lane < nw ? red[32 + lane] : 0.0;
+        a = warp_sum_s(a);
+        b = warp_sum_s(b);
+    }
     if (threadIdx.x == 0) {
         *p.counter = 0;
         if (p.dot_add != nullptr) { a += p.dot_add[0]; b += p.dot_add[1]; }
@@ -1085,7 +1097,7 @@ int sell_launch(const SpmvArgs &a)
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
     if (grid > (uint64_t)MAX_PARTIALS - 8) grid = MAX_PARTIALS - 8;
-    if (ctx->spmv_ctas_per_sm <= 0) {
+    if (ctx->spmv_ctas_per_sm <= 0 && need > 0) {
         // whole rounds: every CTA walks the same number of 8-slice steps (46 CTAs per SM on the 14 M-row slab meant 8.1
         // rounds, i.e. a ninth, nearly empty one: 636 instead of 653 it/s on eight GPUs)
         const uint64_t rounds = (need + grid - 1) / grid;

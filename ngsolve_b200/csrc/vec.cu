@@ -551,11 +551,12 @@ extern "C" int ngsb_ctx_set_option(ngsb_ctx *ctx, const char *name, long value)
     NGSB_REQUIRE(ctx && name, "ngsb_ctx_set_option: NULL argument");
     if (!strcmp(name, "spmv_algo")) { NGSB_REQUIRE(value >= 0 && value <= 3, "spmv_algo must be 0 (auto = SELL), 1 (sub-warp CSR), 2 (TMA-streamed CSR), 3 (SELL)"); ctx->spmv_algo = value; }
     else if (!strcmp(name, "cg_batch")) { NGSB_REQUIRE(value >= 1 && value <= 4096, "cg_batch out of range"); ctx->cg_batch = value; }
-    else if (!strcmp(name, "spmv_ctas_per_sm")) { NGSB_REQUIRE(value >= 0 && value <= 110, "spmv_ctas_per_sm out of range"); ctx->spmv_ctas_per_sm = value; }
+    else if (!strcmp(name, "spmv_ctas_per_sm")) { NGSB_REQUIRE(value >= 0 && value <= 7000, "spmv_ctas_per_sm out of range"); ctx->spmv_ctas_per_sm = value; }
     else if (!strcmp(name, "timing")) { ctx->timing = value ? 1 : 0; }
     else if (!strcmp(name, "reorder")) { NGSB_REQUIRE(value >= -1 && value <= 1, "reorder must be -1 (automatic), 0 (off) or 1 (always)"); ctx->reorder = value; }
     else if (!strcmp(name, "csr_keep")) { NGSB_REQUIRE(value >= -1 && value <= 1, "csr_keep must be -1 (automatic), 0 (release) or 1 (keep)"); ctx->csr_keep = value; }
     else if (!strcmp(name, "reorder_min_rows")) { NGSB_REQUIRE(value >= 0, "reorder_min_rows must be >= 0"); ctx->reorder_min_rows = value; }
+    else if (!strcmp(name, "cg_stream_hints")) { NGSB_REQUIRE(value == 0 || value == 1, "cg_stream_hints must be 0 or 1"); ctx->cg_stream_hints = value; }
     else if (!strcmp(name, "cg_chunked")) { NGSB_REQUIRE(value == 0 || value == 1, "cg_chunked must be 0 or 1"); ctx->cg_chunked = value; }
     else if (!strcmp(name, "cg_fold_u")) { NGSB_REQUIRE(value == 0 || value == 1, "cg_fold_u must be 0 or 1"); ctx->cg_fold_u = value; }
     else if (!strcmp(name, "dist_fused_push")) { NGSB_REQUIRE(value == 0 || value == 1, "dist_fused_push must be 0 or 1"); ctx->dist_fused_push = value; }

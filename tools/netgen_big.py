@@ -31,6 +31,7 @@ ap.add_argument("--cpu-iters", type=int, default=5)
 ap.add_argument("--cpu-warmup", type=int, default=2)
 ap.add_argument("--cpu-only", action="store_true", help="the reference's CPU CG only (bench.py --impl reference)")
 ap.add_argument("--full", action="store_true")
+ap.add_argument("--cps-sweep", type=int, nargs="*", default=[], help="also time the product and 50 CG iterations with these grids (CTAs per SM)")
 ap.add_argument("--out", default=None)
 args = ap.parse_args()
 ngsolve.ngsglobals.msg_level = 0
@@ -137,6 +138,33 @@ its = inv.GetSteps() - 1
 b_cg = b_alg + 11 * n * 8
 out.update(cg_it_per_s=its / dt, cg_gbs=b_cg * its / dt / 1e9, cg_frac_of_peak=b_cg * its / dt / 1e9 / peak)
 log("cg", out["cg_it_per_s"])
+sweep = []
+for cps in args.cps_sweep:
+    ctx.set_option("spmv_ctas_per_sm", cps)
+    xs = la.BaseVector(np.random.default_rng(1).random(n)); ys = dev.CreateColVector()
+    for _ in range(2):
+        dev.Mult(xs, ys)
+    ctx.sync()
+    ctx.set_option("timing", 1)
+    ctx.kernel_time_reset()
+    for _ in range(5):
+        dev.Mult(xs, ys)
+    ms5, _ = ctx.kernel_time("spmv")
+    ctx.kernel_time_reset()
+    ctx.set_option("timing", 0)
+    del xs, ys
+    inv = la.CGSolver(dev, jac, precision=0.0, maxsteps=50)
+    inv.Mult(fv, uv)
+    ctx.sync()
+    t1 = time.perf_counter()
+    inv.Mult(fv, uv)
+    ctx.sync()
+    dt = time.perf_counter() - t1
+    sweep.append(dict(ctas_per_sm=cps, spmv_kernel_ms=ms5 / 5, cg_it_per_s=(inv.GetSteps() - 1) / dt))
+    log("cps", cps, sweep[-1])
+ctx.set_option("spmv_ctas_per_sm", 0)
+if sweep:
+    out["grid_sweep"] = sweep
 if args.full:
     inv = la.CGSolver(dev, jac, precision=1e-8, maxsteps=20000)
     t1 = time.perf_counter()

@@ -37,8 +37,12 @@ def main():
     ap.add_argument("--cps", type=int, nargs="*", default=[16, 32, 64, 96])
     ap.add_argument("--steps", type=int, default=48)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--opt", action="append", default=[])
     a = ap.parse_args()
     ctx = la.default_context()
+    for o in a.opt:
+        k, v = o.split("=")
+        ctx.set_option(k, int(v))
     G = (a.size,) * 3
     for parts in a.parts:
         slabs = W.slab_partition(G, parts)
@@ -59,7 +63,7 @@ def main():
             inv = la.CGSolver(A, jac, precision=0.0, maxsteps=a.steps)
             inv.Mult(f, u)
             ms_cg = timed(ctx, lambda: inv.Mult(f, u), 3) / a.steps
-            line = dict(parts=parts, rows=A.height, nnz=A.nze, ctas_per_sm=cps, spmv_ms=ms, gbs_algorithmic=A.MultBytes() / ms / 1e6,
+            line = dict(options=a.opt, parts=parts, rows=A.height, nnz=A.nze, ctas_per_sm=cps, spmv_ms=ms, gbs_algorithmic=A.MultBytes() / ms / 1e6,
                         gbs_stored=sb / ms / 1e6, cg_ms_per_iteration=ms_cg, it_per_s_times_parts=parts * 1e3 / ms_cg)
             print(json.dumps(line), flush=True)
             if a.out:
