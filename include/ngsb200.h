@@ -95,6 +95,9 @@ int ngsb_ctx_launch_count(const ngsb_ctx *ctx, uint64_t *count);
  *                        P A P^T with P = Cuthill-McKee of the pattern (ngsb_csr_rcm).  Automatic = at least
  *                        "reorder_min_rows" rows (default 32768) and fewer than half of the natural 32-row slices fit for
  *                        16-bit column offsets -- the signature of netgen's entity-by-entity numbering
+ *     "reorder_slot_order" 0/1 (default 0): the internal permutation = Cuthill-McKee composed with the SELL length sort (rows of the
+ *                        Cuthill-McKee order sorted longest-first, stably, inside windows of sell_sigma rows), so that P A P^T is numbered
+ *                        in slot order: no slot -> row table, y written in whole 256-byte runs.  Measured: no gain, kept for A/B
  *     "sell_c16_all"     0/1: 16-bit column offsets for Complex and Mat<3,3> matrices too (default 0; must still be on at launch)
  *     "sell_cap"         longest row part kept in a slice, 0 = max(64, 4 x mean row length) or the longest row when cheap
  *     "sell_sigma"       rows sorted by length inside windows of this many rows, -1 = automatic (65536 where natural slices would pad > 5 %), 0/1 = off

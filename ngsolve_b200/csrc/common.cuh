@@ -95,6 +95,9 @@ struct ngsb_ctx {
                                  // demand), -1 automatic = release above 4 GiB (read when a matrix is created)
     long reorder = -1;           // internal Cuthill-McKee reordering of square matrices: 0 off, 1 always, -1 automatic
                                  // (read when a matrix is created)
+    long reorder_slot_order = 0; // the internal permutation also absorbs the SELL length sort (inner matrix numbered in slot order).
+                                 // Measured (profiles/r2_slot_order_*.json): same DRAM traffic, product 5 % slower (x gathers
+                                 // scrambled inside the sort windows), CG loop +1 % / +0 % at 13.6 M / 108 M dofs -> off
     long reorder_min_rows = 32768;   // automatic mode: smaller matrices keep their numbering
     long timing = 0;
     // reduction workspace (partials + counters), pinned host scratch

@@ -486,6 +486,65 @@ __global__ void __launch_bounds__(256) perm_rowuser_kernel(const uint32_t *__res
     row_user[t] = r == 0xffffffffu ? r : perm[r];
 }
 
+// Rows of the Cuthill-McKee order sorted by length inside windows of `sigma` rows (the SELL-C-sigma sort, longest first, stable),
+// composed INTO the permutation: the inner matrix is then numbered in slot order, its slices need no slot -> row table, y and
+// the fused dot's vector are written / read as whole 256-byte runs instead of 32 scattered doubles per slice, and x is gathered
+// in the same numbering.  key = (window, 2^20 - min(len, 2^20)).
+__global__ void __launch_bounds__(256) perm_lenkey_kernel(const uint64_t *__restrict__ rowptr, const uint32_t *__restrict__ perm, uint64_t n, uint32_t sigma,
+                                                         uint64_t *__restrict__ key, uint32_t *__restrict__ id)
+{
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const uint32_t o = perm[j];
+    const uint64_t l = rowptr[o + 1] - rowptr[o];
+    const uint32_t len = l > RCM_DEGCAP ? RCM_DEGCAP : (uint32_t)l;
+    key[j] = ((j / sigma) << 21) | (uint64_t)((1u << 20) - len);
+    id[j] = (uint32_t)j;
+}
+
+__global__ void __launch_bounds__(256) perm_compose_kernel(const uint32_t *__restrict__ perm, const uint32_t *__restrict__ order, uint64_t n,
+                                                          uint32_t *__restrict__ perm2, uint32_t *__restrict__ iperm2)
+{
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const uint32_t o = perm[order[j]];
+    perm2[j] = o;
+    iperm2[o] = (uint32_t)j;
+}
+
+// d_perm / d_iperm (Cuthill-McKee) -> composed with the length sort, in place
+int perm_compose_length_sort(ngsb_ctx *ctx, const uint64_t *d_rowptr, size_t n, uint32_t sigma, uint32_t *d_perm, uint32_t *d_iperm)
+{
+    if (sigma <= 1 || n == 0) return NGSB_OK;
+    uint64_t *k1 = nullptr, *k2 = nullptr;
+    uint32_t *id = nullptr, *order = nullptr, *p2 = nullptr;
+    void *tmp = nullptr;
+    size_t bytes = 0;
+    cudaError_t e = cudaMalloc(&k1, n * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&k2, n * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&id, n * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&order, n * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&p2, n * 4);
+    int bits = 22;
+    while (bits < 64 && ((uint64_t)(n / sigma) >> (bits - 21)) != 0) bits++;
+    if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(nullptr, bytes, k1, k2, id, order, (int)n, 0, bits, ctx->stream);
+    if (e == cudaSuccess) e = cudaMalloc(&tmp, bytes);
+    if (e == cudaSuccess) {
+        const unsigned grid = (unsigned)((n + 255) / 256);
+        perm_lenkey_kernel<<<grid, 256, 0, ctx->stream>>>(d_rowptr, d_perm, n, sigma, k1, id);
+        e = cub::DeviceRadixSort::SortPairs(tmp, bytes, k1, k2, id, order, (int)n, 0, bits, ctx->stream);
+        if (e == cudaSuccess) {
+            perm_compose_kernel<<<grid, 256, 0, ctx->stream>>>(d_perm, order, n, p2, d_iperm);
+            e = cudaMemcpyAsync(d_perm, p2, n * 4, cudaMemcpyDeviceToDevice, ctx->stream);
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    }
+    cudaFree(k1); cudaFree(k2); cudaFree(id); cudaFree(order); cudaFree(p2); cudaFree(tmp);
+    if (e != cudaSuccess) { set_error("reorder (length sort): %s", cudaGetErrorString(e)); return NGSB_ERR_CUDA; }
+    ctx->launches += 8;
+    return NGSB_OK;
+}
+
 // build A->inner = P A P^T (SELL only) from a device permutation that A takes ownership of
 int csr_attach_inner(ngsb_csr *A, uint32_t *d_perm, uint32_t *d_iperm)
 {
@@ -541,6 +600,9 @@ int csr_maybe_reorder(ngsb_csr *A, bool *made)
     cudaError_t e = cudaMalloc(&d_iperm, A->h * sizeof(uint32_t));
     if (e != cudaSuccess) { cudaFree(d_perm); set_error("reorder: cudaMalloc failed"); return NGSB_ERR_NOMEM; }
     int rc = rcm_device(ctx, A->h, A->d_rowptr, A->d_col, 64, d_perm, d_iperm);
+    // ... composed with the SELL length sort, so that the inner matrix is numbered in slot order (no row table, coalesced y)
+    if (rc == NGSB_OK && ctx->reorder_slot_order)
+        rc = perm_compose_length_sort(ctx, A->d_rowptr, A->h, ctx->sell_sigma >= 0 ? (uint32_t)ctx->sell_sigma : 65536u, d_perm, d_iperm);
     if (rc == NGSB_OK) rc = csr_attach_inner(A, d_perm, d_iperm);
     if (rc != NGSB_OK) { cudaFree(d_perm); cudaFree(d_iperm); return rc; }
     *made = true;

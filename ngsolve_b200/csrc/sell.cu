@@ -195,7 +195,8 @@ __global__ void __launch_bounds__(256, MINB) sell_spmv_kernel(const SellParams p
         const bool has_if = PUSH && (src_raw >> 31);
         const uint64_t src = PUSH ? (src_raw & 0x7fffffffu) : src_raw;
         const uint32_t slot = (uint32_t)(src * 32 + lane);
-        const uint32_t row = p.row_of[slot];
+        // no table when the rows sit in slot order (natural slices; internally reordered matrices in the solvers' numbering)
+        const uint32_t row = p.row_of != nullptr ? p.row_of[slot] : ((uint64_t)slot < p.nrows ? slot : 0xffffffffu);
         double s0 = 0.0, s1 = 0.0, s2 = 0.0;
         if (KIND == NGSB_REAL && p.slice_c16 != nullptr && p.slice_c16[s]) {
             // compressed slice: per packet 16 B of values and 4 B of column offsets per lane, plus one (uniform) pair of
@@ -891,6 +892,7 @@ int sell_build(ngsb_csr *A, const uint64_t *h_rowptr)
         fill_u32_kernel<<<grid_rows, 256, 0, ctx->stream>>>(A->d_row_of, 0, A->h, 0, 1);
     }
     if (e1 != cudaSuccess) { set_error("SELL build (row order): %s", cudaGetErrorString(e1)); return NGSB_ERR_CUDA; }
+    A->row_identity = sigma <= 1;
     // ---- 2. slice widths, schedule, offsets
     {
         uint32_t *d_len = nullptr, *d_key = nullptr, *d_key2 = nullptr, *d_id = nullptr;
@@ -1028,7 +1030,7 @@ int sell_launch(const SpmvArgs &a)
     ngsb_ctx *ctx = A->ctx;
     SellParams p;
     memset(&p, 0, sizeof(p));
-    p.slice_off = A->d_slice_off; p.slice_src = A->d_slice_src; p.row_of = a.user_rows ? A->d_row_user : A->d_row_of; p.scol = A->d_scol; p.sval = A->d_sval;
+    p.slice_off = A->d_slice_off; p.slice_src = A->d_slice_src; p.row_of = a.user_rows ? A->d_row_user : (A->row_identity ? nullptr : A->d_row_of); p.scol = A->d_scol; p.sval = A->d_sval;
     p.slice_ovf = A->novf ? A->d_slice_ovf : nullptr;
     p.ovf_slot = A->d_ovf_slot; p.ovf_sum = A->d_ovf_sum; p.novf = A->novf;
     p.nslices = A->nslices; p.nrows = A->h;

@@ -63,6 +63,7 @@ struct ngsb_csr {
     uint32_t *d_iperm = nullptr;       // old -> new
     uint32_t *d_row_user = nullptr;    // (inner matrices) slot -> row in the CALLER's numbering, for y / the fused dot
     double *d_xperm = nullptr;         // (inner matrices) x gathered into the permuted numbering for one product
+    bool row_identity = false;         // SELL rows sit in slot order (d_row_of is the identity): the kernels skip the table
     bool csr_released = false;         // d_col / d_val were freed (inner matrices)
     double natural_c16_share = -1.0;   // share of natural slices fit for 16-bit column offsets (automatic reorder criterion)
     uint64_t uid = 0;                  // unique per created matrix (key of cached CUDA graphs)

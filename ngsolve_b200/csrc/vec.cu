@@ -555,6 +555,7 @@ extern "C" int ngsb_ctx_set_option(ngsb_ctx *ctx, const char *name, long value)
     else if (!strcmp(name, "timing")) { ctx->timing = value ? 1 : 0; }
     else if (!strcmp(name, "reorder")) { NGSB_REQUIRE(value >= -1 && value <= 1, "reorder must be -1 (automatic), 0 (off) or 1 (always)"); ctx->reorder = value; }
     else if (!strcmp(name, "csr_keep")) { NGSB_REQUIRE(value >= -1 && value <= 1, "csr_keep must be -1 (automatic), 0 (release) or 1 (keep)"); ctx->csr_keep = value; }
+    else if (!strcmp(name, "reorder_slot_order")) { NGSB_REQUIRE(value == 0 || value == 1, "reorder_slot_order must be 0 or 1"); ctx->reorder_slot_order = value; }
     else if (!strcmp(name, "reorder_min_rows")) { NGSB_REQUIRE(value >= 0, "reorder_min_rows must be >= 0"); ctx->reorder_min_rows = value; }
     else if (!strcmp(name, "cg_stream_hints")) { NGSB_REQUIRE(value == 0 || value == 1, "cg_stream_hints must be 0 or 1"); ctx->cg_stream_hints = value; }
     else if (!strcmp(name, "cg_chunked")) { NGSB_REQUIRE(value == 0 || value == 1, "cg_chunked must be 0 or 1"); ctx->cg_chunked = value; }

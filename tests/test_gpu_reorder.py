@@ -15,6 +15,17 @@ from test_oracle_reorder import _multi_component
 pytestmark = pytest.mark.gpu
 
 
+def internal_perm(rowptr, rcm, sigma=65536):
+    """the permutation option "reorder" uses: Cuthill-McKee composed with the SELL length sort (rows of the Cuthill-McKee order
+    sorted longest first, stably, inside windows of sigma rows; lengths capped at 2^20 - 1) -- restated in numpy"""
+    rcm = np.asarray(rcm, dtype=np.int64)
+    rp = np.asarray(rowptr).astype(np.int64)
+    lens = np.minimum(rp[rcm + 1] - rp[rcm], (1 << 20) - 1)
+    j = np.arange(len(rcm))
+    order = np.lexsort((j, -lens, j // sigma))
+    return rcm[order].astype(np.uint64)
+
+
 @pytest.fixture(scope="module")
 def la():
     import ngsolve_b200.la as la
@@ -181,6 +192,19 @@ def test_netgen_numbering_triggers_the_automatic_mode(la):
         ctx.set_option("reorder", -1)
     on, share, perm = dev.ReorderInfo(want_perm=True)
     assert on and np.array_equal(perm, g["perm"])
+    # option reorder_slot_order: the Cuthill-McKee order composed with the SELL length sort (A/B option, off by default)
+    ctx.set_option("reorder", 1)
+    ctx.set_option("reorder_slot_order", 1)
+    try:
+        dev2 = A.CreateDeviceMatrix()
+    finally:
+        ctx.set_option("reorder", -1)
+        ctx.set_option("reorder_slot_order", 0)
+    assert np.array_equal(dev2.ReorderInfo(want_perm=True)[2], internal_perm(g["rowptr"], g["perm"]))
+    x2 = la.BaseVector(g["x"])
+    y2 = dev2.CreateColVector()
+    dev2.Mult(x2, y2)
+    assert relerr(y2.NumPy(), g["y"]) <= 1e-12
     x = la.BaseVector(g["x"])
     y = dev.CreateColVector()
     dev.Mult(x, y)
