@@ -31,8 +31,8 @@ for r in rows[h0 + 1:]:
 print("# ncu --metrics gpu__time_duration.sum --clock-control none: %s" % cmd)
 print("# (cold-cache, serialised launches: compare SHARES, not absolutes).  'real' = launches that did work; the others are")
 print("# iterations of a batch enqueued after the device-side `done` flag was set: they return in ~3 us.\n")
-iter_kernels = OrderedDict((k, v) for k, v in per.items() if any(t in k for t in ("sell_spmv_kernel", "cg_fused_kernel<0, 1>", "cg_fused_kernel<1, 1>",
-                                                                                  "cg_fused_kernel<3, 1>", "cg_dir_kernel", "halo_", "cg_finalize")))
+iter_kernels = OrderedDict((k, v) for k, v in per.items() if any(t in k for t in ("sell_spmv_kernel", "cg_fused_kernel<0, 1", "cg_fused_kernel<1, 1",
+                                                                                  "cg_fused_kernel<3, 1", "cg_dir_kernel", "halo_", "cg_finalize")))
 real = {k: [t for t in v if t > 20.0] for k, v in iter_kernels.items()}
 step = sum(statistics.mean(v) for v in real.values() if v)
 print("CG iteration kernels (real launches only):")
