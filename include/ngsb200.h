@@ -79,6 +79,8 @@ int ngsb_ctx_launch_count(const ngsb_ctx *ctx, uint64_t *count);
  *     "spmv_algo"        0 auto (= 3), 1 sub-warp CSR, 2 TMA-streamed CSR, 3 SELL-32
  *     "spmv_ctas_per_sm" grid of the SpMV kernels in CTAs per SM, 0 = default (96 for SELL)
  *     "cg_batch"         CG iterations per CUDA graph / between two polls of the device stop flag (default 16)
+ *     "cg_persistent"    real Jacobi-PCG (CGSolver<double> + JacobiPrecond) as ONE persistent cooperative kernel, grid barriers instead
+ *                        of three kernel launches per iteration: -1 automatic (default: matrices below 4 M rows), 0 off, 1 on
  *     "cg_stream_hints"  0/1: the CG update kernel loads u, d, As, diagonal streaming and stores u, d evict-first (default 0; A/B)
  *     "cg_chunked"       0/1: the CG update kernel works on one contiguous chunk per CTA instead of grid-stride (default 0; A/B)
  *     "cg_fold_u"        0/1: the CG direction kernel also does u += al s (10 instead of 11 vector passes per iteration)

@@ -561,6 +561,32 @@ int cg_solve_device(const ngsb_csr *A, const ngsb_jacobi *C, const double *f, do
     }
     NGSB_TRY(launch_cg_fused<0>(ctx, A->kind, v, sub));
 
+    // Small real systems: the whole loop as one persistent cooperative kernel (sell.cu, cg_persistent_kernel) -- grid barriers
+    // instead of three kernel boundaries per iteration.  Automatic below 4 M rows (above, the wide grid of the product
+    // kernel and its sliding x windows win); option cg_persistent 0 / 1 forces it off / on.
+    {
+        const bool want = ctx->cg_persistent == 1 || (ctx->cg_persistent < 0 && A->h < (4u << 20));
+        if (want && !ctx->timing && sell_path(ctx) && cg_persistent_applicable(A, v)) {
+            int rc = cg_persistent_launch(A, v, maxsteps + 1);
+            cudaError_t e = cudaStreamSynchronize(ctx->stream);
+            if (rc == NGSB_OK && e != cudaSuccess) { set_error("CG (persistent kernel): %s", cudaGetErrorString(e)); rc = NGSB_ERR_CUDA; }
+            if (rc == NGSB_OK && Auser != A) rc = launch_perm_gather(ctx, u, Auser->d_iperm, Auser->h, (int)kind_scalars(A->kind), u_user);
+            if (rc == NGSB_OK) {
+                NGSB_CUDA(cudaMemcpyAsync(&hs[3], ws->d_state, sizeof(CgState), cudaMemcpyDeviceToHost, ctx->stream));
+                NGSB_CUDA(cudaStreamSynchronize(ctx->stream));
+                if (steps) *steps = hs[3].n;
+                const int nh = hs[3].nhist;
+                if (nhist) *nhist = nh;
+                const int ncopy = nh < hist_cap ? nh : hist_cap;
+                if (history && ncopy > 0) {
+                    NGSB_CUDA(cudaMemcpyAsync(history, ws->d_hist, ncopy * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+                    NGSB_CUDA(cudaStreamSynchronize(ctx->stream));
+                }
+                ctx->launches += 1;
+            }
+            return rc;
+        }
+    }
     // iterate in batches; the stop flag is polled one batch behind the enqueue front
     const long batch = ctx->cg_batch;
     const bool use_graph = !ctx->timing && getenv("NGSB_NO_CUDA_GRAPH") == nullptr && batch > 1;

@@ -48,6 +48,10 @@ struct GmresDist {
 int gmres_solve_impl(const ngsb_csr *A, const ngsb_jacobi *C, const ngsb_vec *f, ngsb_vec *x, double prec, int maxsteps,
                      int initialize, int *steps, double *history, int hist_cap, int *nhist, const GmresDist *dist);
 
+// the whole real Jacobi-PCG loop as one persistent cooperative kernel (sell.cu)
+bool cg_persistent_applicable(const ngsb_csr *A, const CgVecs &v);
+int cg_persistent_launch(const ngsb_csr *A, const CgVecs &v, int iters);
+
 // solver workspace (cached on the context)
 int ws_get_buf(ngsb_ctx *ctx, size_t nscal, double **out);
 void ws_put_buf(ngsb_ctx *ctx, size_t nscal, double *p);

@@ -20,7 +20,7 @@
 // Grid-stride kernel (about 96 CTAs per SM, 8 slices per CTA step, interleaved so that the resident CTAs sweep each
 // stripe of the schedule as one moving window and x lines are shared through L1/L2); it fuses
 // y = s A x (+ y), the dot <dotvec, result> and the CG scalar step (deterministic last-block finish).
-#include "spmv.cuh"
+#include "krylov.cuh"
 #include "peer.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
@@ -546,6 +546,303 @@ __global__ void __launch_bounds__(256, MINB) sell_spmv_kernel(const SellParams p
         if ((int)threadIdx.x < H->npeers) st_release_sys(H->peer_flags[threadIdx.x] + (xseq & 1) * NGSB_MAX_RANKS + H->rank, xseq);
         if (p.push->R) pr_push_warp(*p.push->R, a, b);
     }
+}
+
+// ------------------------------------------------------------------------------------------
+// The whole Jacobi-PCG loop of a small real system as ONE persistent cooperative kernel.
+//
+// Below a few million rows an iteration is three short kernels (1 M dofs: about 95 + 12 + 6 us of work) and the three kernel
+// boundaries -- drain, launch, ramp-up against an L2 full of the previous kernel's dirty lines -- cost as much as a third
+// of it (167 us per iteration measured on BASELINE configs[0]).  Here the grid stays resident (one launch per solve or per
+// batch), the phases of CGSolver<double>::Mult (linalg/cg.cpp:593-620) are separated by grid barriers, and the scalars
+// kss, al, wdn, be and the loop condition are computed redundantly but identically by every block from per-block partials
+// summed in a fixed order -- no block waits for another one's scalar step.
+//   phase A  as = A s (SELL slices, same loops and summation order as sell_spmv_kernel), partial <s, as>      | barrier
+//   phase B  al = wd / kss;  u += al s;  d -= al as;  w = C d;  partial <d, w>                                 | barrier
+//   phase C  be = wdn / wd;  history;  loop condition;  s = be s + w                                           | barrier
+// ------------------------------------------------------------------------------------------
+struct CgPersistParams {
+    SellParams sp;
+    CgVecs v;
+    double *part_a, *part_b;        // per-block partials of the two dots
+    unsigned int *bar_count;
+    unsigned int *bar_gen;
+    int iters;                      // iterations this launch may run
+};
+
+__device__ __forceinline__ void grid_barrier(unsigned int *count, unsigned int *gen, unsigned int nblocks)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int g = *(volatile unsigned int *)gen;
+        __threadfence();
+        if (atomicAdd(count, 1u) == nblocks - 1) {
+            *(volatile unsigned int *)count = 0;
+            __threadfence();
+            atomicAdd(gen, 1u);
+        } else {
+            while (*(volatile unsigned int *)gen == g) { }
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// sum of the per-block partials in a fixed order, by every block for itself (result in all threads)
+__device__ __forceinline__ double block_sum_partials(const double *part, unsigned int n, double *red)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    double a = 0.0;
+    for (unsigned int k = threadIdx.x; k < n; k += blockDim.x) a += __ldcg(part + k);
+    a = warp_sum_s(a);
+    __syncthreads();
+    if (lane == 0) red[wid] = a;
+    __syncthreads();
+    double t = 0.0;
+    const int nw = blockDim.x >> 5;
+    for (int w = 0; w < nw; w++) t += red[w];
+    return t;
+}
+
+// one row of a real SELL slice (compressed or 32-bit columns): the software-pipelined default loops of sell_spmv_kernel
+__device__ __forceinline__ double sell_row_real(const SellParams &p, uint64_t s, uint64_t off, uint32_t width, int lane)
+{
+    double s0 = 0.0;
+    const double2 *v2 = reinterpret_cast<const double2 *>(p.sval + off) + lane;
+    const uint32_t np = width >> 1;
+    uint32_t q = 0;
+    if (p.slice_c16 != nullptr && p.slice_c16[s]) {
+        const unsigned int *h2 = reinterpret_cast<const unsigned int *>(p.scol16 + off) + lane;
+        const int2 *b2 = reinterpret_cast<const int2 *>(p.sbase + (off >> 5));
+#define NGSB_C16(h, b, c0, c1) { c0 = (b).x + (int)((h) & 0xffffu); c1 = (b).y + (int)((h) >> 16); }
+        if (np >= 4) {
+            double2 va = ldg_stream_d2(v2), vb = ldg_stream_d2(v2 + 32), vc = ldg_stream_d2(v2 + 64), vd = ldg_stream_d2(v2 + 96);
+            int ca0, ca1, cb0, cb1, cc0, cc1, cd0, cd1;
+            {
+                const unsigned int ha = ldg_stream_u32(h2), hb = ldg_stream_u32(h2 + 32), hc = ldg_stream_u32(h2 + 64), hd = ldg_stream_u32(h2 + 96);
+                const int2 ba = __ldg(b2), bb = __ldg(b2 + 1), bc = __ldg(b2 + 2), bd = __ldg(b2 + 3);
+                NGSB_C16(ha, ba, ca0, ca1) NGSB_C16(hb, bb, cb0, cb1) NGSB_C16(hc, bc, cc0, cc1) NGSB_C16(hd, bd, cd0, cd1)
+            }
+            for (q = 4; q + 4 <= np; q += 4) {
+                double x0 = __ldg(p.x + ca0), x1 = __ldg(p.x + ca1), x2 = __ldg(p.x + cb0), x3 = __ldg(p.x + cb1);
+                double x4 = __ldg(p.x + cc0), x5 = __ldg(p.x + cc1), x6 = __ldg(p.x + cd0), x7 = __ldg(p.x + cd1);
+                double2 na = ldg_stream_d2(v2 + (q + 0) * 32), nb = ldg_stream_d2(v2 + (q + 1) * 32);
+                double2 nc = ldg_stream_d2(v2 + (q + 2) * 32), nd = ldg_stream_d2(v2 + (q + 3) * 32);
+                const unsigned int ha = ldg_stream_u32(h2 + (q + 0) * 32), hb = ldg_stream_u32(h2 + (q + 1) * 32);
+                const unsigned int hc = ldg_stream_u32(h2 + (q + 2) * 32), hd = ldg_stream_u32(h2 + (q + 3) * 32);
+                const int2 ba = __ldg(b2 + q), bb = __ldg(b2 + q + 1), bc = __ldg(b2 + q + 2), bd = __ldg(b2 + q + 3);
+                s0 = fma(va.x, x0, s0); s0 = fma(va.y, x1, s0); s0 = fma(vb.x, x2, s0); s0 = fma(vb.y, x3, s0);
+                s0 = fma(vc.x, x4, s0); s0 = fma(vc.y, x5, s0); s0 = fma(vd.x, x6, s0); s0 = fma(vd.y, x7, s0);
+                va = na; vb = nb; vc = nc; vd = nd;
+                NGSB_C16(ha, ba, ca0, ca1) NGSB_C16(hb, bb, cb0, cb1) NGSB_C16(hc, bc, cc0, cc1) NGSB_C16(hd, bd, cd0, cd1)
+            }
+            double x0 = __ldg(p.x + ca0), x1 = __ldg(p.x + ca1), x2 = __ldg(p.x + cb0), x3 = __ldg(p.x + cb1);
+            double x4 = __ldg(p.x + cc0), x5 = __ldg(p.x + cc1), x6 = __ldg(p.x + cd0), x7 = __ldg(p.x + cd1);
+            s0 = fma(va.x, x0, s0); s0 = fma(va.y, x1, s0); s0 = fma(vb.x, x2, s0); s0 = fma(vb.y, x3, s0);
+            s0 = fma(vc.x, x4, s0); s0 = fma(vc.y, x5, s0); s0 = fma(vd.x, x6, s0); s0 = fma(vd.y, x7, s0);
+        }
+        for (; q < np; q++) {
+            const double2 va = ldg_stream_d2(v2 + q * 32);
+            const unsigned int ha = ldg_stream_u32(h2 + q * 32);
+            const int2 ba = __ldg(b2 + q);
+            int c0, c1;
+            NGSB_C16(ha, ba, c0, c1)
+            s0 = fma(va.x, __ldg(p.x + c0), s0);
+            s0 = fma(va.y, __ldg(p.x + c1), s0);
+        }
+#undef NGSB_C16
+        return s0;
+    }
+    const int2 *c2 = reinterpret_cast<const int2 *>(p.scol + off) + lane;
+    if (np >= 4) {
+        double2 va = ldg_stream_d2(v2), vb = ldg_stream_d2(v2 + 32), vc = ldg_stream_d2(v2 + 64), vd = ldg_stream_d2(v2 + 96);
+        int2 ca = ldg_stream_i2(c2), cb = ldg_stream_i2(c2 + 32), cc = ldg_stream_i2(c2 + 64), cd = ldg_stream_i2(c2 + 96);
+        for (q = 4; q + 4 <= np; q += 4) {
+            double x0 = __ldg(p.x + ca.x), x1 = __ldg(p.x + ca.y), x2 = __ldg(p.x + cb.x), x3 = __ldg(p.x + cb.y);
+            double x4 = __ldg(p.x + cc.x), x5 = __ldg(p.x + cc.y), x6 = __ldg(p.x + cd.x), x7 = __ldg(p.x + cd.y);
+            double2 na = ldg_stream_d2(v2 + (q + 0) * 32), nb = ldg_stream_d2(v2 + (q + 1) * 32);
+            double2 nc = ldg_stream_d2(v2 + (q + 2) * 32), nd = ldg_stream_d2(v2 + (q + 3) * 32);
+            int2 ea = ldg_stream_i2(c2 + (q + 0) * 32), eb = ldg_stream_i2(c2 + (q + 1) * 32);
+            int2 ec = ldg_stream_i2(c2 + (q + 2) * 32), ed = ldg_stream_i2(c2 + (q + 3) * 32);
+            s0 = fma(va.x, x0, s0); s0 = fma(va.y, x1, s0); s0 = fma(vb.x, x2, s0); s0 = fma(vb.y, x3, s0);
+            s0 = fma(vc.x, x4, s0); s0 = fma(vc.y, x5, s0); s0 = fma(vd.x, x6, s0); s0 = fma(vd.y, x7, s0);
+            va = na; vb = nb; vc = nc; vd = nd; ca = ea; cb = eb; cc = ec; cd = ed;
+        }
+        double x0 = __ldg(p.x + ca.x), x1 = __ldg(p.x + ca.y), x2 = __ldg(p.x + cb.x), x3 = __ldg(p.x + cb.y);
+        double x4 = __ldg(p.x + cc.x), x5 = __ldg(p.x + cc.y), x6 = __ldg(p.x + cd.x), x7 = __ldg(p.x + cd.y);
+        s0 = fma(va.x, x0, s0); s0 = fma(va.y, x1, s0); s0 = fma(vb.x, x2, s0); s0 = fma(vb.y, x3, s0);
+        s0 = fma(vc.x, x4, s0); s0 = fma(vc.y, x5, s0); s0 = fma(vd.x, x6, s0); s0 = fma(vd.y, x7, s0);
+    }
+    for (; q < np; q++) {
+        double2 va = ldg_stream_d2(v2 + q * 32);
+        int2 ca = ldg_stream_i2(c2 + q * 32);
+        s0 = fma(va.x, __ldg(p.x + ca.x), s0);
+        s0 = fma(va.y, __ldg(p.x + ca.y), s0);
+    }
+    return s0;
+}
+
+__global__ void __launch_bounds__(256, 4) cg_persistent_kernel(const CgPersistParams P)
+{
+    __shared__ double red[8];
+    const SellParams &p = P.sp;
+    const CgVecs &v = P.v;
+    CgState *st = v.state;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned int nb = gridDim.x;
+    // every block carries the scalar state of the loop itself -- in shared memory, so that the streaming loops of phase A
+    // keep their registers (all threads compute the same values; thread 0 stores them)
+    __shared__ double sh_wdn;
+    __shared__ int sh_n, sh_nhist, sh_done;
+    if (threadIdx.x == 0) { sh_wdn = st->wdn[0]; sh_n = st->n; sh_nhist = st->nhist; sh_done = st->done; }
+    __syncthreads();
+    for (int it = 0; it < P.iters && !sh_done; it++) {
+        // ---- phase A: as = A s, partial <s, as>
+        double dr = 0.0;
+        for (uint64_t s = (uint64_t)blockIdx.x * 8 + wid; s < p.nslices; s += (uint64_t)nb * 8) {
+            const uint64_t off = p.slice_off[s];
+            const uint32_t width = (uint32_t)((p.slice_off[s + 1] - off) >> 5);
+            const uint32_t slot = (uint32_t)((uint64_t)p.slice_src[s] * 32 + lane);
+            const uint32_t row = p.row_of != nullptr ? p.row_of[slot] : ((uint64_t)slot < p.nrows ? slot : 0xffffffffu);
+            const double r = sell_row_real(p, s, off, width, lane);
+            if (row != 0xffffffffu) {
+                p.y[row] = r;
+                dr = fma(p.x[row], r, dr);
+            }
+        }
+        dr = warp_sum_s(dr);
+        __syncthreads();
+        if (lane == 0) red[wid] = dr;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+            for (int w = 0; w < 8; w++) t += red[w];
+            P.part_a[blockIdx.x] = t;
+        }
+        grid_barrier(P.bar_count, P.bar_gen, nb);
+        const double kss = block_sum_partials(P.part_a, nb, red);
+        const double wd = sh_wdn;
+        if (kss == 0.0) {                                         // `if (kss == 0.0) break;` (uniform over the grid)
+            __syncthreads();
+            if (threadIdx.x == 0) sh_done = 1;
+            __syncthreads();
+            break;
+        }
+        const double al = wd / kss;
+        const uint64_t first = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, step = (uint64_t)nb * blockDim.x;
+        const uint64_t n2 = v.n & ~(uint64_t)1;
+        // ---- phase B: u += al s, d -= al as, w = C d, partial <d, w>
+        double acc0 = 0.0, acc1 = 0.0;
+        for (uint64_t i = 2 * first; i < n2; i += 2 * step) {
+            const double2 a2 = *reinterpret_cast<const double2 *>(v.as + i);
+            const double2 m2 = *reinterpret_cast<const double2 *>(v.invdiag + i);
+            const double2 s2 = *reinterpret_cast<const double2 *>(v.s + i);
+            double2 d2 = *reinterpret_cast<double2 *>(v.d + i);
+            double2 u2 = *reinterpret_cast<double2 *>(v.u + i);
+            u2.x += al * s2.x; u2.y += al * s2.y;
+            d2.x -= al * a2.x; d2.y -= al * a2.y;
+            const unsigned bits = v.bits ? (unsigned)(v.bits[i >> 3] >> (i & 7)) : 3u;
+            double2 w2;
+            w2.x = (bits & 1u) ? m2.x * d2.x : 0.0;
+            w2.y = (bits & 2u) ? m2.y * d2.y : 0.0;
+            *reinterpret_cast<double2 *>(v.u + i) = u2;
+            *reinterpret_cast<double2 *>(v.d + i) = d2;
+            *reinterpret_cast<double2 *>(v.w + i) = w2;
+            acc0 = fma(d2.x, w2.x, acc0);
+            acc1 = fma(d2.y, w2.y, acc1);
+        }
+        if (n2 < v.n && first == 0) {
+            const uint64_t i = n2;
+            v.u[i] += al * v.s[i];
+            const double dn = v.d[i] - al * v.as[i];
+            const double wn = (v.bits == nullptr || ((v.bits[i >> 3] >> (i & 7)) & 1)) ? v.invdiag[i] * dn : 0.0;
+            v.d[i] = dn;
+            v.w[i] = wn;
+            acc0 = fma(dn, wn, acc0);
+        }
+        acc0 += acc1;
+        acc0 = warp_sum_s(acc0);
+        __syncthreads();
+        if (lane == 0) red[wid] = acc0;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+            for (int w = 0; w < 8; w++) t += red[w];
+            P.part_b[blockIdx.x] = t;
+        }
+        grid_barrier(P.bar_count, P.bar_gen, nb);
+        const double wdn = block_sum_partials(P.part_b, nb, red);
+        const double be = wdn / wd;
+        if (threadIdx.x == 0) {
+            if (blockIdx.x == 0 && sh_nhist < st->hist_cap) v.hist[sh_nhist] = fabs(wdn);
+            sh_nhist++;
+            sh_wdn = wdn;
+            // `while (n++ < maxsteps && Abs(wdn) > err)` of the next pass
+            sh_done = !((sh_n++ < st->maxsteps) && (fabs(wdn) > st->err));
+        }
+        // ---- phase C: s = be s + w  (two roundings, like `s *= be; s += w`); also when the loop ends here, like the reference
+        for (uint64_t i = 2 * first; i < n2; i += 2 * step) {
+            const double2 a = *reinterpret_cast<const double2 *>(v.s + i);
+            const double2 b = *reinterpret_cast<const double2 *>(v.w + i);
+            *reinterpret_cast<double2 *>(v.s + i) = make_double2(__dadd_rn(__dmul_rn(a.x, be), b.x), __dadd_rn(__dmul_rn(a.y, be), b.y));
+        }
+        if (n2 < v.n && first == 0) v.s[n2] = __dadd_rn(__dmul_rn(v.s[n2], be), v.w[n2]);
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            st->wd[0] = wd; st->kss[0] = kss; st->al[0] = al; st->be[0] = be;
+        }
+        grid_barrier(P.bar_count, P.bar_gen, nb);
+    }
+    __syncthreads();
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        st->wdn[0] = sh_wdn; st->wdn[1] = 0.0;
+        st->n = sh_n;
+        st->nhist = sh_nhist;
+        st->done = sh_done;
+    }
+}
+
+// can this solve run as the persistent kernel?  (real, Jacobi, no overflow rows, everything 16-byte aligned)
+bool cg_persistent_applicable(const ngsb_csr *A, const CgVecs &v)
+{
+    if (A->kind != NGSB_REAL || A->novf != 0 || A->nslices == 0 || v.invdiag == nullptr || v.master != nullptr || v.dot_out != nullptr || v.R != nullptr) return false;
+    if (v.fold_u || v.ip_mode != NGSB_IP_REAL) return false;
+    const uintptr_t al = reinterpret_cast<uintptr_t>(v.u) | reinterpret_cast<uintptr_t>(v.d) | reinterpret_cast<uintptr_t>(v.w) | reinterpret_cast<uintptr_t>(v.s) |
+                         reinterpret_cast<uintptr_t>(v.as) | reinterpret_cast<uintptr_t>(v.invdiag);
+    return (al & 15) == 0;
+}
+
+// run up to `iters` iterations of the loop whose state lives in v.state (initialised by the init kernel)
+int cg_persistent_launch(const ngsb_csr *A, const CgVecs &v, int iters)
+{
+    ngsb_ctx *ctx = A->ctx;
+    static int occ = 0;
+    if (occ == 0) {
+        NGSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cg_persistent_kernel, 256, 0));
+        if (occ < 1) { set_error("persistent CG: the kernel does not fit an SM"); return NGSB_ERR_UNSUPPORTED; }
+    }
+    uint64_t grid = (uint64_t)ctx->sm_count * (uint64_t)occ;
+    const uint64_t need = ((uint64_t)A->nslices + 7) / 8;
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    CgPersistParams P;
+    memset(&P, 0, sizeof(P));
+    SellParams &p = P.sp;
+    p.slice_off = A->d_slice_off; p.slice_src = A->d_slice_src; p.row_of = A->row_identity ? nullptr : A->d_row_of; p.scol = A->d_scol; p.sval = A->d_sval;
+    if (A->sell_c16_entries > 0 && ctx->sell_c16 != 0) { p.scol16 = A->d_scol16; p.sbase = A->d_sbase; p.slice_c16 = A->d_slice_c16; }
+    p.nslices = A->nslices; p.nrows = A->h;
+    p.x = v.s; p.y = const_cast<double *>(v.as);
+    P.v = v;
+    // partials and barrier words live behind the reduction workspace of the context (the fused kernels are not running)
+    P.part_a = ctx->d_partials;
+    P.part_b = ctx->d_partials + 8192;
+    P.bar_count = ctx->d_counter + 2;
+    P.bar_gen = ctx->d_counter + 3;
+    P.iters = iters;
+    NGSB_REQUIRE(grid <= 8192, "persistent CG: grid too large");
+    void *args[] = {(void *)&P};
+    SpanGuard g(ctx, KC_SPMV);
+    NGSB_CUDA(cudaLaunchCooperativeKernel((const void *)cg_persistent_kernel, dim3((unsigned)grid), dim3(256), args, 0, ctx->stream));
+    return NGSB_OK;
 }
 
 // SparseMatrix<double>::MultAdd(FlatVector alpha, MultiVector x, MultiVector y) (linalg/sparsematrix.cpp:2274-2351): four

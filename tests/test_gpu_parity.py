@@ -130,11 +130,14 @@ def test_jacobi(la, sysm):
     assert relerr(y2.NumPy().reshape(-1), g["jac_mult"]) <= 1e-13
 
 
-@pytest.mark.parametrize("graph", [True, False])
+@pytest.mark.parametrize("graph", [True, False, "three-kernels"])
 def test_cg_fused_matches_reference(la, sysm, graph, monkeypatch):
+    """graph = True: the default path (real + Jacobi below 4 M rows: the persistent cooperative kernel; everything else CUDA
+    graphs of 16 iterations x 3 kernels); False: no CUDA graphs; "three-kernels": option cg_persistent = 0"""
     name, g, A, dev = sysm
-    if not graph:
+    if graph is False:
         monkeypatch.setenv("NGSB_NO_CUDA_GRAPH", "1")
+    dev.ctx.set_option("cg_persistent", 0 if graph == "three-kernels" or graph is False else -1)
     kind = kind_of(g)
     jac = A.CreateSmoother(la.BitArray(g["freebits"]))
     f = vec(la, g, g["f"])
@@ -157,6 +160,7 @@ def test_cg_fused_matches_reference(la, sysm, graph, monkeypatch):
     ou, osteps, ohist = orc.cg_solve(oA, orc.Jacobi(oA, g["freebits"]), g["f"], prec=float(g["cg_prec"]), maxsteps=int(g["cg_maxsteps"]))
     assert abs(inv.GetSteps() - osteps) <= slack
     assert np.allclose(inv.history[:k], ohist[:k], rtol=1e-6, atol=0)
+    dev.ctx.set_option("cg_persistent", -1)
     # exit by maxsteps: 7 iterations -> GetSteps() == 8
     inv7 = la.CGSolver(dev, jac, precision=1e-30, maxsteps=7)
     u7 = (inv7 * f).Evaluate()
@@ -489,3 +493,35 @@ def test_cg_graph_is_updated_for_fresh_result_vectors(la):
         assert relerr(uk.NumPy().reshape(-1), (k + 1.0) * ref) <= 1e-9
     inv.Mult(f, u0)
     assert np.array_equal(u0.NumPy(), ref)
+
+
+def test_persistent_cg_kernel_equals_three_kernel_loop(la):
+    """the persistent cooperative kernel (real Jacobi-PCG below 4 M rows) against the three-kernel loop on the same system: same
+    steps, same residual history to rounding, same solution; exit by maxsteps; odd vector length; start value"""
+    g = load_golden("poisson_h1p3")
+    A = host_matrix(la, g)
+    dev = A.CreateDeviceMatrix()
+    ctx = dev.ctx
+    jac = dev.CreateSmoother(la.BitArray(g["freebits"]))
+    f = vec(la, g, g["f"])
+    res = {}
+    for mode in (1, 0):
+        ctx.set_option("cg_persistent", mode)
+        l0 = ctx.launches
+        inv = la.CGSolver(dev, jac, precision=float(g["cg_prec"]), maxsteps=int(g["cg_maxsteps"]))
+        u = (inv * f).Evaluate()
+        short = la.CGSolver(dev, jac, precision=1e-30, maxsteps=7)
+        us = (short * f).Evaluate()
+        u2 = u.CreateVector()
+        u2.data = us
+        cont = la.CGSolver(dev, jac, precision=1e-6, maxsteps=int(g["cg_maxsteps"]))
+        cont.Mult(f, u2, initialize=False)
+        res[mode] = (inv.GetSteps(), inv.history.copy(), u.NumPy().copy(), short.GetSteps(), us.NumPy().copy(), cont.GetSteps(), u2.NumPy().copy(), ctx.launches - l0)
+    ctx.set_option("cg_persistent", -1)
+    p, t = res[1], res[0]
+    assert p[0] == t[0] and abs(p[0] - int(g["cg_steps"])) <= 2
+    assert len(p[1]) == len(t[1]) and np.allclose(p[1][:20], t[1][:20], rtol=1e-9, atol=0)     # later entries drift with the rounding
+    assert relerr(p[2], t[2]) <= 1e-9 and relerr(p[2], g["cg_u"]) <= 1e-6
+    assert p[3] == t[3] == 8 and relerr(p[4], t[4]) <= 1e-12           # exit by maxsteps: GetSteps() = maxsteps + 1
+    assert abs(p[5] - t[5]) <= 1 and relerr(p[6], t[6]) <= 1e-7
+    assert p[7] < t[7] / 10                                              # a handful of launches instead of three per iteration
