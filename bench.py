@@ -219,6 +219,14 @@ def netgen_big(nref, extra, timeout=1500):
     env = _reference_env()
     if env is None:
         return None
+    if nref >= 3:
+        # the 108 M-dof system needs about 80 GB of host memory while NGSolve holds it: fall back to two refinements (13.6 M dofs)
+        try:
+            avail = [int(l.split()[1]) for l in open("/proc/meminfo") if l.startswith("MemAvailable")][0] / 2 ** 20
+            if avail < 110:
+                nref = 2
+        except Exception:
+            pass
     try:
         r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "netgen_big.py"), "--nref", str(nref)] + extra, env=env,
                            capture_output=True, text=True, timeout=timeout)

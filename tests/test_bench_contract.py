@@ -13,8 +13,10 @@ BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_ste
 
 
 def test_reference_arm_prints_one_contract_line():
+    # --netgen-nref 0: the reference arm's netgen system without refinement (46 k tets; the default, 3 refinements = 108 M dofs,
+    # is for the GPU box); without the reference build the oracle port on the tiny generator sample stands in
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--size", "12", "--steps", "3", "--warmup", "1",
-                        "--cpu-sample", "6", "--cpu-sample-t1", "4"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+                        "--cpu-sample", "6", "--cpu-sample-t1", "4", "--netgen-nref", "0"], capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.strip()]
     assert len(lines) == 1, r.stdout
@@ -33,6 +35,17 @@ def test_reference_arm_other_ranks_exit_quietly():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"], capture_output=True, text=True,
                        timeout=120, cwd=ROOT, env=env)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_round2_line_carries_the_netgen_check():
+    d = json.load(open(os.path.join(ROOT, "profiles", "r2_bench_n1.json")))
+    assert BASE_KEYS | {"roofline", "clocks"} <= set(d)
+    ng = d["config"]["netgen_check"]
+    assert ng["ndof"] > 100e6 and ng["reordered"] is True and ng["cg_it_per_s"] > 0 and ng["cpu_reference_it_per_s"] > 0
+    assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["sample_ndof"] == ng["ndof"]     # measured at full size
+    rf = d["roofline"]
+    assert abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-12 and rf["traffic"] > 0
+    assert d["e2e"]["value"] < d["value"] and d["gpu_launches"] > 0
 
 
 def test_committed_gpu_line_keeps_the_contract():
