@@ -196,6 +196,13 @@ int ngsb_csr_layout(const ngsb_csr *A, uint64_t *sell_entries, uint32_t *overflo
  * store 16-bit column offsets per slice where the columns of one entry step lie within 65535 of each
  * other: 10.125 instead of 12 bytes per entry); *c16_entries = padded entries in such slices */
 int ngsb_csr_stream_bytes(const ngsb_csr *A, double *bytes, uint64_t *c16_entries);
+/* Checkpoint wire format of a device system: the bytes SparseMatrix<TM>::DoArchive writes into ngcore's BinaryOutArchive
+ * (linalg/sparsematrix_impl.hpp:443-452; raw little-endian: size_t size, width, nze; Array<size_t> firsti; Array<int> colnr;
+ * Array<TM> data, each array as size_t count + elements).  What _write produces the reference's BinaryInArchive reads, and
+ * _create_from_archive reads what the reference wrote. */
+int ngsb_csr_archive_size(const ngsb_csr *A, size_t *bytes);
+int ngsb_csr_archive_write(const ngsb_csr *A, void *buf, size_t capacity);
+int ngsb_csr_create_from_archive(ngsb_ctx *ctx, const void *buf, size_t bytes, int kind, ngsb_csr **out);
 /* device memory the matrix holds right now: row pointers + (if resident) the uploaded CSR arrays [+ permutation tables];
  * the SELL copy the products stream; whether the CSR arrays are resident (option csr_keep) */
 int ngsb_csr_memory(const ngsb_csr *A, uint64_t *csr_bytes, uint64_t *sell_bytes, int *csr_resident);

@@ -65,6 +65,9 @@ PROTOTYPES = {
     "ngsb_csr_reorder": [_vp, _vp, _pvp],
     "ngsb_csr_rcm": [_vp, _vp],
     "ngsb_csr_memory": [_vp, _vp, _vp, _vp],
+    "ngsb_csr_archive_size": [_vp, C.POINTER(_sz)],
+    "ngsb_csr_archive_write": [_vp, _vp, _sz],
+    "ngsb_csr_create_from_archive": [_vp, _vp, _sz, _i, _pvp],
     "ngsb_csr_reorder_info": [_vp, _vp, _vp, _vp],
     "ngsb_csr_download": [_vp, _vp, _vp, _vp],
     "ngsb_csr_mult_bytes": [_vp, C.POINTER(_d)],

@@ -268,3 +268,63 @@ extern "C" int ngsb_csr_memory(const ngsb_csr *A, uint64_t *csr_bytes, uint64_t 
     if (csr_resident) *csr_resident = A->csr_released ? 0 : 1;
     return NGSB_OK;
 }
+
+// ---- checkpoint wire format: SparseMatrix<TM>::DoArchive (linalg/sparsematrix_impl.hpp:443-452) into ngcore's BinaryOutArchive
+// (raw little-endian scalars; Array<T> = size_t count + elements):
+//   size_t size, width, nze | size_t n = size + 1, size_t firsti[n] | size_t nze, int colnr[nze] | size_t nze, TM data[nze]
+// A device system written here is read by the reference's BinaryInArchive + DoArchive and vice versa.
+static size_t archive_bytes(size_t h, size_t nnz, size_t ms) { return 24 + 8 + 8 * (h + 1) + 8 + 4 * nnz + 8 + 8 * ms * nnz; }
+
+extern "C" int ngsb_csr_archive_size(const ngsb_csr *A, size_t *bytes)
+{
+    NGSB_REQUIRE(A && bytes, "ngsb_csr_archive_size: NULL argument");
+    *bytes = archive_bytes(A->h, A->nnz, kind_matscalars(A->kind));
+    return NGSB_OK;
+}
+
+extern "C" int ngsb_csr_archive_write(const ngsb_csr *A, void *buf, size_t capacity)
+{
+    NGSB_REQUIRE(A && buf, "ngsb_csr_archive_write: NULL argument");
+    const size_t ms = kind_matscalars(A->kind), need = archive_bytes(A->h, A->nnz, ms);
+    NGSB_REQUIRE(capacity >= need, "ngsb_csr_archive_write: buffer of %zu bytes, %zu needed", capacity, need);
+    char *p = (char *)buf;
+    auto put = [&](uint64_t v) { memcpy(p, &v, 8); p += 8; };
+    put(A->h); put(A->w); put(A->nnz);
+    put(A->h + 1);
+    uint64_t *rp = (uint64_t *)p; p += 8 * (A->h + 1);
+    put(A->nnz);
+    int32_t *col = (int32_t *)p; p += 4 * A->nnz;
+    put(A->nnz);
+    // the three array sections are not 8-byte aligned in general: download into aligned scratch only when needed
+    if (((uintptr_t)p & 7) == 0 && ((uintptr_t)col & 3) == 0 && ((uintptr_t)rp & 7) == 0) return ngsb_csr_download(A, rp, col, p);
+    std::vector<uint64_t> trp(A->h + 1);
+    std::vector<int32_t> tcol(A->nnz);
+    std::vector<double> tval(A->nnz * ms);
+    NGSB_TRY(ngsb_csr_download(A, trp.data(), tcol.data(), tval.data()));
+    memcpy(rp, trp.data(), 8 * (A->h + 1));
+    memcpy(col, tcol.data(), 4 * A->nnz);
+    memcpy(p, tval.data(), 8 * ms * A->nnz);
+    return NGSB_OK;
+}
+
+extern "C" int ngsb_csr_create_from_archive(ngsb_ctx *ctx, const void *buf, size_t bytes, int kind, ngsb_csr **out)
+{
+    NGSB_REQUIRE(ctx && buf && out, "ngsb_csr_create_from_archive: NULL argument");
+    NGSB_REQUIRE(kind_valid(kind), "ngsb_csr_create_from_archive: bad kind %d", kind);
+    NGSB_REQUIRE(bytes >= 48, "ngsb_csr_create_from_archive: truncated archive");
+    const char *p = (const char *)buf;
+    auto get = [&]() { uint64_t v; memcpy(&v, p, 8); p += 8; return v; };
+    const uint64_t h = get(), w = get(), nnz = get(), n1 = get();
+    const size_t ms = kind_matscalars(kind);
+    NGSB_REQUIRE(n1 == h + 1 && bytes == archive_bytes(h, nnz, ms), "ngsb_csr_create_from_archive: %zu bytes do not hold a %llu x %llu matrix with %llu entries of kind %d",
+                 bytes, (unsigned long long)h, (unsigned long long)w, (unsigned long long)nnz, kind);
+    std::vector<uint64_t> rp(h + 1);
+    memcpy(rp.data(), p, 8 * (h + 1)); p += 8 * (h + 1);
+    NGSB_REQUIRE(get() == nnz, "ngsb_csr_create_from_archive: column count does not match nze");
+    std::vector<int32_t> col(nnz);
+    memcpy(col.data(), p, 4 * nnz); p += 4 * nnz;
+    NGSB_REQUIRE(get() == nnz, "ngsb_csr_create_from_archive: value count does not match nze");
+    std::vector<double> val(nnz * ms);
+    memcpy(val.data(), p, 8 * ms * nnz);
+    return ngsb_csr_create(ctx, h, w, nnz, rp.data(), col.data(), val.data(), kind, out);
+}

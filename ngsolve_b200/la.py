@@ -227,6 +227,9 @@ class BaseVector:
         self._host_uptodate = False
         self._dev_uptodate = True
         self._parent = _parent
+        self._views = []            # weak references to live Range() views (aliases of this vector's device storage)
+        if _parent is not None:
+            _parent._views.append(weakref.ref(self))
         if _handle is not None:
             self.handle = _handle
         else:
@@ -269,28 +272,70 @@ class BaseVector:
             raise NgsbError("size of vector = %d scalars != size of array = %d" % (ns.value, a.size))
         check(_capi.lib().ngsb_vec_h2d(self.handle, _np_ptr(a), 0, n.value))
 
-    def UpdateDevice(self):
-        if self._parent is not None:
-            self._parent.UpdateDevice()
+    # Range() views alias the parent's DEVICE storage but keep a host mirror of their own.  Parent and views stay coherent in
+    # both directions (the reference's UnifiedVectorWrapper updates the device copy and invalidates the host copy of the wrapped
+    # vector, ngscuda/unifiedvector.cpp:376-377): before any alias touches the device copy, pending host writes of all aliases
+    # are flushed in program order (ancestors, self, views); a device write through one alias invalidates the others' mirrors.
+    def _ancestors(self):
+        chain, p = [], self._parent
+        while p is not None:
+            chain.append(p)
+            p = p._parent
+        return chain[::-1]                      # root first
+
+    def _descendants(self):
+        out = []
+        self._views = [r for r in self._views if r() is not None]
+        for r in self._views:
+            v = r()
+            if v is not None:
+                out.append(v)
+                out.extend(v._descendants())
+        return out
+
+    def __del__(self):
+        # a dying view must not lose host writes that never reached the shared device storage
+        try:
+            if self._parent is not None and not self._dev_uptodate and self._host is not None:
+                self._flush_all(True)
+        except Exception:
+            pass
+
+    def _flush_own(self):
         if not self._dev_uptodate:
             self._upload(self._host)
             self._dev_uptodate = True
+
+    def _flush_all(self, own=True):
+        for a in self._ancestors():
+            a._flush_own()
+        if own:
+            self._flush_own()
+        for d in self._descendants():
+            d._flush_own()
+
+    def _invalidate_others_host(self):
+        for a in self._ancestors() + self._descendants():
+            a._host_uptodate = False
+
+    def UpdateDevice(self):
+        self._flush_all(True)
 
     def UpdateHost(self):
         if self._host is None:
             self._host = np.zeros(self.size * self.entrysize, dtype=self._dtype())
             self._host_uptodate = False
+        self._flush_all(False)
         if not self._host_uptodate:
-            self.UpdateDevice()
+            self._flush_own()
             check(_capi.lib().ngsb_vec_d2h(self.handle, _np_ptr(self._host), 0, self.size))
             self._host_uptodate = True
 
     def _dev_write(self):
         """about to be written on the device"""
-        self.UpdateDevice()
+        self._flush_all(True)
         self._host_uptodate = False
-        if self._parent is not None:
-            self._parent._host_uptodate = False
+        self._invalidate_others_host()
 
     def _dev_read(self):
         self.UpdateDevice()
@@ -307,6 +352,7 @@ class BaseVector:
         def NumPy(self):
             v = self.vec
             v.UpdateHost()
+            v._invalidate_others_host()  # ... and the aliases' mirrors go stale with it
             v._dev_uptodate = False      # non-const FVDouble(): the host copy may be written
             return v._host.reshape(-1, 3) if v.entrysize == 3 else v._host
 
@@ -342,9 +388,8 @@ class BaseVector:
         return BaseVector(None, ctx=self.ctx, _handle=h, _parent=self)
 
     def SetScalar(self, s):
-        self._host_uptodate, self._dev_uptodate = False, True
-        if self._parent is not None:
-            self._dev_write()
+        self._dev_uptodate = True            # whatever the host mirror held is overwritten as a whole
+        self._dev_write()
         check(_capi.lib().ngsb_vec_set_scalar(self.handle, scal2(s)))
         return self
 
@@ -874,6 +919,23 @@ class DevSparseMatrix(BaseMatrix):
         h = C.c_void_p()
         check(_capi.lib().ngsb_csr_reorder(self.handle, _np_ptr(p), C.byref(h)))
         return DevSparseMatrix(None, ctx=self.ctx, _handle=h)
+
+    def Archive(self):
+        """the bytes SparseMatrix<TM>::DoArchive writes into a BinaryOutArchive (linalg/sparsematrix_impl.hpp:443-452)"""
+        n = C.c_size_t()
+        check(_capi.lib().ngsb_csr_archive_size(self.handle, C.byref(n)))
+        buf = np.empty(n.value, dtype=np.uint8)
+        check(_capi.lib().ngsb_csr_archive_write(self.handle, _np_ptr(buf), n.value))
+        return buf
+
+    @staticmethod
+    def FromArchive(data, kind=REAL, ctx=None):
+        """device matrix from such bytes (kind: REAL, COMPLEX or BLOCK3 -- the archive does not name its entry type)"""
+        ctx = ctx or default_context()
+        buf = np.ascontiguousarray(np.frombuffer(bytes(data), dtype=np.uint8))
+        h = C.c_void_p()
+        check(_capi.lib().ngsb_csr_create_from_archive(ctx.handle, _np_ptr(buf), len(buf), kind, C.byref(h)))
+        return DevSparseMatrix(None, ctx=ctx, _handle=h)
 
     def Memory(self):
         """(bytes of CSR arrays + tables resident, bytes of the SELL copy, CSR column/value arrays resident?)"""

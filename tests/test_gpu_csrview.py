@@ -97,3 +97,18 @@ def test_transpose_and_reorder_after_release(la, released):
     ref = orc.Csr(g["rowptr"], g["col"], g["val"], 0).reorder(perm)
     val, col, rowptr = dev.Reorder(perm).CSR()
     assert np.array_equal(rowptr, ref.rowptr) and np.array_equal(col, ref.col) and np.array_equal(val, ref.val)
+
+
+@pytest.mark.parametrize("name,kind", [("real", 0), ("complex", 1), ("block3", 3)])
+def test_archive_wire_format_equals_the_reference(la, name, kind):
+    """SparseMatrix<TM>::DoArchive (linalg/sparsematrix_impl.hpp:443-452): the library writes the bytes the reference's
+    BinaryOutArchive holds for the same matrix, and reads what the reference wrote (tests/golden/make_golden_archive.py)"""
+    g = load_golden("archive_wire")
+    rowptr, col, val, ref = g[name + "_rowptr"], g[name + "_col"], g[name + "_val"], g[name + "_bytes"]
+    dev = la.SparseMatrix(rowptr, col, val, entrysize=3 if kind == 3 else 1).CreateDeviceMatrix()
+    assert np.array_equal(dev.Archive(), ref)
+    back = la.DevSparseMatrix.FromArchive(ref.tobytes(), kind=kind)
+    v2, c2, r2 = back.CSR()
+    assert np.array_equal(r2, rowptr) and np.array_equal(c2, col) and np.array_equal(v2.reshape(-1), np.asarray(val).reshape(-1))
+    with pytest.raises(la.NgsbError):
+        la.DevSparseMatrix.FromArchive(ref.tobytes()[:-8], kind=kind)

@@ -396,6 +396,30 @@ def test_host_device_coherence(la):
     assert w.InnerProduct(w) == pytest.approx(49.0 + float(np.sum((2.0 * np.arange(1, 1000.0)) ** 2)), rel=1e-14)
 
 
+def test_range_views_and_parent_stay_coherent_both_ways(la):
+    """Range() views alias the parent's device storage (ngscuda/unifiedvector.cpp:363-405): device and host writes through either
+    alias are seen by the other, whichever side (host mirror / device) it is read from"""
+    n, h = 1000, 400
+    v = la.UnifiedVector(n)
+    v.FV().NumPy()[:] = np.arange(float(n))
+    view = v.Range(0, h)
+    view.data = 2.0 * view                                   # device write through the view ...
+    assert np.array_equal(v.FV().NumPy()[:h], 2.0 * np.arange(float(h))) and v.FV().NumPy()[h] == float(h)   # ... parent's host side
+    v.FV().NumPy()[:] = 1.0                                  # host write to the parent ...
+    assert view.Norm() ** 2 == pytest.approx(h, rel=1e-14)   # ... device read through the view
+    view.FV().NumPy()[:] = 3.0                               # host write through the view ...
+    assert v.InnerProduct(v) == pytest.approx(9.0 * h + (n - h), rel=1e-14)     # ... parent on the device
+    v.data = 5.0 * v                                         # device write to the parent ...
+    assert np.array_equal(view.FV().NumPy(), np.full(h, 15.0))                   # ... view's host side
+    v.SetScalar(2.0)
+    assert np.array_equal(view.NumPy(), np.full(h, 2.0))
+    inner = view.Range(10, 20)                               # a view of a view
+    inner.FV().NumPy()[:] = -1.0
+    assert v.NumPy()[9:21].tolist() == [2.0] + [-1.0] * 10 + [2.0]
+    del inner, view
+    assert v.Norm() ** 2 == pytest.approx(4.0 * (n - 10) + 10.0, rel=1e-14)
+
+
 def test_cg_solve_host_entry(la):
     g = load_golden("poisson_h1p3")
     dev = host_matrix(la, g).CreateDeviceMatrix()

@@ -82,3 +82,16 @@ def test_rcm_components_and_cutoff():
     cut = A.rcm(max_components=2)[::-1].astype(np.int64)
     assert np.array_equal(cut[:57], order[:57])
     assert np.array_equal(cut[57:], np.arange(57, n))
+
+
+def test_archive_wire_layout_of_the_reference():
+    """SparseMatrix<TM>::DoArchive into a BinaryOutArchive (linalg/sparsematrix_impl.hpp:443-452), restated: size_t size, width,
+    nze; Array<size_t> firsti; Array<int> colnr; Array<TM> data -- each array as size_t count + raw elements"""
+    import struct
+    g = load_golden("archive_wire")
+    for name in ("real", "complex", "block3"):
+        rp, col, val = g[name + "_rowptr"], g[name + "_col"], g[name + "_val"]
+        n, nnz = len(rp) - 1, len(col)
+        exp = (struct.pack("<QQQ", n, n, nnz) + struct.pack("<Q", n + 1) + rp.tobytes() + struct.pack("<Q", nnz) + col.tobytes()
+               + struct.pack("<Q", nnz) + np.ascontiguousarray(val).view(np.float64).tobytes())
+        assert exp == g[name + "_bytes"].tobytes()
