@@ -85,6 +85,8 @@ struct ngsb_ctx {
     long sell_c16_all = 0;       // the same for complex and 3x3-block matrices (18.1 instead of 20, 74.1 instead of 76 bytes per entry)
     long spmv_tile = 0, spmv_ncw = 0, spmv_stages = 0, spmv_subwarp = 0;   // 0 = default; read when a matrix is created
     long cg_persistent = -1;     // real Jacobi-PCG as one persistent cooperative kernel: -1 automatic (< 4 M rows), 0 off, 1 on
+    long gmres_orth = 1;         // GMRES orthogonalisation: 1 = V^T w in one batched reduction + triangular solve (2 (j+1) vector passes per
+                                 // step, same coefficients as MGS in exact arithmetic), 0 = the reference's serial modified Gram-Schmidt
     long cg_stream_hints = 0;    // CG update kernel: streaming loads of u, d, As, diagonal and evict-first stores of u, d (A/B)
     long cg_chunked = 0;         // CG update kernel: contiguous chunk per CTA instead of the grid-stride split (A/B)
     long cg_fold_u = 0;          // CG: `u += al s` in the direction kernel instead of the update kernel (10 vector passes, not 11)

@@ -878,6 +878,183 @@ __global__ void __launch_bounds__(256) gmres_update_kernel(double *__restrict__ 
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// GMRES, orthogonalisation with ONE batched reduction per step (option gmres_orth = 1)
+//
+// The reference's loop (cg.cpp:927-932) is modified Gram-Schmidt: h_i = <v_i, w>, w -= h_i v_i, one after the other -- j+1
+// dependent reductions and, however the two operations are fused, two reads of every v_i plus a read and a write of w per
+// projection (4 (j+1) + O(1) vector passes per step).  MGS applies (I - v_j v_j^T) ... (I - v_0 v_0^T) to w; written out,
+// its coefficients solve the unit lower triangular system
+//      (I + L) h = V^T w,      L_ik = <v_i, v_k>  (k < i),
+// so the same h -- identical in exact arithmetic, and with the same O(eps * kappa) loss of orthogonality, since the
+// triangular solve is carried out exactly instead of being truncated -- comes from
+//   pass 1:  V^T w together with the new row of L (<v_k, v_j>, k < j): every v_k is read ONCE for both dots, the per-CTA
+//            partials are summed in CTA order by the finish kernel (bitwise reproducible), which also runs the forward
+//            substitution and stores H(0..j, j);
+//   pass 2:  w -= sum_k h_k v_k in ascending k (each v_k read once, w read and written once) fused with <w, w>.
+// That is 2 (j+1) + O(1) passes and two reductions per step, the byte model SURVEY 8(d) states for GMRES.
+// All inner products are the reference's bilinear ones (no conjugation: GMRESSolver<Complex> uses S_InnerProduct).
+// ------------------------------------------------------------------------------------------
+__global__ void gmres_set_ptr_kernel(const double **tab, int idx, const double *p) { tab[idx] = p; }
+
+// pass 1, one tile of T basis vectors: out[blockIdx.x][32] = per-CTA partials of (<v_k, w>, <v_k, v_j>), k = k0 .. k0+nk-1
+template <bool CPLX>
+__global__ void __launch_bounds__(256, CPLX ? 2 : 1) gmres_dots_kernel(const double *const *__restrict__ vtab, int k0, int nk, int jlast,
+                                                        const double *__restrict__ w, uint64_t nscal, const GmresState *st,
+                                                        double *__restrict__ out)
+{
+    constexpr int T = CPLX ? 8 : 16;          // T * (CPLX ? 4 : 2) = 32 accumulators per thread
+    if (st->done) return;
+    const double *p[T];
+#pragma unroll
+    for (int t = 0; t < T; t++) p[t] = vtab[k0 + (t < nk ? t : nk - 1)];     // short tile: repeat the last vector (same lines, L1 hits)
+    const double *vj = vtab[jlast];
+    double acc[32];
+#pragma unroll
+    for (int i = 0; i < 32; i++) acc[i] = 0.0;
+    const uint64_t ne = (nscal + 1) >> 1;       // pairs of doubles (one complex entry, or two real ones)
+    const uint64_t stride = (uint64_t)gridDim.x * 256;
+    for (uint64_t e = (uint64_t)blockIdx.x * 256 + threadIdx.x; e < ne; e += stride) {
+        double2 a, b, v[T];
+        if (2 * e + 1 < nscal) {
+            a = *reinterpret_cast<const double2 *>(w + 2 * e);
+            b = *reinterpret_cast<const double2 *>(vj + 2 * e);
+#pragma unroll
+            for (int t = 0; t < T; t++) v[t] = *reinterpret_cast<const double2 *>(p[t] + 2 * e);
+        } else {                                 // odd real length: the last entry alone
+            a = make_double2(w[2 * e], 0.0);
+            b = make_double2(vj[2 * e], 0.0);
+#pragma unroll
+            for (int t = 0; t < T; t++) v[t] = make_double2(p[t][2 * e], 0.0);
+        }
+#pragma unroll
+        for (int t = 0; t < T; t++) {
+            if (CPLX) {
+                acc[4 * t + 0] = fma(-v[t].y, a.y, fma(v[t].x, a.x, acc[4 * t + 0]));
+                acc[4 * t + 1] = fma(v[t].y, a.x, fma(v[t].x, a.y, acc[4 * t + 1]));
+                acc[4 * t + 2] = fma(-v[t].y, b.y, fma(v[t].x, b.x, acc[4 * t + 2]));
+                acc[4 * t + 3] = fma(v[t].y, b.x, fma(v[t].x, b.y, acc[4 * t + 3]));
+            } else {
+                acc[2 * t + 0] = fma(v[t].x, a.x, fma(v[t].y, a.y, acc[2 * t + 0]));
+                acc[2 * t + 1] = fma(v[t].x, b.x, fma(v[t].y, b.y, acc[2 * t + 1]));
+            }
+        }
+    }
+    __shared__ double red[8][32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    double mine = 0.0;
+#pragma unroll
+    for (int i = 0; i < 32; i++) {
+        const double s = warp_sum_k(acc[i]);
+        if (lane == i) mine = s;                 // lane i keeps accumulator i
+    }
+    red[wid][lane] = mine;
+    __syncthreads();
+    if (wid == 0) {
+        double s = 0.0;
+#pragma unroll
+        for (int q = 0; q < 8; q++) s += red[q][lane];
+        out[(size_t)blockIdx.x * 32 + lane] = s;
+    }
+}
+
+// one CTA, blockDim >= nv: sums the partials of all tiles in CTA order, stores row j of L, solves (I + L) h = V^T w by forward
+// substitution (thread k owns h_k; the subtractions run in ascending i, the order of the serial loop) and writes H(0..j, j)
+__global__ void __launch_bounds__(1024) gmres_orth_finish_kernel(const GmresState *st, double2 *__restrict__ h, double2 *__restrict__ L,
+                                                               const double *__restrict__ partials, int grid, int nv, int ms, int ldl, int cplx)
+{
+    extern __shared__ double s_raw[];            // [nv][4]: <v_k,w> (re,im), <v_k,v_j> (re,im); then [nv] double2 h
+    if (st->done) return;
+    const int T = cplx ? 8 : 16, VALS = cplx ? 4 : 2;
+    const int j = nv - 1;
+    double2 *s_h = reinterpret_cast<double2 *>(s_raw + 4 * (size_t)nv);
+    for (int idx = threadIdx.x; idx < nv * VALS; idx += blockDim.x) {
+        const int k = idx / VALS, c = idx % VALS, tile = k / T, t = k % T;
+        const double *p = partials + (size_t)tile * grid * 32 + t * VALS + c;
+        double s = 0.0;
+        for (int b = 0; b < grid; b++) s += p[(size_t)b * 32];
+        if (cplx) s_raw[4 * k + c] = s;
+        else { s_raw[4 * k + 2 * c] = s; s_raw[4 * k + 2 * c + 1] = 0.0; }
+    }
+    __syncthreads();
+    const int k = threadIdx.x;
+    if (k < j) L[(size_t)j * ldl + k] = make_double2(s_raw[4 * k + 2], s_raw[4 * k + 3]);
+    double2 mine = k <= j ? make_double2(s_raw[4 * k], s_raw[4 * k + 1]) : make_double2(0.0, 0.0);
+    for (int i = 0; i < j; i++) {
+        if (k == i) s_h[i] = mine;
+        __syncthreads();
+        if (k > i && k <= j) {
+            const double2 l = k == j ? make_double2(s_raw[4 * i + 2], s_raw[4 * i + 3]) : L[(size_t)k * ldl + i];
+            const double2 hi = s_h[i];
+            mine.x -= l.x * hi.x - l.y * hi.y;
+            mine.y -= l.x * hi.y + l.y * hi.x;
+        }
+    }
+    if (k <= j) h[(size_t)k * ms + j] = mine;
+}
+
+// pass 2: w -= sum_k H(k,j) v_k (ascending k), fused with <w, w> -> st->tmp
+template <bool CPLX>
+__global__ void __launch_bounds__(256) gmres_project_kernel(double *__restrict__ w, const double *const *__restrict__ vtab,
+                                                           const double2 *__restrict__ hcol, int ms, int nv, uint64_t nscal,
+                                                           GmresState *st, double *partials, unsigned int *counter)
+{
+    __shared__ double2 s_h[1024];
+    __shared__ const double *s_p[1024];
+    if (st->done) return;
+    for (int k = threadIdx.x; k < nv; k += 256) { s_h[k] = hcol[(size_t)k * ms]; s_p[k] = vtab[k]; }
+    __syncthreads();
+    const uint64_t ne = (nscal + 1) >> 1;
+    const uint64_t stride = (uint64_t)gridDim.x * 256;
+    double ar = 0.0, ai = 0.0;
+    for (uint64_t e = (uint64_t)blockIdx.x * 256 + threadIdx.x; e < ne; e += stride) {
+        const bool full = 2 * e + 1 < nscal;
+        double2 a = full ? *reinterpret_cast<const double2 *>(w + 2 * e) : make_double2(w[2 * e], 0.0);
+        int k = 0;
+        if (full) {
+            for (; k + 8 <= nv; k += 8) {
+                double2 v[8];
+#pragma unroll
+                for (int q = 0; q < 8; q++) v[q] = *reinterpret_cast<const double2 *>(s_p[k + q] + 2 * e);
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    const double2 hk = s_h[k + q];
+                    if (CPLX) {
+                        a.x = fma(hk.y, v[q].y, fma(-hk.x, v[q].x, a.x));
+                        a.y = fma(-hk.y, v[q].x, fma(-hk.x, v[q].y, a.y));
+                    } else {
+                        a.x = fma(-hk.x, v[q].x, a.x);
+                        a.y = fma(-hk.x, v[q].y, a.y);
+                    }
+                }
+            }
+        }
+        for (; k < nv; k++) {
+            const double2 hk = s_h[k];
+            const double2 v = full ? *reinterpret_cast<const double2 *>(s_p[k] + 2 * e) : make_double2(s_p[k][2 * e], 0.0);
+            if (CPLX) {
+                a.x = fma(hk.y, v.y, fma(-hk.x, v.x, a.x));
+                a.y = fma(-hk.y, v.x, fma(-hk.x, v.y, a.y));
+            } else {
+                a.x = fma(-hk.x, v.x, a.x);
+                a.y = fma(-hk.x, v.y, a.y);
+            }
+        }
+        if (full) *reinterpret_cast<double2 *>(w + 2 * e) = a;
+        else w[2 * e] = a.x;
+        if (CPLX) {
+            ar += a.x * a.x - a.y * a.y;
+            ai += a.x * a.y + a.y * a.x;
+        } else ar = fma(a.x, a.x, fma(a.y, a.y, ar));
+    }
+    double2 total;
+    if (grid_finish(ar, ai, partials, counter, &total)) {
+        st->tmp[0] = total.x;
+        st->tmp[1] = total.y;
+    }
+}
+
 } // namespace ngsb
 
 using namespace ngsb;
@@ -977,6 +1154,9 @@ int ngsb::gmres_solve_impl(const ngsb_csr *A, const ngsb_jacobi *C, const ngsb_v
     GmresState *d_st = nullptr;
     double2 *d_h = nullptr, *d_gam = nullptr, *d_ci = nullptr, *d_si = nullptr, *d_y = nullptr;
     double *d_hist = nullptr, *d_scale = nullptr;
+    const double **d_vtab = nullptr;      // one-reduction orthogonalisation: table of the basis vectors, L, per-CTA partials
+    double2 *d_L = nullptr;
+    double *d_dotp = nullptr;
     std::vector<double *> vi, chunks;     // basis vectors live in chunks of up to 8 (one cudaMalloc = one device sync)
     double *av = nullptr, *w = nullptr, *r = nullptr;
     int rc = NGSB_OK;
@@ -984,6 +1164,7 @@ int ngsb::gmres_solve_impl(const ngsb_csr *A, const ngsb_jacobi *C, const ngsb_v
     auto cleanup = [&]() {
         cudaStreamSynchronize(ctx->stream);
         cudaFree(d_st); cudaFree(d_h); cudaFree(d_gam); cudaFree(d_ci); cudaFree(d_si); cudaFree(d_y); cudaFree(d_hist); cudaFree(d_scale);
+        cudaFree(d_vtab); cudaFree(d_L); cudaFree(d_dotp);
         // the big buffers come from the stream-ordered pool: the next solve gets them back without mapping memory again
         for (auto p : chunks) cudaFreeAsync(p, ctx->stream);
         if (av) cudaFreeAsync(av, ctx->stream);
@@ -1014,6 +1195,22 @@ int ngsb::gmres_solve_impl(const ngsb_csr *A, const ngsb_jacobi *C, const ngsb_v
     GM_CUDA(cudaMemsetAsync(d_y, 0, sizeof(double2) * (ms + 2), ctx->stream));
     GM_CUDA(cudaMalloc(&d_hist, sizeof(double) * (hist_cap + 1)));
     GM_CUDA(cudaMalloc(&d_scale, sizeof(double) * 2));
+    // gmres_orth = 1: V^T w in one batched reduction (see gmres_dots_kernel).  The distributed solve keeps the serial form
+    // (its reductions travel as single (re,im) pairs), and so do Krylov spaces beyond the finish kernel's block size.
+    const bool batched = ctx->gmres_orth == 1 && !dist && ms + 1 <= 1024;
+    const int tile = cplx ? 8 : 16;
+    int dgrid = 1;
+    if (batched) {
+        int per_sm = 1;
+        if (cplx) GM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gmres_dots_kernel<true>, 256, 0));
+        else GM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gmres_dots_kernel<false>, 256, 0));
+        dgrid = ctx->sm_count * std::max(1, std::min(per_sm, 4));
+        const uint64_t need = (((uint64_t)(A->h * kind_scalars(A->kind)) / 2 + 256) / 256);
+        if ((uint64_t)dgrid > need) dgrid = (int)std::max<uint64_t>(1, need);
+        GM_CUDA(cudaMalloc(&d_vtab, sizeof(double *) * (size_t)(ms + 2)));
+        GM_CUDA(cudaMalloc(&d_L, sizeof(double2) * (size_t)(ms + 1) * (ms + 1)));
+        GM_CUDA(cudaMalloc(&d_dotp, sizeof(double) * 32 * (size_t)dgrid * ((ms + tile) / tile)));
+    }
     const size_t vbytes = (nscal ? nscal : 2) * sizeof(double);
     {
         // keep up to a fifth of the device memory in the default pool between solves (cudaMalloc/cudaFree of the multi-GB
@@ -1101,6 +1298,7 @@ int ngsb::gmres_solve_impl(const ngsb_csr *A, const ngsb_jacobi *C, const ngsb_v
         double *v0 = nullptr;
         GM_CUDA(new_basis_vector(&v0));
         vi.push_back(v0);
+        if (batched) gmres_set_ptr_kernel<<<1, 1, 0, ctx->stream>>>(d_vtab, 0, v0);
         GM_TRY(launch_axpby_dev(ctx, v0, r, N, d_st_scale, cplx, false, false));
     }
 
@@ -1125,13 +1323,33 @@ int ngsb::gmres_solve_impl(const ngsb_csr *A, const ngsb_jacobi *C, const ngsb_v
         GM_TRY(spmv(v, C ? av : w));
         GM_TRY(cumulate(C ? av : w));
         if (C) GM_TRY(jacobi_apply(C, 1.0, 0.0, av, w, false));
-        // MGS: h(i,j) = <v_i, w>; w -= h(i,j) v_i  (projection i fused with inner product i+1)
-        for (int i = 0; i <= j; i++) {
-            GM_TRY(mgs(i > 0 ? vi[i - 1] : nullptr, i > 0 ? d_h + (size_t)(i - 1) * ms + j : nullptr, vi[i], 0));
-            SpanGuard g(ctx, KC_OTHER);
-            gmres_store_h_kernel<<<1, 1, 0, ctx->stream>>>(d_st, d_h, ms, i, R);
+        if (batched) {
+            const int nv = j + 1;
+            for (int k0 = 0, t = 0; k0 < nv; k0 += tile, t++) {
+                SpanGuard g(ctx, KC_VEC);
+                const int nk = std::min(tile, nv - k0);
+                double *out = d_dotp + (size_t)t * dgrid * 32;
+                if (cplx) gmres_dots_kernel<true><<<dgrid, 256, 0, ctx->stream>>>(d_vtab, k0, nk, j, w, nscal, d_st, out);
+                else gmres_dots_kernel<false><<<dgrid, 256, 0, ctx->stream>>>(d_vtab, k0, nk, j, w, nscal, d_st, out);
+            }
+            {
+                SpanGuard g(ctx, KC_OTHER);
+                const int bs = std::max(64, (nv + 31) & ~31);
+                gmres_orth_finish_kernel<<<1, bs, (size_t)nv * 48, ctx->stream>>>(d_st, d_h, d_L, d_dotp, dgrid, nv, ms, ms + 1, cplx ? 1 : 0);
+            }
+            SpanGuard g(ctx, KC_VEC);
+            if (cplx) gmres_project_kernel<true><<<rgrid, 256, 0, ctx->stream>>>(w, d_vtab, d_h + j, ms, nv, nscal, d_st, ctx->d_partials, ctx->d_counter);
+            else gmres_project_kernel<false><<<rgrid, 256, 0, ctx->stream>>>(w, d_vtab, d_h + j, ms, nv, nscal, d_st, ctx->d_partials, ctx->d_counter);
+            GM_CUDA(cudaGetLastError());
+        } else {
+            // MGS: h(i,j) = <v_i, w>; w -= h(i,j) v_i  (projection i fused with inner product i+1)
+            for (int i = 0; i <= j; i++) {
+                GM_TRY(mgs(i > 0 ? vi[i - 1] : nullptr, i > 0 ? d_h + (size_t)(i - 1) * ms + j : nullptr, vi[i], 0));
+                SpanGuard g(ctx, KC_OTHER);
+                gmres_store_h_kernel<<<1, 1, 0, ctx->stream>>>(d_st, d_h, ms, i, R);
+            }
+            GM_TRY(mgs(vi[j], d_h + (size_t)j * ms + j, nullptr, 1));       // last projection + <w,w>
         }
-        GM_TRY(mgs(vi[j], d_h + (size_t)j * ms + j, nullptr, 1));       // last projection + <w,w>
         {
             SpanGuard g(ctx, KC_OTHER);
             gmres_givens_kernel<<<1, 1, 0, ctx->stream>>>(d_st, d_h, d_gam, d_ci, d_si, ms, d_hist, R);
@@ -1140,6 +1358,7 @@ int ngsb::gmres_solve_impl(const ngsb_csr *A, const ngsb_jacobi *C, const ngsb_v
         double *vn = nullptr;
         GM_CUDA(new_basis_vector(&vn));
         vi.push_back(vn);
+        if (batched) gmres_set_ptr_kernel<<<1, 1, 0, ctx->stream>>>(d_vtab, (int)vi.size() - 1, vn);
         GM_TRY(launch_axpby_dev(ctx, vn, w, N, d_st_scale, cplx, false, false));
         GM_CUDA(cudaMemcpyAsync(&slot[enq & 1], d_st, sizeof(GmresState), cudaMemcpyDeviceToHost, ctx->stream));
         GM_CUDA(cudaEventRecord(ev[enq & 1], ctx->stream));

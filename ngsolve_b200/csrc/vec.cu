@@ -558,6 +558,7 @@ extern "C" int ngsb_ctx_set_option(ngsb_ctx *ctx, const char *name, long value)
     else if (!strcmp(name, "reorder_slot_order")) { NGSB_REQUIRE(value == 0 || value == 1, "reorder_slot_order must be 0 or 1"); ctx->reorder_slot_order = value; }
     else if (!strcmp(name, "reorder_min_rows")) { NGSB_REQUIRE(value >= 0, "reorder_min_rows must be >= 0"); ctx->reorder_min_rows = value; }
     else if (!strcmp(name, "cg_persistent")) { NGSB_REQUIRE(value >= -1 && value <= 1, "cg_persistent must be -1 (automatic), 0 or 1"); ctx->cg_persistent = value; }
+    else if (!strcmp(name, "gmres_orth")) { NGSB_REQUIRE(value == 0 || value == 1, "gmres_orth must be 0 (serial MGS) or 1 (one batched reduction)"); ctx->gmres_orth = value; }
     else if (!strcmp(name, "cg_stream_hints")) { NGSB_REQUIRE(value == 0 || value == 1, "cg_stream_hints must be 0 or 1"); ctx->cg_stream_hints = value; }
     else if (!strcmp(name, "cg_chunked")) { NGSB_REQUIRE(value == 0 || value == 1, "cg_chunked must be 0 or 1"); ctx->cg_chunked = value; }
     else if (!strcmp(name, "cg_fold_u")) { NGSB_REQUIRE(value == 0 || value == 1, "cg_fold_u must be 0 or 1"); ctx->cg_fold_u = value; }

@@ -205,17 +205,52 @@ def test_cg_op_by_op_paths(la, name):
     assert relerr(up.NumPy().reshape(-1), g["cg_u"]) <= 1e-6
 
 
+@pytest.mark.parametrize("orth", [1, 0], ids=["batched", "serial-mgs"])
 @pytest.mark.parametrize("name", ["poisson_h1p3", "helmholtz_h1p4_complex", "shifted_laplace_complex", "square_h1p4_testsolvers"])
-def test_gmres_matches_reference(la, name):
+def test_gmres_matches_reference(la, name, orth):
+    """GMRESSolver::Mult (linalg/cg.cpp:854-1022) against the reference's steps and solution, with the orthogonalisation as one
+    batched reduction (default) and as the reference's serial modified Gram-Schmidt loop (cg.cpp:927-932)."""
     g = load_golden(name)
     A = host_matrix(la, g)
     dev = A.CreateDeviceMatrix()
     jac = dev.CreateSmoother(la.BitArray(g["freebits"]))
     f = vec(la, g, g["f"])
-    inv = la.GMRESSolver(dev, jac, precision=float(g["gmres_prec"]), maxsteps=int(g["gmres_maxsteps"]))
-    x = (inv * f).Evaluate()
+    dev.ctx.set_option("gmres_orth", orth)
+    try:
+        inv = la.GMRESSolver(dev, jac, precision=float(g["gmres_prec"]), maxsteps=int(g["gmres_maxsteps"]))
+        x = (inv * f).Evaluate()
+    finally:
+        dev.ctx.set_option("gmres_orth", 1)
     assert abs(inv.GetSteps() - int(g["gmres_steps"])) <= 2, (inv.GetSteps(), int(g["gmres_steps"]))
     assert relerr(x.NumPy().reshape(-1), g["gmres_u"]) <= 1e-6
+
+
+@pytest.mark.parametrize("name,maxsteps", [("poisson_h1p3", 200), ("helmholtz_h1p4_complex", 200), ("elasticity_h1p4_dim3", 300),
+                                            ("square_h1p4_testsolvers", 7), ("shifted_laplace_complex", 17)])
+def test_gmres_batched_orthogonalisation_follows_the_serial_loop(la, name, maxsteps):
+    """(I + L) h = V^T w gives the coefficients of modified Gram-Schmidt: same step count (also when maxsteps cuts the solve
+    short, one tile boundary is 8 complex / 16 real vectors), residual history to 1e-6, solution to 1e-8; twice the same bits."""
+    g = load_golden(name)
+    A = host_matrix(la, g)
+    dev = A.CreateDeviceMatrix()
+    jac = dev.CreateSmoother(la.BitArray(g["freebits"]))
+    f = vec(la, g, g["f"])
+    out = {}
+    try:
+        for orth in (0, 1, 1):
+            dev.ctx.set_option("gmres_orth", orth)
+            inv = la.GMRESSolver(dev, jac, precision=1e-9, maxsteps=maxsteps)
+            x = (inv * f).Evaluate()
+            out.setdefault(orth, []).append((inv.GetSteps(), inv.history.copy(), x.NumPy().reshape(-1).copy()))
+    finally:
+        dev.ctx.set_option("gmres_orth", 1)
+    (s0, h0, x0), = out[0]
+    (s1, h1, x1), (s2, h2, x2) = out[1]
+    assert s1 == s2 and np.array_equal(h1, h2) and np.array_equal(x1, x2)
+    assert abs(s0 - s1) <= 1, (s0, s1)
+    m = min(len(h0), len(h1))
+    assert m >= min(maxsteps, 5) and np.allclose(h0[:m], h1[:m], rtol=1e-6, atol=1e-14 * h0[0])
+    assert relerr(x1, x0) <= 1e-8
 
 
 def test_python_gmres_solver(la):

@@ -156,12 +156,19 @@ for cfg in args.configs:
     if cfg == "c5":
         K = args.gmres_steps
         inv = la.GMRESSolver(dev, jd, precision=1e-30, maxsteps=K)
-        inv.Mult(fv, uv)
-        ctx.sync()
-        t1 = time.perf_counter()
-        inv.Mult(fv, uv)
-        ctx.sync()
-        dt = time.perf_counter() - t1
+        ab = {}
+        for orth in (0, 1):           # the reference's serial modified Gram-Schmidt loop, then the one-reduction form (default)
+            ctx.set_option("gmres_orth", orth)
+            inv.Mult(fv, uv)
+            ctx.sync()
+            t1 = time.perf_counter()
+            inv.Mult(fv, uv)
+            ctx.sync()
+            dt = time.perf_counter() - t1
+            ab[orth] = dict(steps=inv.GetSteps(), steps_per_s=inv.GetSteps() / dt, last_residual=float(inv.history[-1]),
+                            u_norm=float(np.linalg.norm(uv.NumPy())))
+            log(cfg, "gmres_orth", orth, ab[orth])
+        out["gmres_orth_ab"] = ab
         steps = inv.GetSteps()
         # SURVEY 8d byte model of step j: B_spmv + 3 N S + (2 (j+1) + 4) N S, summed over the steps
         bytes_model = sum(b_alg + 3 * n * S + (2 * (j + 1) + 4) * n * S for j in range(steps))
