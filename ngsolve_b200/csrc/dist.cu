@@ -94,6 +94,8 @@ static const size_t MB_SLOTS = 0;                 // PeerSlot[2][NGSB_MAX_RANKS]
 static const size_t MB_SEQ = 4096;                // unsigned long long
 static const size_t MB_ERR = 4096 + 64;           // int
 static const size_t MB_MAGIC = 8192;              // unsigned long long, checked through the mapping
+static const size_t MB_VEC = 65536;               // double[2][NGSB_MAX_RANKS][NGSB_PEER_VEC_LEN]: vector all-reduce area (1 MiB)
+static_assert(MB_VEC + 2 * NGSB_MAX_RANKS * NGSB_PEER_VEC_LEN * sizeof(double) <= (2u << 20), "vector area must fit the mailbox");
 static const size_t MB_BYTES = 2u << 20;          // own 2 MiB block: the IPC handle maps exactly this allocation
 // halo block layout
 static const size_t HB_FLAGS = 0;                 // unsigned long long[2][NGSB_MAX_RANKS]
@@ -513,6 +515,8 @@ static int comm_setup_p2p(ngsb_comm *c)
     R.err = (int *)(c->mailbox + MB_ERR);
     R.mine = (PeerSlot *)(c->mailbox + MB_SLOTS);
     for (int p = 0; p < c->nranks; p++) R.theirs[p] = (PeerSlot *)(c->peer_mailbox[p] + MB_SLOTS);
+    R.vec_mine = (double *)(c->mailbox + MB_VEC);
+    for (int p = 0; p < c->nranks; p++) R.vec_theirs[p] = (double *)(c->peer_mailbox[p] + MB_VEC);
     c->d_err = R.err;
     NGSB_CUDA(cudaMalloc(&c->d_R, sizeof(PeerReduce)));
     NGSB_CUDA(cudaMemcpy(c->d_R, &R, sizeof(R), cudaMemcpyHostToDevice));

@@ -902,7 +902,7 @@ __global__ void gmres_set_ptr_kernel(const double **tab, int idx, const double *
 template <bool CPLX>
 __global__ void __launch_bounds__(256, CPLX ? 2 : 1) gmres_dots_kernel(const double *const *__restrict__ vtab, int k0, int nk, int jlast,
                                                         const double *__restrict__ w, uint64_t nscal, const GmresState *st,
-                                                        double *__restrict__ out)
+                                                        double *__restrict__ out, const uint8_t *__restrict__ master, unsigned mask_div)
 {
     constexpr int T = CPLX ? 8 : 16;          // T * (CPLX ? 4 : 2) = 32 accumulators per thread
     if (st->done) return;
@@ -927,6 +927,14 @@ __global__ void __launch_bounds__(256, CPLX ? 2 : 1) gmres_dots_kernel(const dou
             b = make_double2(vj[2 * e], 0.0);
 #pragma unroll
             for (int t = 0; t < T; t++) v[t] = make_double2(p[t][2 * e], 0.0);
+        }
+        if (master) {                            // parallel vectors: inner products over the master dofs only
+            if (CPLX) {
+                if (!master[e]) a = b = make_double2(0.0, 0.0);
+            } else {
+                if (!master[(2 * e) / mask_div]) a.x = b.x = 0.0;
+                if (2 * e + 1 < nscal && !master[(2 * e + 1) / mask_div]) a.y = b.y = 0.0;
+            }
         }
 #pragma unroll
         for (int t = 0; t < T; t++) {
@@ -962,7 +970,8 @@ __global__ void __launch_bounds__(256, CPLX ? 2 : 1) gmres_dots_kernel(const dou
 // one CTA, blockDim >= nv: sums the partials of all tiles in CTA order, stores row j of L, solves (I + L) h = V^T w by forward
 // substitution (thread k owns h_k; the subtractions run in ascending i, the order of the serial loop) and writes H(0..j, j)
 __global__ void __launch_bounds__(1024) gmres_orth_finish_kernel(const GmresState *st, double2 *__restrict__ h, double2 *__restrict__ L,
-                                                               const double *__restrict__ partials, int grid, int nv, int ms, int ldl, int cplx)
+                                                               const double *__restrict__ partials, int grid, int nv, int ms, int ldl, int cplx,
+                                                               const PeerReduce *R)
 {
     extern __shared__ double s_raw[];            // [nv][4]: <v_k,w> (re,im), <v_k,v_j> (re,im); then [nv] double2 h
     if (st->done) return;
@@ -978,6 +987,7 @@ __global__ void __launch_bounds__(1024) gmres_orth_finish_kernel(const GmresStat
         else { s_raw[4 * k + 2 * c] = s; s_raw[4 * k + 2 * c + 1] = 0.0; }
     }
     __syncthreads();
+    if (R) pr_allreduce_vec_block(*R, s_raw, 4 * nv);        // distributed: all 2 (j+1) inner products in ONE exchange
     const int k = threadIdx.x;
     if (k < j) L[(size_t)j * ldl + k] = make_double2(s_raw[4 * k + 2], s_raw[4 * k + 3]);
     double2 mine = k <= j ? make_double2(s_raw[4 * k], s_raw[4 * k + 1]) : make_double2(0.0, 0.0);
@@ -998,7 +1008,8 @@ __global__ void __launch_bounds__(1024) gmres_orth_finish_kernel(const GmresStat
 template <bool CPLX>
 __global__ void __launch_bounds__(256) gmres_project_kernel(double *__restrict__ w, const double *const *__restrict__ vtab,
                                                            const double2 *__restrict__ hcol, int ms, int nv, uint64_t nscal,
-                                                           GmresState *st, double *partials, unsigned int *counter)
+                                                           GmresState *st, double *partials, unsigned int *counter,
+                                                           const uint8_t *__restrict__ master, unsigned mask_div)
 {
     __shared__ double2 s_h[1024];
     __shared__ const double *s_p[1024];
@@ -1044,9 +1055,17 @@ __global__ void __launch_bounds__(256) gmres_project_kernel(double *__restrict__
         if (full) *reinterpret_cast<double2 *>(w + 2 * e) = a;
         else w[2 * e] = a.x;
         if (CPLX) {
-            ar += a.x * a.x - a.y * a.y;
-            ai += a.x * a.y + a.y * a.x;
-        } else ar = fma(a.x, a.x, fma(a.y, a.y, ar));
+            if (!master || master[e]) {
+                ar += a.x * a.x - a.y * a.y;
+                ai += a.x * a.y + a.y * a.x;
+            }
+        } else {
+            if (master) {
+                if (!master[(2 * e) / mask_div]) a.x = 0.0;
+                if (full && !master[(2 * e + 1) / mask_div]) a.y = 0.0;
+            }
+            ar = fma(a.x, a.x, fma(a.y, a.y, ar));
+        }
     }
     double2 total;
     if (grid_finish(ar, ai, partials, counter, &total)) {
@@ -1195,9 +1214,10 @@ int ngsb::gmres_solve_impl(const ngsb_csr *A, const ngsb_jacobi *C, const ngsb_v
     GM_CUDA(cudaMemsetAsync(d_y, 0, sizeof(double2) * (ms + 2), ctx->stream));
     GM_CUDA(cudaMalloc(&d_hist, sizeof(double) * (hist_cap + 1)));
     GM_CUDA(cudaMalloc(&d_scale, sizeof(double) * 2));
-    // gmres_orth = 1: V^T w in one batched reduction (see gmres_dots_kernel).  The distributed solve keeps the serial form
-    // (its reductions travel as single (re,im) pairs), and so do Krylov spaces beyond the finish kernel's block size.
-    const bool batched = ctx->gmres_orth == 1 && !dist && ms + 1 <= 1024;
+    // gmres_orth = 1: V^T w in one batched reduction (see gmres_dots_kernel); distributed, the 2 (j+1) sums of a step travel
+    // in one peer-memory exchange.  The NCCL data path keeps the serial form (its reductions are single (re,im) pairs), and
+    // so do Krylov spaces beyond the finish kernel's block size.
+    const bool batched = ctx->gmres_orth == 1 && !(dist && dist->allreduce) && ms + 1 <= 1024 && 4 * (ms + 1) <= NGSB_PEER_VEC_LEN + 4;
     const int tile = cplx ? 8 : 16;
     int dgrid = 1;
     if (batched) {
@@ -1329,17 +1349,17 @@ int ngsb::gmres_solve_impl(const ngsb_csr *A, const ngsb_jacobi *C, const ngsb_v
                 SpanGuard g(ctx, KC_VEC);
                 const int nk = std::min(tile, nv - k0);
                 double *out = d_dotp + (size_t)t * dgrid * 32;
-                if (cplx) gmres_dots_kernel<true><<<dgrid, 256, 0, ctx->stream>>>(d_vtab, k0, nk, j, w, nscal, d_st, out);
-                else gmres_dots_kernel<false><<<dgrid, 256, 0, ctx->stream>>>(d_vtab, k0, nk, j, w, nscal, d_st, out);
+                if (cplx) gmres_dots_kernel<true><<<dgrid, 256, 0, ctx->stream>>>(d_vtab, k0, nk, j, w, nscal, d_st, out, master, mask_div);
+                else gmres_dots_kernel<false><<<dgrid, 256, 0, ctx->stream>>>(d_vtab, k0, nk, j, w, nscal, d_st, out, master, mask_div);
             }
             {
                 SpanGuard g(ctx, KC_OTHER);
                 const int bs = std::max(64, (nv + 31) & ~31);
-                gmres_orth_finish_kernel<<<1, bs, (size_t)nv * 48, ctx->stream>>>(d_st, d_h, d_L, d_dotp, dgrid, nv, ms, ms + 1, cplx ? 1 : 0);
+                gmres_orth_finish_kernel<<<1, bs, (size_t)nv * 48, ctx->stream>>>(d_st, d_h, d_L, d_dotp, dgrid, nv, ms, ms + 1, cplx ? 1 : 0, R);
             }
             SpanGuard g(ctx, KC_VEC);
-            if (cplx) gmres_project_kernel<true><<<rgrid, 256, 0, ctx->stream>>>(w, d_vtab, d_h + j, ms, nv, nscal, d_st, ctx->d_partials, ctx->d_counter);
-            else gmres_project_kernel<false><<<rgrid, 256, 0, ctx->stream>>>(w, d_vtab, d_h + j, ms, nv, nscal, d_st, ctx->d_partials, ctx->d_counter);
+            if (cplx) gmres_project_kernel<true><<<rgrid, 256, 0, ctx->stream>>>(w, d_vtab, d_h + j, ms, nv, nscal, d_st, ctx->d_partials, ctx->d_counter, master, mask_div);
+            else gmres_project_kernel<false><<<rgrid, 256, 0, ctx->stream>>>(w, d_vtab, d_h + j, ms, nv, nscal, d_st, ctx->d_partials, ctx->d_counter, master, mask_div);
             GM_CUDA(cudaGetLastError());
         } else {
             // MGS: h(i,j) = <v_i, w>; w -= h(i,j) v_i  (projection i fused with inner product i+1)

@@ -22,6 +22,7 @@
 #include <stdint.h>
 
 #define NGSB_MAX_RANKS 16
+#define NGSB_PEER_VEC_LEN 4096           // doubles per rank and parity in the vector all-reduce area
 
 struct PeerSlot {
     double v[2];
@@ -35,6 +36,8 @@ struct PeerReduce {
     int *err;                            // local: set to 1 when a wait timed out
     PeerSlot *mine;                      // local mailbox: [2][NGSB_MAX_RANKS]
     PeerSlot *theirs[NGSB_MAX_RANKS];    // theirs[p]: rank p's mailbox (mapped); theirs[rank] == mine
+    double *vec_mine;                    // local vector area: [2][NGSB_MAX_RANKS][NGSB_PEER_VEC_LEN]
+    double *vec_theirs[NGSB_MAX_RANKS];  // the same area of rank p (mapped); vec_theirs[rank] == vec_mine
 };
 
 struct PeerHalo {
@@ -150,6 +153,36 @@ __device__ __forceinline__ double2 pr_wait_sum(const PeerReduce &R)
     }
     *(volatile unsigned long long *)R.seq = s;
     return make_double2(a, b);
+}
+
+// a whole CTA (blockDim >= 32, every thread calls): buf[0..n) <- sum over ranks, n <= NGSB_PEER_VEC_LEN; buf is memory the
+// whole CTA sees (shared or global).  Every rank stores its n values into slot [parity][own rank] of EVERY rank's vector area,
+// publishes them with the flag of a scalar reduction (the stores are fenced before the CTA barrier that precedes the release)
+// and, once all flags are there, sums the nranks copies in its own area in rank order: the same bits on every rank.  Counts as
+// reduction number *seq + 1 like the scalar form, so the two kinds may be mixed freely as long as all ranks issue them in the
+// same order.
+__device__ __forceinline__ void pr_allreduce_vec_block(const PeerReduce &R, double *buf, int n)
+{
+    const unsigned long long s = *(volatile unsigned long long *)R.seq + 1;
+    __syncthreads();                                       // everybody has read seq before warp 0 completes the reduction
+    for (int p = 0; p < R.nranks; p++) {
+        double *dst = R.vec_theirs[p] + ((s & 1) * NGSB_MAX_RANKS + R.rank) * (size_t)NGSB_PEER_VEC_LEN;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) *(volatile double *)&dst[i] = buf[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        pr_push_warp(R, 0.0, 0.0);
+        pr_wait_sum_warp(R);
+    }
+    __syncthreads();
+    const double *src = R.vec_mine + (s & 1) * NGSB_MAX_RANKS * (size_t)NGSB_PEER_VEC_LEN;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        double a = 0.0;
+        for (int p = 0; p < R.nranks; p++) a += *(volatile const double *)&src[p * (size_t)NGSB_PEER_VEC_LEN + i];
+        buf[i] = a;
+    }
+    __syncthreads();
 }
 
 // one thread: buf(re,im) <- sum over ranks

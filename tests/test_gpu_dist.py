@@ -51,6 +51,8 @@ def _worker(rank, world, port, cfg, out):
         ctx.set_option("cg_fold_u", 1)
     if "fused_push" in cfg:
         ctx.set_option("dist_fused_push", cfg["fused_push"])
+    if "gmres_orth" in cfg:
+        ctx.set_option("gmres_orth", cfg["gmres_orth"])
     G = tuple(cfg.get("G", G_DEFAULT))
     boxes = [W.FemBox(n, offset=o, global_n=G, **_box_kw(cfg)) for n, o in W.slab_partition(G, world)]
     box = boxes[rank]
@@ -144,6 +146,17 @@ def test_two_ranks_on_one_gpu_peer_memory(case):
     context switch -> keep the GMRES systems small: step j has j+2 reductions)"""
     extra = dict(G=(6, 5, 8)) if case["solver"] == "gmres" else {}
     _run(dict(case, devices="same", p2p=1, **extra))
+
+
+@pytest.mark.parametrize("case", CASES[4:], ids=IDS[4:])
+def test_two_ranks_gmres_serial_orthogonalisation(case):
+    """option gmres_orth = 0: the reference's loop, j+2 single reductions per step (the default batches them into one exchange)"""
+    _run(dict(case, devices="same", p2p=1, G=(6, 5, 8), gmres_orth=0))
+
+
+def test_three_ranks_gmres_batched_reduction():
+    """the vector all-reduce of the batched orthogonalisation with a middle rank that has two neighbours"""
+    _run(dict(CASES[4], devices="same", p2p=1, G=(5, 4, 9)), world=3)
 
 
 @pytest.mark.parametrize("case", CASES[:3], ids=IDS[:3])

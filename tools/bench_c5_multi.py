@@ -9,6 +9,7 @@ import torch.distributed as dist
 ap = argparse.ArgumentParser()
 ap.add_argument("--m", type=int, default=77)
 ap.add_argument("--steps", type=int, default=40)
+ap.add_argument("--orth", type=int, nargs="+", default=[1], help="gmres_orth modes to time (0 serial MGS, 1 batched)")
 a = ap.parse_args()
 if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
     os.environ["NCCL_DEBUG"] = "WARN"
@@ -51,20 +52,23 @@ def barrier():
     torch.cuda.synchronize()
 
 
-solve()
-barrier()
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record(stream)
-steps = solve()
-e1.record(stream)
-barrier()
-ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
-if world > 1:
-    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-if rank == 0:
-    print(json.dumps({"config": "C5 Helmholtz H1 p4 complex, Jacobi-GMRES (no restart), %d^3 cubes" % a.m, "n_gpus": world, "global_dofs": box.global_ndof,
-                      "rows_per_gpu": A.height, "gmres_steps": steps, "seconds": float(ms.item()) * 1e-3, "steps_per_s": steps / (float(ms.item()) * 1e-3),
-                      "data_path": "peer memory" if world > 1 and pmat.peer_memory else ("single GPU" if world == 1 else "nccl")}), flush=True)
+for orth in a.orth:
+    ctx.set_option("gmres_orth", orth)
+    solve()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    steps = solve()
+    e1.record(stream)
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        print(json.dumps({"config": "C5 Helmholtz H1 p4 complex, Jacobi-GMRES (no restart), %d^3 cubes" % a.m, "n_gpus": world, "global_dofs": box.global_ndof,
+                          "rows_per_gpu": A.height, "gmres_steps": steps, "seconds": float(ms.item()) * 1e-3, "steps_per_s": steps / (float(ms.item()) * 1e-3),
+                          "gmres_orth": orth, "reductions_per_step": "2" if orth else "j+2",
+                          "data_path": "peer memory" if world > 1 and pmat.peer_memory else ("single GPU" if world == 1 else "nccl")}), flush=True)
 if world > 1:
     dist.barrier()
     dist.destroy_process_group()
