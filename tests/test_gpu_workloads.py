@@ -208,6 +208,7 @@ def test_cg_fold_u_is_the_same_solve(kind, stop):
     kw = dict(precision=1e-9, maxsteps=2000) if stop != "maxsteps" else dict(precision=1e-30, maxsteps=37)
     out = []
     try:
+        ctx.set_option("cg_persistent", 0)      # the option belongs to the three-kernel loop (the persistent kernel never folds)
         for fold in (0, 1):
             ctx.set_option("cg_fold_u", fold)
             for batch in ((16,) if stop != "batches" else (1, 5)):      # 1: no CUDA graph, 5: the loop ends inside a batch
@@ -219,6 +220,7 @@ def test_cg_fold_u_is_the_same_solve(kind, stop):
     finally:
         ctx.set_option("cg_fold_u", 0)
         ctx.set_option("cg_batch", 16)
+        ctx.set_option("cg_persistent", -1)
     ref = out[0]
     assert ref[0] > 10
     if stop == "maxsteps":
