@@ -85,7 +85,8 @@ int ngsb_ctx_launch_count(const ngsb_ctx *ctx, uint64_t *count);
  *                        part of V^T V in ONE batched reduction (each v_k read once), H(0..j,j) from the unit triangular system
  *                        (I + L) h = V^T w, then w -= V h in one pass -- the coefficients modified Gram-Schmidt produces (identical in
  *                        exact arithmetic), 2 (j+1) instead of 4 (j+1) vector passes and 2 instead of j+2 reductions per step.
- *                        0: the reference's serial loop (linalg/cg.cpp:927-932).  The distributed solve always uses 0.
+ *                        0: the reference's serial loop (linalg/cg.cpp:927-932).  On parallel vectors (peer-memory data path) the
+ *                        2 (j+1) sums of a step travel in one exchange; the NCCL data path and Krylov spaces beyond 1023 vectors use 0.
  *     "cg_stream_hints"  0/1: the CG update kernel loads u, d, As, diagonal streaming and stores u, d evict-first (default 0; A/B)
  *     "cg_chunked"       0/1: the CG update kernel works on one contiguous chunk per CTA instead of grid-stride (default 0; A/B)
  *     "cg_fold_u"        0/1: the CG direction kernel also does u += al s (10 instead of 11 vector passes per iteration)
