@@ -10,9 +10,12 @@
 // at once when state->done is set, so the host enqueues iterations in batches (optionally
 // as one CUDA graph per batch) and only polls the flag between batches.
 //
-// GMRES: GMRESSolver<IPTYPE>::Mult (linalg/cg.cpp:854-1022): left preconditioning, modified
-// Gram-Schmidt in the reference's order (each projection fused with the next inner product),
-// Givens rotations and the triangular solve in single-thread kernels on the device.
+// GMRES: GMRESSolver<IPTYPE>::Mult (linalg/cg.cpp:854-1022): left preconditioning, Givens
+// rotations and the triangular solve in single-thread kernels on the device.  The
+// orthogonalisation produces the coefficients of the reference's modified Gram-Schmidt loop
+// with one batched reduction per step (gmres_dots_kernel and the comment above it); option
+// gmres_orth = 0 runs the loop in the reference's order, each projection fused with the next
+// inner product.
 #include "krylov.cuh"
 #include "peer.cuh"
 
